@@ -1,0 +1,420 @@
+"""Generate the golden fixtures under tests/golden/ by running the reference's
+own, unedited code through oracle/ref_shim.py.
+
+TEST INFRASTRUCTURE ONLY.  Run in the build container (needs /root/reference):
+
+    python -m oracle.gen_golden            # writes tests/golden/*.npz
+
+The fixtures are what travels to the GPU box (the reference tree does not).
+Each .npz carries a JSON ``meta`` string with the config, the draw mode and the
+reference commit-independent description of how it was made.
+
+Fixture families
+  rollout_philox_*.npz  N envs x T steps with the vector wrapper's auto-reset /
+                        time-limit semantics wrapped around the reference env;
+                        every draw answered from Philox4x32-10 at its address
+                        (oracle/draws.py) - the production draw stream.
+  rollout_mt_*.npz      same, but the reference draws from np.random (MT19937,
+                        np.random.seed(s)) and the recorded draws are stored as
+                        slot-addressed tapes (parity / tape mode).
+  edge_gym.npz          hand-built single-step cases on injected states.
+  window_kat.npz        RNG-free window-observation known answers (W=5,10,21).
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+
+import numpy as np
+
+from . import draws as D
+from . import ref_shim as R
+from .ballenv_oracle import AGENT_MOVES
+
+OUT_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+CFG_DEFAULT = dict(static_obstacles=13, dynamic_obstacles=5, obstacle_speed=[1, 1, 1, 1, 1],
+                   obs_goal_position=['12,122', '123,93', '87,150', '430,440', '230,11'],
+                   time_step_for_change=50, rd_th_obs=60, static_penalty=[1, 1], dynamic_penalty=[4000, 8000])
+
+# config 3 of BASELINE.json ("dense moving obstacles"), SURVEY.md section 8d
+_LATTICE = ['%d,%d' % (x, y) for y in (100, 200, 300, 400) for x in (50, 130, 210, 290, 370, 450)]
+CFG_DENSE = dict(static_obstacles=8, dynamic_obstacles=24, obstacle_speed=[1] * 24,
+                 obs_goal_position=_LATTICE, time_step_for_change=50, rd_th_obs=60,
+                 static_penalty=[1, 1], dynamic_penalty=[4000, 8000])
+
+# small, fast-changing config: exercises goal changes, axis moves and truncation often
+CFG_BUSY = dict(static_obstacles=3, dynamic_obstacles=4, obstacle_speed=[1, 2, 1, 3],
+                obs_goal_position=['40,30', '250,5', '250,60', '460,20'],
+                time_step_for_change=7, rd_th_obs=45, static_penalty=[1, 1], dynamic_penalty=[4000, 8000])
+
+
+def _pack_rows(obs, window):
+    """float obs [4 + W*W] -> (quadrant index, W row bitmasks)."""
+    q = int(np.argmax(obs[:4]))
+    assert obs[:4].sum() == 1.0
+    grid = obs[4:].reshape(window, window)
+    rows = [int(sum(int(grid[r, c]) << c for c in range(window))) for r in range(window)]
+    return q, rows
+
+
+def _action_for(policy, src, g, t, ref):
+    w = src.action_word(g, t)
+    if policy == "random":
+        return D.mulhi(w, 9)
+    # goal seeking with 25 % random moves
+    if D.mulhi(w, 4) == 0:
+        return D.mulhi(D.mullo(w, 4), 9)
+    (ax, ay), (gx, gy) = ref.env.state[0], ref.env.state[1]
+    sx = (gx > ax) - (gx < ax)
+    sy = (gy > ay) - (gy < ay)
+    return AGENT_MOVES.index((sx, sy))
+
+
+def rollout(cfg, n_envs, T, seed, mode, max_steps, windows=(5, 10), g0=0, policies=("random", "seek")):
+    args = R.default_args(**cfg)
+    ks, kd = cfg["static_obstacles"], cfg["dynamic_obstacles"]
+    K = ks + kd
+    act_src = D.PhiloxDraws(seed ^ 0x5EED)
+    if mode == "philox":
+        src = D.PhiloxDraws(seed)
+        refs = [R.ReferenceEnv(args, R.AddressedRouter(src, g0 + i)) for i in range(n_envs)]
+    else:
+        np.random.seed(seed)
+        refs = [R.ReferenceEnv(args, R.MTRouter()) for i in range(n_envs)]
+
+    rec = dict(
+        actions=np.zeros((T, n_envs), np.uint8),
+        agent=np.zeros((T, n_envs, 2), np.float64), goal=np.zeros((T, n_envs, 2), np.float64),
+        dist=np.zeros((T, n_envs), np.float64), total_distance=np.zeros((T, n_envs), np.float64),
+        acc=np.zeros((T, n_envs), np.float64),
+        reward=np.zeros((T, n_envs), np.float64), done=np.zeros((T, n_envs), np.uint8),
+        flags=np.zeros((T, n_envs), np.uint8), ep_len=np.zeros((T, n_envs), np.int32),
+        obst=np.zeros((T, n_envs, K, 2), np.float64),
+        dyn_goal=np.zeros((T, n_envs, kd), np.uint8), dyn_counter=np.zeros((T, n_envs, kd), np.int32),
+        quadrant=np.zeros((T, n_envs), np.uint8),
+    )
+    for w in windows:
+        rec["rows%d" % w] = np.zeros((T, n_envs, w), np.uint32)
+    init = dict(agent=np.zeros((n_envs, 2)), goal=np.zeros((n_envs, 2)), dist=np.zeros(n_envs),
+                total_distance=np.zeros(n_envs), obst=np.zeros((n_envs, K, 2)))
+    for w in windows:
+        init["rows%d" % w] = np.zeros((n_envs, w), np.uint32)
+    init["quadrant"] = np.zeros(n_envs, np.uint8)
+
+    # tape recording (mt mode): per env list of per-episode reset draws and per-step draws
+    A = 8
+    step_val = np.zeros((T, n_envs, kd, 2), np.uint8)
+    step_n = np.zeros((T, n_envs, kd, 2), np.uint8)
+    reset_logs = [[] for _ in range(n_envs)]   # env -> list of episodes -> list of (lo, hi, v)
+
+    def take_reset_log(i):
+        if mode != "mt":
+            return
+        log = refs[i].router.log
+        reset_logs[i].append([(lo, hi, v) for (c, lo, hi, v) in log if c == "reset"])
+        del log[:]
+
+    def take_step_log(i, t):
+        if mode != "mt":
+            return
+        log = refs[i].router.log
+        j = -1
+        second = False
+        for (c, lo, hi, v) in log:
+            assert c == "step" and lo == 0
+            if second:
+                step_val[t, i, j, 1], step_n[t, i, j, 1] = v, hi
+                second = False
+                continue
+            j += 1
+            step_val[t, i, j, 0], step_n[t, i, j, 0] = v, hi
+            if hi == 100 and v >= cfg["rd_th_obs"]:
+                second = True
+        assert j == kd - 1 and not second, (j, kd)
+        del log[:]
+
+    ep_len = [0] * n_envs
+    stats = dict(episodes=0, return_sum=0.0, length_sum=0, goals=0, hits_static=0, hits_dynamic=0,
+                 timeouts=0, steps=0)
+    for i, ref in enumerate(refs):
+        if mode == "mt":
+            del ref.router.log[:]
+        s = ref.reset()
+        take_reset_log(i)
+        init["agent"][i], init["goal"][i], init["dist"][i] = s[0], s[1], s[2]
+        init["total_distance"][i] = ref.env.total_distance
+        init["obst"][i] = np.array([tuple(p) for p in s[3:]], dtype=np.float64).reshape(K, 2)
+        for w in windows:
+            q, rows = _pack_rows(ref.observe(s, w), w)
+            init["rows%d" % w][i] = rows
+            init["quadrant"][i] = q
+
+    for t in range(T):
+        for i, ref in enumerate(refs):
+            a = _action_for(policies[i % len(policies)], act_src, g0 + i, t, ref)
+            rec["actions"][t, i] = a
+            s, r, d, _ = ref.step(AGENT_MOVES[a])
+            take_step_log(i, t)
+            ep_len[i] += 1
+            env = ref.env
+            goal_flag = s[2] < env.threshold_goal
+            hit_idx = next((k for k, p in enumerate(s[3:]) if env.check_overlap(s[0], p)), -1)
+            hit = hit_idx >= 0
+            assert bool(d) == (goal_flag or hit)
+            trunc = max_steps > 0 and ep_len[i] >= max_steps
+            done = bool(d) or trunc
+            f = (1 if goal_flag else 0) | (2 if hit else 0) | (4 if trunc else 0) | (8 if hit_idx >= ks else 0)
+            rec["reward"][t, i], rec["done"][t, i], rec["flags"][t, i] = r, done, f
+            stats["steps"] += 1
+            if done:
+                stats["episodes"] += 1
+                stats["return_sum"] += env.total_reward_accumulated
+                stats["length_sum"] += ep_len[i]
+                stats["goals"] += int(goal_flag)
+                stats["hits_static"] += int(hit and hit_idx < ks)
+                stats["hits_dynamic"] += int(hit_idx >= ks)
+                stats["timeouts"] += int(trunc and not d)
+                s = ref.reset()
+                take_reset_log(i)
+                ep_len[i] = 0
+            rec["agent"][t, i], rec["goal"][t, i], rec["dist"][t, i] = s[0], s[1], s[2]
+            rec["total_distance"][t, i] = env.total_distance
+            rec["acc"][t, i] = env.total_reward_accumulated
+            rec["ep_len"][t, i] = ep_len[i]
+            rec["obst"][t, i] = np.array([tuple(p) for p in s[3:]], dtype=np.float64).reshape(K, 2)
+            for j, o in enumerate(env.obstacle_list[ks:]):
+                rec["dyn_goal"][t, i, j] = env.obstacle_goal_list.index(o.curr_goal)
+                rec["dyn_counter"][t, i, j] = o.curr_counter
+            for w in windows:
+                q, rows = _pack_rows(ref.observe(s, w), w)
+                rec["rows%d" % w][t, i] = rows
+                rec["quadrant"][t, i] = q
+
+    out = {"rec_" + k: v for k, v in rec.items()}
+    out.update({"init_" + k: v for k, v in init.items()})
+    if mode == "mt":
+        E = max(len(x) for x in reset_logs)
+        reset_val = np.zeros((E, n_envs, D.reset_tape_width(ks, kd, A)), np.uint16)
+        for i, eps in enumerate(reset_logs):
+            for e, log in enumerate(eps):
+                vals = [v - lo for (lo, hi, v) in log]
+                reset_val[e, i, 0:4] = vals[0:4]
+                pairs = [(vals[k], vals[k + 1]) for k in range(4, len(vals), 2)]
+                # replay acceptance to slot the pairs: static i attempts, then dynamic
+                gx, gy = vals[0], 480 + vals[1]
+                ax, ay = vals[2], vals[3]
+                p = 0
+                for si in range(ks):
+                    a = 0
+                    while True:
+                        x, y = pairs[p][0], 20 + pairs[p][1]
+                        assert a < A, "raise A"
+                        reset_val[e, i, 4 + (si * A + a) * 2: 4 + (si * A + a) * 2 + 2] = pairs[p]
+                        p += 1
+                        a += 1
+                        rej = (abs(x - ax) < 25 and abs(y - ay) < 15) or (abs(x - gx) < 25 and abs(y - gy) < 15)
+                        if not rej:
+                            break
+                for dj in range(kd):
+                    reset_val[e, i, 4 + 2 * A * ks + 2 * dj: 4 + 2 * A * ks + 2 * dj + 2] = pairs[p]
+                    p += 1
+                assert p == len(pairs)
+        out.update(tape_step_val=step_val, tape_step_n=step_n, tape_reset_val=reset_val)
+    meta = dict(kind="rollout", ruleset="gym", mode=mode, seed=seed, n_envs=n_envs, T=T, g0=g0,
+                max_episode_steps=max_steps, auto_reset=True, windows=list(windows), cfg=cfg,
+                tape_attempts=A, stats=stats, action_seed=seed ^ 0x5EED, policies=list(policies),
+                made_by="oracle/gen_golden.py running /root/reference unedited via oracle/ref_shim.py")
+    out["meta"] = np.array(json.dumps(meta))
+    return out
+
+
+def compress_rollout(out):
+    """Shrink dtypes where the values are integral (checked)."""
+    for k in list(out):
+        v = out[k]
+        if isinstance(v, np.ndarray) and v.dtype == np.float64 and k.split("_", 1)[1] in ("agent", "goal", "obst"):
+            assert np.all(v == np.round(v)) and np.abs(v).max() < 32000
+            out[k] = v.astype(np.int16)
+    return out
+
+
+# --------------------------------------------------------------------------- edge cases
+def edge_cases():
+    """Single-step transitions on injected states (gym ruleset, 2 static + 3
+    dynamic obstacles).  Every case: state, action, tape words -> next state,
+    reward, done, flags, W=5 / W=10 observation."""
+    cfg = dict(static_obstacles=2, dynamic_obstacles=3, obstacle_speed=[1, 2, 1],
+               obs_goal_position=['100,100', '300,300', '50,400'], time_step_for_change=50, rd_th_obs=60,
+               static_penalty=[1, 1], dynamic_penalty=[4000, 8000])
+    args = R.default_args(**cfg)
+    far = [(400, 100), (420, 300)]                 # statics far from everything
+    dfar = [(300, 50), (310, 200), (320, 350)]      # dynamics far from everything
+    W100 = lambda v: D.word_for(v, 100)
+    W9 = lambda v: D.word_for(v, 9)
+    W2 = lambda v: D.word_for(v, 2)
+    cases = []
+
+    def case(name, agent, goal, obst, action, words, dist=None, goal_idx=(0, 1, 2), counter=(0, 0, 0)):
+        d = float(np.hypot(goal[0] - agent[0], goal[1] - agent[1])) if dist is None else dist
+        cases.append(dict(name=name, agent=agent, goal=goal, obst=list(obst), action=action, words=words,
+                          dist=d, goal_idx=list(goal_idx), counter=list(counter)))
+
+    follow = [(W100(0), 0)] * 3      # every dynamic obstacle follows its goal direction
+    # walls: agent at 0 / 500 pushed outwards
+    case("wall_low", (0, 0), (250, 490), far + dfar, (-1, -1), follow)
+    case("wall_high", (500, 500), (250, 490), far + dfar, (1, 1), follow)
+    case("wall_mixed", (500, 0), (250, 490), far + dfar, (1, -1), follow)
+    case("big_action_clamped", (495, 3), (250, 490), far + dfar, (10, -10), follow)
+    # overlap boundary: distance exactly 25 after the move (15,20) and just outside (26)
+    case("hit_exact_25_static", (99, 100), (250, 490), [(115, 120), far[1]] + dfar, (1, 0), follow)
+    case("miss_26_static", (99, 100), (250, 490), [(126, 100), far[1]] + dfar, (0, 0), follow)
+    case("hit_25_axis", (99, 100), (250, 490), [(125, 100), far[1]] + dfar, (1, 0), follow)
+    # dynamic obstacle moves INTO the agent this step (post-move positions are tested, :262-278)
+    case("dynamic_moves_into_agent", (200, 200), (250, 490), far + [(216, 221), dfar[1], dfar[2]], (0, 0), follow)
+    # first hit in list order: static before dynamic -> static penalty
+    case("static_and_dynamic_hit", (200, 200), (250, 490), [(210, 210), far[1]] + [(190, 190), dfar[1], dfar[2]],
+         (0, 0), follow)
+    # goal: distance exactly 10 is NOT goal (<), 9.x is
+    case("goal_exact_10_not", (239, 490), (250, 490), far + dfar, (1, 0), follow)
+    case("goal_inside", (240, 490), (250, 490), far + dfar, (1, 0), follow)
+    case("goal_and_hit_same_step", (240, 490), (250, 490), [(260, 480), far[1]] + dfar, (1, 0), follow)
+    # obstacle on an axis of its goal: single randint(9) draw, all nine table entries
+    for k in range(9):
+        case("axis_move_%d" % k, (10, 5), (250, 490), far + [(100, 50), dfar[1], dfar[2]], (0, 0),
+             [(W9(k), 0), (W100(0), 0), (W100(0), 0)])
+    # off-axis, u >= threshold: second draw picks the table entry (speed 2 obstacle)
+    for k in range(9):
+        case("random_move_%d" % k, (10, 5), (250, 490), far + dfar, (0, 0),
+             [(W100(0), 0), (W100(60 + k), W9(k)), (W100(59), 0)])
+    # goal-change step: counter reached -> no move, new goal among the others
+    case("goal_change_pick0", (10, 5), (250, 490), far + dfar, (0, 0),
+         [(W2(0), 0), (W2(1), 0), (W2(1), 0)], counter=(50, 50, 50))
+    case("goal_change_mixed", (10, 5), (250, 490), far + dfar, (0, 0),
+         [(W2(1), 0), (W100(10), 0), (W2(0), 0)], counter=(50, 49, 51), goal_idx=(2, 0, 1))
+    # obstacle outside the world keeps moving (no clamp, :334-347)
+    case("obstacle_outside_world", (10, 5), (250, 490), far + [(-30, 520), (510, -12), dfar[2]], (0, 0),
+         [(W100(99), W9(7)), (W100(99), W9(1)), (W100(0), 0)])
+    # obstacle straddling the window edge, agent near a wall (window pokes outside the world)
+    case("window_outside_world", (1, 1), (250, 490), [(20, 20), far[1]] + dfar, (-1, -1), follow)
+    case("window_partial", (100, 100), (250, 490), [(127, 100), (100, 128)] + dfar, (0, 0), follow)
+    # stored dist that disagrees with the positions (old_dist is the stored value, :236)
+    case("stale_dist", (100, 100), (250, 490), far + dfar, (1, 1), follow, dist=123.5)
+
+    n = len(cases)
+    ks, kd, K = 2, 3, 5
+    out = dict(
+        in_agent=np.zeros((n, 2)), in_goal=np.zeros((n, 2)), in_dist=np.zeros(n), in_total=np.zeros(n),
+        in_obst=np.zeros((n, K, 2)), in_goal_idx=np.zeros((n, kd), np.uint8), in_counter=np.zeros((n, kd), np.int32),
+        action=np.zeros((n, 2)), words=np.zeros((n, kd, 2), np.uint32),
+        out_agent=np.zeros((n, 2)), out_dist=np.zeros(n), out_obst=np.zeros((n, K, 2)),
+        out_goal_idx=np.zeros((n, kd), np.uint8), out_counter=np.zeros((n, kd), np.int32),
+        out_reward=np.zeros(n), out_done=np.zeros(n, np.uint8), out_flags=np.zeros(n, np.uint8),
+        out_acc=np.zeros(n), out_quadrant=np.zeros(n, np.uint8),
+        out_rows5=np.zeros((n, 5), np.uint32), out_rows10=np.zeros((n, 10), np.uint32),
+    )
+    names = []
+    for i, c in enumerate(cases):
+        tape = np.array(c["words"], dtype=np.uint64).astype(np.uint32).reshape(1, 1, kd, 2)
+        src = D.TapeDraws(step_tape=tape, n_static=ks, n_dynamic=kd)
+        ref = R.ReferenceEnv(args, R.AddressedRouter(D.PhiloxDraws(99), 0))
+        ref.reset()                                 # creates the obstacle objects
+        ref.router.src = src
+        ref.router.tick = 0
+        total = 400.0
+        ref.inject(c["agent"], c["goal"], c["dist"], c["obst"], c["goal_idx"], c["counter"],
+                   total_distance=total, acc=0.25)
+        s, r, d, _ = ref.step(c["action"])
+        env = ref.env
+        goal_flag = s[2] < env.threshold_goal
+        hit_idx = next((k for k, p in enumerate(s[3:]) if env.check_overlap(s[0], p)), -1)
+        assert bool(d) == (goal_flag or hit_idx >= 0), c["name"]
+        f = (1 if goal_flag else 0) | (2 if hit_idx >= 0 else 0) | (8 if hit_idx >= ks else 0)
+        names.append(c["name"])
+        out["in_agent"][i], out["in_goal"][i], out["in_dist"][i], out["in_total"][i] = c["agent"], c["goal"], c["dist"], total
+        out["in_obst"][i] = c["obst"]
+        out["in_goal_idx"][i], out["in_counter"][i] = c["goal_idx"], c["counter"]
+        out["action"][i], out["words"][i] = c["action"], tape[0, 0]
+        out["out_agent"][i], out["out_dist"][i] = s[0], s[2]
+        out["out_obst"][i] = np.array([tuple(p) for p in s[3:]], dtype=np.float64)
+        for j, o in enumerate(env.obstacle_list[ks:]):
+            out["out_goal_idx"][i, j] = env.obstacle_goal_list.index(o.curr_goal)
+            out["out_counter"][i, j] = o.curr_counter
+        out["out_reward"][i], out["out_done"][i], out["out_flags"][i] = r, d, f
+        out["out_acc"][i] = env.total_reward_accumulated
+        for w in (5, 10):
+            q, rows = _pack_rows(ref.observe(s, w), w)
+            out["out_rows%d" % w][i] = rows
+            out["out_quadrant"][i] = q
+    meta = dict(kind="edge", ruleset="gym", cfg=cfg, names=names, in_acc=0.25,
+                made_by="oracle/gen_golden.py running /root/reference unedited via oracle/ref_shim.py")
+    out["meta"] = np.array(json.dumps(meta))
+    return out
+
+
+def window_kats():
+    """RNG-free window observations straight from the reference's prep_state4."""
+    args = R.default_args(static_obstacles=0, dynamic_obstacles=0, obstacle_speed=[], obs_goal_position=[])
+    ref = R.ReferenceEnv(args, R.MTRouter())
+    rng = np.random.RandomState(12345)
+    states = [[(82, 82), (400, 490), 0.0, (100, 100)]]          # SURVEY.md section 8c KAT
+    for n in range(120):
+        ax, ay = int(rng.randint(0, 501)), int(rng.randint(0, 501))
+        k = int(rng.randint(0, 7))
+        obst = []
+        for _ in range(k):
+            # cluster obstacles around the agent so windows are not all empty
+            obst.append((ax + int(rng.randint(-45, 46)), ay + int(rng.randint(-45, 46))))
+        states.append([(ax, ay), (int(rng.randint(0, 500)), int(rng.randint(0, 500))), 1.0] + obst)
+    # goal exactly on an axis of the agent (quadrant tie-breaks, >= vs <)
+    states.append([(50, 50), (50, 50), 0.0])
+    states.append([(50, 50), (49, 50), 0.0])
+    states.append([(50, 50), (50, 49), 0.0])
+    states.append([(50, 50), (49, 49), 0.0])
+    kmax = max(len(s) - 3 for s in states)
+    n = len(states)
+    out = dict(agent=np.zeros((n, 2), np.int32), goal=np.zeros((n, 2), np.int32),
+               n_obst=np.zeros(n, np.int32), obst=np.full((n, kmax, 2), 10000, np.int32),
+               quadrant=np.zeros(n, np.uint8))
+    for w in (5, 10, 21):
+        out["rows%d" % w] = np.zeros((n, w), np.uint32)
+    for i, s in enumerate(states):
+        out["agent"][i], out["goal"][i], out["n_obst"][i] = s[0], s[1], len(s) - 3
+        for k, p in enumerate(s[3:]):
+            out["obst"][i, k] = p
+        for w in (5, 10, 21):
+            q, rows = _pack_rows(ref.observe(s, w), w)
+            out["rows%d" % w][i] = rows
+            out["quadrant"][i] = q
+    out["meta"] = np.array(json.dumps(dict(
+        kind="window_kat", made_by="oracle/gen_golden.py: prep_state4 of examples/ball_cnn_ac3.py:384-412, AST-lifted")))
+    return out
+
+
+def main(argv):
+    if not R.reference_available():
+        print("reference tree missing; cannot generate", file=sys.stderr)
+        return 1
+    os.makedirs(OUT_DIR, exist_ok=True)
+    jobs = {
+        "window_kat": lambda: window_kats(),
+        "edge_gym": lambda: edge_cases(),
+        "rollout_philox_default": lambda: compress_rollout(rollout(CFG_DEFAULT, 24, 260, 7, "philox", 120, g0=1000)),
+        "rollout_philox_busy": lambda: compress_rollout(rollout(CFG_BUSY, 16, 200, 11, "philox", 40, g0=5)),
+        "rollout_philox_dense": lambda: compress_rollout(rollout(CFG_DENSE, 8, 120, 3, "philox", 1000, windows=(10,))),
+        "rollout_mt_default": lambda: compress_rollout(rollout(CFG_DEFAULT, 8, 150, 0, "mt", 60)),
+    }
+    only = set(argv[1:])
+    for name, fn in jobs.items():
+        if only and name not in only:
+            continue
+        out = fn()
+        path = os.path.join(OUT_DIR, name + ".npz")
+        np.savez_compressed(path, **out)
+        print("%-28s %8.1f KiB" % (name, os.path.getsize(path) / 1024.0))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main(sys.argv))
