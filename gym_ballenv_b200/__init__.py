@@ -1,0 +1,32 @@
+"""gym_ballenv_b200 - B200-native batched step()/reset()/window-observe of ranok92/gym-ballenv.
+
+Public surface
+  BallVecEnv              N environments per launch, CUDA tensors in/out (new; vec_env.py)
+  BallEnv, make           the registered gym env's API on the same kernels (env.py)
+  EnvConfig               the reference's argparse fields as a dataclass (config.py)
+  make_prep_state         prep_state2 / prep_state4 of examples/ball_cnn_ac3.py, GPU-evaluated
+Importing this package loads libballenv_b200.so (built by ``python -m gym_ballenv_b200.build``);
+there is no CPU fallback.
+"""
+from ._lib import (LIB, BallenvError, FLAG_GOAL, FLAG_HIT, FLAG_HIT_DYNAMIC, FLAG_TRUNCATED, LIB_PATH,
+                   STAT_NAMES)
+from .config import EnvConfig
+from .env import BallEnv, TimeLimit, make, make_prep_state
+from .vec_env import MOVE_LIST, BallVecEnv
+
+__all__ = ["BallVecEnv", "BallEnv", "TimeLimit", "make", "make_prep_state", "EnvConfig", "MOVE_LIST",
+           "BallenvError", "FLAG_GOAL", "FLAG_HIT", "FLAG_TRUNCATED", "FLAG_HIT_DYNAMIC", "STAT_NAMES", "LIB_PATH"]
+
+
+def _register_with_gym():
+    """If a real ``gym`` is importable, register the same id the reference registers
+    (gym_ballenv/__init__.py:4-11) pointing at this implementation."""
+    try:
+        from gym.envs.registration import register
+        register(id='gymball-b200-v0', entry_point='gym_ballenv_b200.env:BallEnv', max_episode_steps=1000,
+                 reward_threshold=100.0, nondeterministic=False)
+    except Exception:
+        pass
+
+
+_register_with_gym()

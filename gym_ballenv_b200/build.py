@@ -1,0 +1,77 @@
+"""Build libballenv_b200.so in-tree with nvcc for sm_100a (no torch headers involved).
+
+    python -m gym_ballenv_b200.build [--force]
+
+The kernel instantiations (precision x window) are separate translation units compiled in
+parallel; the objects land in gym_ballenv_b200/csrc/_obj/ and the library next to this file
+(git-ignored, but it travels to the GPU box with the gpurun snapshot).
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(CSRC, "_obj")
+LIB = os.path.join(HERE, "libballenv_b200.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+
+INSTANCES = [("float", 5, "launch_f32_w5"), ("float", 10, "launch_f32_w10"), ("float", 0, "launch_f32_wany"),
+             ("double", 5, "launch_f64_w5"), ("double", 10, "launch_f64_w10"), ("double", 0, "launch_f64_wany")]
+
+
+def _sources():
+    deps = [os.path.join(CSRC, f) for f in ("ballenv_kernels.cuh", "ballenv_rng.cuh")]
+    deps.append(os.path.join(os.path.dirname(HERE), "include", "ballenv.h"))
+    jobs = [(os.path.join(CSRC, "ballenv_capi.cu"), os.path.join(OBJ, "ballenv_capi.o"), [])]
+    for t, w, name in INSTANCES:
+        jobs.append((os.path.join(CSRC, "ballenv_inst.cu"), os.path.join(OBJ, name + ".o"),
+                     ["-DBALLENV_T=" + t, "-DBALLENV_W=%d" % w, "-DBALLENV_NAME=" + name]))
+    return deps, jobs
+
+
+def _stale(target, srcs):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in srcs)
+
+
+def _compile(job, deps, force, log):
+    src, obj, defs = job
+    if not force and not _stale(obj, [src] + deps):
+        return obj
+    cmd = [NVCC] + ARCH + FLAGS + defs + ["-c", src, "-o", obj]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    log.append((os.path.basename(obj), r.stderr))
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (obj, " ".join(cmd), r.stderr))
+    return obj
+
+
+def build(force=False, verbose=False):
+    os.makedirs(OBJ, exist_ok=True)
+    deps, jobs = _sources()
+    log = []
+    with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
+        objs = list(ex.map(lambda j: _compile(j, deps, force, log), jobs))
+    if force or _stale(LIB, objs):
+        cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + objs
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("link failed:\n%s\n%s" % (" ".join(cmd), r.stderr))
+    if verbose:
+        for name, err in log:
+            for line in err.splitlines():
+                if "Used" in line or "spill" in line or "error" in line or "warning" in line:
+                    print("[%s] %s" % (name, line.strip()))
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

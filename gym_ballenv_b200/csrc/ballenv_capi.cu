@@ -1,0 +1,580 @@
+// C ABI (include/ballenv.h) over the sm_100a kernels in ballenv_kernels.cuh.
+// Host-side runtime: config validation, SoA arena layout, draw tapes, launches, host-buffer staging.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+
+#include "ballenv_kernels.cuh"
+
+using namespace ballenv;
+
+namespace ballenv {  // ballenv_inst.cu, one translation unit per instantiation
+void launch_f32_w5(const Params&, unsigned, cudaStream_t);
+void launch_f32_w10(const Params&, unsigned, cudaStream_t);
+void launch_f32_wany(const Params&, unsigned, cudaStream_t);
+void launch_f64_w5(const Params&, unsigned, cudaStream_t);
+void launch_f64_w10(const Params&, unsigned, cudaStream_t);
+void launch_f64_wany(const Params&, unsigned, cudaStream_t);
+}  // namespace ballenv
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                     \
+  do {                                                                                     \
+    cudaError_t err__ = (expr);                                                            \
+    if (err__ != cudaSuccess)                                                              \
+      return fail(BALLENV_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(err__), __FILE__, __LINE__); \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+};
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int obs_row_elems(const BallenvConfig& c) {
+  const int nb = 4 + c.window * c.window;
+  switch (c.obs_format) {
+    case BALLENV_OBS_F32:
+    case BALLENV_OBS_U8: return nb;
+    case BALLENV_OBS_BITS: return (nb + 31) / 32;
+    case BALLENV_OBS_FEAT20: return 20;
+  }
+  return 0;
+}
+
+size_t obs_elem_bytes(const BallenvConfig& c) { return c.obs_format == BALLENV_OBS_U8 ? 1 : 4; }
+
+int action_bytes(int kind) {
+  switch (kind) {
+    case BALLENV_ACT_INDEX_I64: return 8;
+    case BALLENV_ACT_INDEX_I32: return 4;
+    case BALLENV_ACT_INDEX_U8: return 1;
+    case BALLENV_ACT_XY_F32: return 8;
+    case BALLENV_ACT_XY_F64: return 16;
+  }
+  return 0;
+}
+
+int validate(const BallenvConfig* c) {
+  if (c == nullptr) return fail(BALLENV_EINVAL, "config is NULL");
+  if (c->abi_version != BALLENV_ABI_VERSION)
+    return fail(BALLENV_EINVAL, "config.abi_version %d != %d", c->abi_version, BALLENV_ABI_VERSION);
+  if (c->ruleset != BALLENV_RULESET_GYM && c->ruleset != BALLENV_RULESET_PYGAME)
+    return fail(BALLENV_EINVAL, "unknown ruleset %d", c->ruleset);
+  if (c->window < 1 || c->window > BALLENV_MAX_WINDOW)
+    return fail(BALLENV_EINVAL, "window %d outside [1, %d]", c->window, BALLENV_MAX_WINDOW);
+  if (c->static_obstacles < 0 || c->static_obstacles > BALLENV_MAX_STATIC)
+    return fail(BALLENV_EINVAL, "static_obstacles %d outside [0, %d]", c->static_obstacles, BALLENV_MAX_STATIC);
+  if (c->dynamic_obstacles < 0 || c->dynamic_obstacles > BALLENV_MAX_DYNAMIC)
+    return fail(BALLENV_EINVAL, "dynamic_obstacles %d outside [0, %d]", c->dynamic_obstacles, BALLENV_MAX_DYNAMIC);
+  if (c->precision != BALLENV_F32 && c->precision != BALLENV_F64)
+    return fail(BALLENV_EINVAL, "unknown precision %d", c->precision);
+  if (c->obs_format < BALLENV_OBS_F32 || c->obs_format > BALLENV_OBS_BITS)
+    return fail(BALLENV_EINVAL, "unsupported obs_format %d", c->obs_format);
+  if (c->max_episode_steps < 0) return fail(BALLENV_EINVAL, "max_episode_steps < 0");
+  if (c->ruleset == BALLENV_RULESET_PYGAME) {
+    // createBoard's dynamic-obstacle branch references undefined names (ballenv_pygame.py:502-506): unusable there too.
+    if (c->dynamic_obstacles != 0)
+      return fail(BALLENV_EINVAL, "the pygame ruleset has no working dynamic obstacles (ballenv_pygame.py:502-506)");
+    if (!(c->agent_radius >= 0) || !(c->static_obstacle_radius >= 0))
+      return fail(BALLENV_EINVAL, "negative radius");
+  } else if (c->dynamic_obstacles > 0) {
+    if (c->n_goals < c->dynamic_obstacles || c->n_goals > BALLENV_MAX_GOALS)
+      return fail(BALLENV_EINVAL, "n_goals %d must be in [dynamic_obstacles = %d, %d] (ballenv_env.py:160)",
+                  c->n_goals, c->dynamic_obstacles, BALLENV_MAX_GOALS);
+    if (c->n_goals - 1 == 100)
+      return fail(BALLENV_EINVAL, "101 obstacle goals are not supported");
+    // every goal needs at least one *different* goal to change to, else np.random.randint(0) raises
+    // at the first change step (ballenv_env.py:351-352)
+    for (int i = 0; i < c->n_goals; ++i) {
+      bool other = false;
+      for (int k = 0; k < c->n_goals; ++k)
+        other |= c->obs_goal_x[k] != c->obs_goal_x[i] || c->obs_goal_y[k] != c->obs_goal_y[i];
+      if (!other) return fail(BALLENV_EINVAL, "obstacle goals must contain at least two distinct positions");
+    }
+    if (c->time_step_for_change < 0 || c->time_step_for_change >= (1 << 23))
+      return fail(BALLENV_EINVAL, "time_step_for_change out of range");
+  }
+  return BALLENV_OK;
+}
+
+struct Layout {
+  size_t agent_x, agent_y, goal_x, goal_y, dist, total, acc, ep_len, episode, tick;
+  size_t stat_x, stat_y, dyn_x, dyn_y, dyn_meta, flags, stats, errors, bytes;
+  long long stride;
+};
+
+Layout make_layout(const BallenvConfig& c, long long n) {
+  Layout L{};
+  const size_t rb = c.precision == BALLENV_F64 ? 8 : 4;
+  const long long S = (long long)align_up((size_t)n, 128);
+  L.stride = S;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t at = off;
+    off = align_up(off + bytes, 256);
+    return at;
+  };
+  L.agent_x = take(rb * S);
+  L.agent_y = take(rb * S);
+  L.goal_x = take(rb * S);
+  L.goal_y = take(rb * S);
+  L.dist = take(8 * S);
+  L.total = take(8 * S);
+  L.acc = take(8 * S);
+  L.ep_len = take(4 * S);
+  L.episode = take(4 * S);
+  L.tick = take(4 * S);
+  L.stat_x = take(rb * S * c.static_obstacles);
+  L.stat_y = take(rb * S * c.static_obstacles);
+  L.dyn_x = take(rb * S * c.dynamic_obstacles);
+  L.dyn_y = take(rb * S * c.dynamic_obstacles);
+  L.dyn_meta = take(4 * S * c.dynamic_obstacles);
+  L.flags = take(S);
+  L.stats = take(8 * BALLENV_NUM_STATS);
+  L.errors = take(256);
+  L.bytes = off;
+  return L;
+}
+
+}  // namespace
+
+struct BallenvHandle {
+  BallenvConfig cfg;
+  long long n = 0, g0 = 0;
+  int device = 0;
+  uint64_t seed = 0;
+  char* arena = nullptr;
+  bool owns_arena = false;
+  Layout L{};
+  Params base{};
+  // draw tapes (device copies)
+  uint32_t* step_tape = nullptr;
+  long long step_tape_steps = 0, step_tape_pos = 0;
+  uint32_t* reset_tape = nullptr;
+  // device staging for ballenv_step_host
+  char* stage = nullptr;
+  size_t stage_bytes = 0;
+  size_t stage_act = 0, stage_obs = 0, stage_rew = 0, stage_done = 0;
+  long long launches = 0;
+};
+
+namespace {
+
+int launch(BallenvHandle* h, const Params& p, cudaStream_t s) {
+  const unsigned grid = (unsigned)((p.n + kBlock - 1) / kBlock);
+  const bool f64 = h->cfg.precision == BALLENV_F64;
+  switch (h->cfg.window) {
+    case 5: f64 ? launch_f64_w5(p, grid, s) : launch_f32_w5(p, grid, s); break;
+    case 10: f64 ? launch_f64_w10(p, grid, s) : launch_f32_w10(p, grid, s); break;
+    default: f64 ? launch_f64_wany(p, grid, s) : launch_f32_wany(p, grid, s); break;
+  }
+  h->launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  return BALLENV_OK;
+}
+
+void fill_dev_config(const BallenvConfig& c, DevConfig* d) {
+  memset(d, 0, sizeof(*d));
+  d->ruleset = c.ruleset;
+  d->window = c.window;
+  d->ks = c.static_obstacles;
+  d->kd = c.dynamic_obstacles;
+  d->n_goals = c.dynamic_obstacles > 0 ? c.n_goals : 0;
+  d->change_step = c.time_step_for_change;
+  d->rd_th = c.rd_th_obs;
+  d->max_steps = c.max_episode_steps;
+  d->auto_reset = c.auto_reset;
+  d->obs_format = c.obs_format;
+  d->obs_row_elems = obs_row_elems(c);
+  d->static_penalty = c.static_penalty;
+  d->dynamic_penalty = c.dynamic_penalty;
+  if (c.ruleset == BALLENV_RULESET_GYM) {
+    d->world_w = 500.0;       // _screen_width / _screen_height, ballenv_env.py:11-12
+    d->world_h = 500.0;
+    d->radius_sum = 20.0 + 5.0;   // radius_rand_person + radius_ctrl_person, :49-50,188
+    d->goal_threshold = 10.0;     // :64
+    d->step_x = 1.0;              // speedx_ctrl_person / speedy_ctrl_person, :53-54
+    d->step_y = 1.0;
+  } else {
+    d->world_w = 100.0;       // ballenv_pygame.py:8-9
+    d->world_h = 100.0;
+    d->radius_sum = c.static_obstacle_radius + c.agent_radius;   // :384
+    d->goal_threshold = 15.0;     // :345
+    d->step_x = 1.0;
+    d->step_y = 1.0;
+    d->reset_agent_thresh = 15.0; // :494
+    d->reset_goal_thresh = 5.0;
+  }
+  bool distinct = true;
+  for (int i = 0; i < d->n_goals; ++i) {
+    d->goal_x[i] = c.obs_goal_x[i];
+    d->goal_y[i] = c.obs_goal_y[i];
+    for (int k = 0; k < i; ++k)
+      distinct &= c.obs_goal_x[k] != c.obs_goal_x[i] || c.obs_goal_y[k] != c.obs_goal_y[i];
+  }
+  d->goals_distinct = distinct ? 1 : 0;
+  for (int j = 0; j < c.dynamic_obstacles; ++j) d->speed[j] = c.obstacle_speed[j];
+}
+
+int ensure_stage(BallenvHandle* h, int action_kind) {
+  const size_t n = (size_t)h->n;
+  const size_t a = align_up(n * 16, 256);   // largest action layout
+  const size_t o = align_up(n * (size_t)obs_row_elems(h->cfg) * obs_elem_bytes(h->cfg), 256);
+  const size_t r = align_up(n * 8, 256);
+  const size_t d = align_up(n, 256);
+  const size_t need = a + o + r + d;
+  (void)action_kind;
+  if (h->stage_bytes < need) {
+    if (h->stage) cudaFree(h->stage);
+    h->stage = nullptr;
+    h->stage_bytes = 0;
+    CUDA_TRY(cudaMalloc(&h->stage, need));
+    h->stage_bytes = need;
+    h->stage_act = 0;
+    h->stage_obs = a;
+    h->stage_rew = a + o;
+    h->stage_done = a + o + r;
+  }
+  return BALLENV_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ballenv_abi_version(void) { return BALLENV_ABI_VERSION; }
+
+const char* ballenv_last_error(void) { return g_err; }
+
+int ballenv_config_default(BallenvConfig* cfg, int ruleset) {
+  if (cfg == nullptr) return fail(BALLENV_EINVAL, "cfg is NULL");
+  memset(cfg, 0, sizeof(*cfg));
+  cfg->abi_version = BALLENV_ABI_VERSION;
+  cfg->ruleset = ruleset;
+  cfg->window = 5;
+  cfg->max_episode_steps = 1000;
+  cfg->auto_reset = 1;
+  cfg->precision = BALLENV_F32;
+  cfg->obs_format = BALLENV_OBS_F32;
+  cfg->agent_radius = 10.0;
+  cfg->static_obstacle_radius = 10.0;
+  if (ruleset == BALLENV_RULESET_GYM) {  // examples/ball_cnn_ac3.py:40-51
+    static const double gx[5] = {12, 123, 87, 430, 230}, gy[5] = {122, 93, 150, 440, 11};
+    cfg->static_obstacles = 13;
+    cfg->dynamic_obstacles = 5;
+    cfg->n_goals = 5;
+    for (int i = 0; i < 5; ++i) {
+      cfg->obstacle_speed[i] = 1.0;
+      cfg->obs_goal_x[i] = gx[i];
+      cfg->obs_goal_y[i] = gy[i];
+    }
+    cfg->time_step_for_change = 50;
+    cfg->rd_th_obs = 60;
+    cfg->static_penalty = 1.0;
+    cfg->dynamic_penalty = 8000.0;
+  } else if (ruleset == BALLENV_RULESET_PYGAME) {  // createBoard() defaults, ballenv_pygame.py:316
+    cfg->static_obstacles = 0;
+    cfg->max_episode_steps = 0;
+  } else {
+    return fail(BALLENV_EINVAL, "unknown ruleset %d", ruleset);
+  }
+  return BALLENV_OK;
+}
+
+int64_t ballenv_state_bytes(const BallenvConfig* cfg, int64_t n_envs) {
+  int rc = validate(cfg);
+  if (rc != BALLENV_OK) return rc;
+  if (n_envs <= 0) return fail(BALLENV_EINVAL, "n_envs must be positive");
+  return (int64_t)make_layout(*cfg, n_envs).bytes;
+}
+
+int ballenv_create(const BallenvConfig* cfg, int64_t n_envs, int64_t global_env_offset, int device, uint64_t seed,
+                   void* arena, BallenvHandle** out) {
+  if (out == nullptr) return fail(BALLENV_EINVAL, "out is NULL");
+  *out = nullptr;
+  int rc = validate(cfg);
+  if (rc != BALLENV_OK) return rc;
+  if (n_envs <= 0 || n_envs > (1ll << 31) - 256) return fail(BALLENV_EINVAL, "n_envs %lld out of range", (long long)n_envs);
+  if (global_env_offset < 0 || global_env_offset + n_envs > (1ll << 32))
+    return fail(BALLENV_EINVAL, "global env ids must fit 32 bits");
+  int ndev = 0;
+  CUDA_TRY(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(BALLENV_EINVAL, "device %d not in [0, %d)", device, ndev);
+  DeviceGuard guard(device);
+  BallenvHandle* h = new (std::nothrow) BallenvHandle();
+  if (h == nullptr) return fail(BALLENV_ENOMEM, "out of host memory");
+  h->cfg = *cfg;
+  h->n = n_envs;
+  h->g0 = global_env_offset;
+  h->device = device;
+  h->seed = seed;
+  h->L = make_layout(*cfg, n_envs);
+  if (arena != nullptr) {
+    if (((uintptr_t)arena & 255) != 0) {
+      delete h;
+      return fail(BALLENV_EINVAL, "arena must be 256-byte aligned");
+    }
+    h->arena = (char*)arena;
+  } else {
+    cudaError_t e = cudaMalloc(&h->arena, h->L.bytes);
+    if (e != cudaSuccess) {
+      delete h;
+      return fail(BALLENV_ENOMEM, "cudaMalloc(%zu) failed: %s", h->L.bytes, cudaGetErrorString(e));
+    }
+    h->owns_arena = true;
+  }
+  cudaError_t e = cudaMemset(h->arena, 0, h->L.bytes);
+  if (e == cudaSuccess) e = cudaMemset(h->arena + h->L.episode, 0xff, 4 * (size_t)h->L.stride);  // episode = -1: none yet
+  if (e != cudaSuccess) {
+    if (h->owns_arena) cudaFree(h->arena);
+    delete h;
+    return fail(BALLENV_ECUDA, "cudaMemset failed: %s", cudaGetErrorString(e));
+  }
+  Params& p = h->base;
+  memset(&p, 0, sizeof(p));
+  fill_dev_config(h->cfg, &p.cfg);
+  const Layout& L = h->L;
+  p.n = n_envs;
+  p.stride = L.stride;
+  p.g0 = (uint32_t)global_env_offset;
+  p.k0 = (uint32_t)(seed & 0xffffffffu);
+  p.k1 = (uint32_t)(seed >> 32);
+  char* a = h->arena;
+  p.agent_x = a + L.agent_x;
+  p.agent_y = a + L.agent_y;
+  p.goal_x = a + L.goal_x;
+  p.goal_y = a + L.goal_y;
+  p.dist = (double*)(a + L.dist);
+  p.total = (double*)(a + L.total);
+  p.acc = (double*)(a + L.acc);
+  p.ep_len = (int*)(a + L.ep_len);
+  p.episode = (uint32_t*)(a + L.episode);
+  p.tick = (uint32_t*)(a + L.tick);
+  p.stat_x = a + L.stat_x;
+  p.stat_y = a + L.stat_y;
+  p.dyn_x = a + L.dyn_x;
+  p.dyn_y = a + L.dyn_y;
+  p.dyn_meta = (uint32_t*)(a + L.dyn_meta);
+  p.flags = (uint8_t*)(a + L.flags);
+  p.stats = (double*)(a + L.stats);
+  p.errors = (uint32_t*)(a + L.errors);
+  *out = h;
+  return BALLENV_OK;
+}
+
+int ballenv_destroy(BallenvHandle* h) {
+  if (h == nullptr) return BALLENV_OK;
+  DeviceGuard guard(h->device);
+  cudaDeviceSynchronize();
+  if (h->owns_arena && h->arena) cudaFree(h->arena);
+  if (h->step_tape) cudaFree(h->step_tape);
+  if (h->reset_tape) cudaFree(h->reset_tape);
+  if (h->stage) cudaFree(h->stage);
+  delete h;
+  return BALLENV_OK;
+}
+
+int ballenv_state_ptrs(BallenvHandle* h, BallenvStatePtrs* out) {
+  if (h == nullptr || out == nullptr) return fail(BALLENV_EINVAL, "NULL argument");
+  const Params& p = h->base;
+  memset(out, 0, sizeof(*out));
+  out->n_envs = h->n;
+  out->n_stride = h->L.stride;
+  out->real_bytes = h->cfg.precision == BALLENV_F64 ? 8 : 4;
+  out->obs_row_elems = obs_row_elems(h->cfg);
+  out->agent_x = p.agent_x;
+  out->agent_y = p.agent_y;
+  out->goal_x = p.goal_x;
+  out->goal_y = p.goal_y;
+  out->dist = p.dist;
+  out->total_distance = p.total;
+  out->acc_reward = p.acc;
+  out->ep_len = p.ep_len;
+  out->episode = p.episode;
+  out->tick = p.tick;
+  out->static_x = p.stat_x;
+  out->static_y = p.stat_y;
+  out->dynamic_x = p.dyn_x;
+  out->dynamic_y = p.dyn_y;
+  out->dynamic_meta = p.dyn_meta;
+  out->flags = p.flags;
+  out->stats = p.stats;
+  out->error_flags = p.errors;
+  return BALLENV_OK;
+}
+
+int ballenv_reset(BallenvHandle* h, const uint8_t* mask, void* obs_out, ballenv_stream_t stream) {
+  if (h == nullptr) return fail(BALLENV_EINVAL, "handle is NULL");
+  DeviceGuard guard(h->device);
+  Params p = h->base;
+  p.mode = kModeReset;
+  p.reset_mask = mask;
+  p.obs = obs_out;
+  p.reset_tape = h->reset_tape;
+  return launch(h, p, (cudaStream_t)stream);
+}
+
+int ballenv_observe(BallenvHandle* h, void* obs_out, ballenv_stream_t stream) {
+  if (h == nullptr || obs_out == nullptr) return fail(BALLENV_EINVAL, "NULL argument");
+  DeviceGuard guard(h->device);
+  Params p = h->base;
+  p.mode = kModeObserve;
+  p.obs = obs_out;
+  return launch(h, p, (cudaStream_t)stream);
+}
+
+int ballenv_step(BallenvHandle* h, const void* actions, int action_kind, void* obs_out, void* reward_out,
+                 uint8_t* done_out, ballenv_stream_t stream) {
+  if (h == nullptr || actions == nullptr) return fail(BALLENV_EINVAL, "NULL argument");
+  if (action_bytes(action_kind) == 0) return fail(BALLENV_EINVAL, "unknown action_kind %d", action_kind);
+  DeviceGuard guard(h->device);
+  Params p = h->base;
+  p.mode = kModeStep;
+  p.actions = actions;
+  p.action_kind = action_kind;
+  p.obs = obs_out;
+  p.reward = reward_out;
+  p.done = done_out;
+  p.reset_tape = h->reset_tape;
+  if (h->step_tape != nullptr) {
+    if (h->step_tape_pos >= h->step_tape_steps)
+      return fail(BALLENV_ESTATE, "step tape exhausted after %lld steps", h->step_tape_steps);
+    p.step_tape = h->step_tape + (size_t)h->step_tape_pos * (size_t)h->n * h->cfg.dynamic_obstacles * 2;
+    h->step_tape_pos += 1;
+  }
+  return launch(h, p, (cudaStream_t)stream);
+}
+
+int ballenv_step_many(BallenvHandle* h, const void* actions, int action_kind, int32_t n_steps, void* obs_out,
+                      int32_t obs_all_steps, void* reward_out, uint8_t* done_out, ballenv_stream_t stream) {
+  if (h == nullptr || actions == nullptr) return fail(BALLENV_EINVAL, "NULL argument");
+  const int ab = action_bytes(action_kind);
+  if (ab == 0) return fail(BALLENV_EINVAL, "unknown action_kind %d", action_kind);
+  if (n_steps < 0) return fail(BALLENV_EINVAL, "n_steps < 0");
+  const size_t n = (size_t)h->n;
+  const size_t obs_row = (size_t)obs_row_elems(h->cfg) * obs_elem_bytes(h->cfg);
+  const size_t rew_b = h->cfg.precision == BALLENV_F64 ? 8 : 4;
+  for (int t = 0; t < n_steps; ++t) {
+    void* obs_t = nullptr;
+    if (obs_out != nullptr) {
+      if (obs_all_steps) obs_t = (char*)obs_out + (size_t)t * n * obs_row;
+      else if (t == n_steps - 1) obs_t = obs_out;
+    }
+    int rc = ballenv_step(h, (const char*)actions + (size_t)t * n * ab, action_kind, obs_t,
+                          reward_out ? (char*)reward_out + (size_t)t * n * rew_b : nullptr,
+                          done_out ? done_out + (size_t)t * n : nullptr, stream);
+    if (rc != BALLENV_OK) return rc;
+  }
+  return BALLENV_OK;
+}
+
+int ballenv_step_host(BallenvHandle* h, const void* actions_host, int action_kind, void* obs_host, void* reward_host,
+                      uint8_t* done_host, ballenv_stream_t stream) {
+  if (h == nullptr || actions_host == nullptr) return fail(BALLENV_EINVAL, "NULL argument");
+  const int ab = action_bytes(action_kind);
+  if (ab == 0) return fail(BALLENV_EINVAL, "unknown action_kind %d", action_kind);
+  DeviceGuard guard(h->device);
+  int rc = ensure_stage(h, action_kind);
+  if (rc != BALLENV_OK) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t n = (size_t)h->n;
+  char* st = h->stage;
+  CUDA_TRY(cudaMemcpyAsync(st + h->stage_act, actions_host, n * ab, cudaMemcpyHostToDevice, s));
+  rc = ballenv_step(h, st + h->stage_act, action_kind, obs_host ? st + h->stage_obs : nullptr,
+                    reward_host ? st + h->stage_rew : nullptr, done_host ? (uint8_t*)(st + h->stage_done) : nullptr,
+                    stream);
+  if (rc != BALLENV_OK) return rc;
+  if (obs_host)
+    CUDA_TRY(cudaMemcpyAsync(obs_host, st + h->stage_obs, n * obs_row_elems(h->cfg) * obs_elem_bytes(h->cfg),
+                             cudaMemcpyDeviceToHost, s));
+  if (reward_host)
+    CUDA_TRY(cudaMemcpyAsync(reward_host, st + h->stage_rew, n * (h->cfg.precision == BALLENV_F64 ? 8 : 4),
+                             cudaMemcpyDeviceToHost, s));
+  if (done_host) CUDA_TRY(cudaMemcpyAsync(done_host, st + h->stage_done, n, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return BALLENV_OK;
+}
+
+int ballenv_set_draw_tape(BallenvHandle* h, const uint32_t* step_tape, int64_t n_steps, const uint32_t* reset_tape,
+                          int64_t n_episodes, int32_t attempts) {
+  if (h == nullptr) return fail(BALLENV_EINVAL, "handle is NULL");
+  DeviceGuard guard(h->device);
+  CUDA_TRY(cudaDeviceSynchronize());
+  if (h->step_tape) cudaFree(h->step_tape);
+  if (h->reset_tape) cudaFree(h->reset_tape);
+  h->step_tape = nullptr;
+  h->reset_tape = nullptr;
+  h->step_tape_steps = h->step_tape_pos = 0;
+  h->base.reset_tape_episodes = 0;
+  h->base.tape_attempts = 0;
+  h->base.reset_tape_width = 0;
+  if (step_tape != nullptr && n_steps > 0 && h->cfg.dynamic_obstacles > 0) {
+    const size_t bytes = (size_t)n_steps * (size_t)h->n * h->cfg.dynamic_obstacles * 2 * sizeof(uint32_t);
+    CUDA_TRY(cudaMalloc(&h->step_tape, bytes));
+    CUDA_TRY(cudaMemcpy(h->step_tape, step_tape, bytes, cudaMemcpyHostToDevice));
+    h->step_tape_steps = n_steps;
+  }
+  if (reset_tape != nullptr && n_episodes > 0) {
+    if (h->cfg.ruleset != BALLENV_RULESET_GYM) return fail(BALLENV_EINVAL, "reset tapes exist for the gym ruleset only");
+    if (attempts < 1) return fail(BALLENV_EINVAL, "attempts must be >= 1");
+    const int width = 4 + 2 * attempts * h->cfg.static_obstacles + 2 * h->cfg.dynamic_obstacles;
+    const size_t bytes = (size_t)n_episodes * (size_t)h->n * width * sizeof(uint32_t);
+    CUDA_TRY(cudaMalloc(&h->reset_tape, bytes));
+    CUDA_TRY(cudaMemcpy(h->reset_tape, reset_tape, bytes, cudaMemcpyHostToDevice));
+    h->base.reset_tape_episodes = n_episodes;
+    h->base.tape_attempts = attempts;
+    h->base.reset_tape_width = width;
+  }
+  return BALLENV_OK;
+}
+
+int ballenv_stats(BallenvHandle* h, double* out, ballenv_stream_t stream) {
+  if (h == nullptr || out == nullptr) return fail(BALLENV_EINVAL, "NULL argument");
+  DeviceGuard guard(h->device);
+  CUDA_TRY(cudaMemcpyAsync(out, h->base.stats, sizeof(double) * BALLENV_NUM_STATS, cudaMemcpyDeviceToHost,
+                           (cudaStream_t)stream));
+  CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  return BALLENV_OK;
+}
+
+int ballenv_stats_reset(BallenvHandle* h, ballenv_stream_t stream) {
+  if (h == nullptr) return fail(BALLENV_EINVAL, "handle is NULL");
+  DeviceGuard guard(h->device);
+  CUDA_TRY(cudaMemsetAsync(h->base.stats, 0, sizeof(double) * BALLENV_NUM_STATS, (cudaStream_t)stream));
+  return BALLENV_OK;
+}
+
+int ballenv_error_flags(BallenvHandle* h, uint32_t* out, ballenv_stream_t stream) {
+  if (h == nullptr || out == nullptr) return fail(BALLENV_EINVAL, "NULL argument");
+  DeviceGuard guard(h->device);
+  CUDA_TRY(cudaMemcpyAsync(out, h->base.errors, sizeof(uint32_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  CUDA_TRY(cudaMemsetAsync(h->base.errors, 0, sizeof(uint32_t), (cudaStream_t)stream));
+  CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  return BALLENV_OK;
+}
+
+int64_t ballenv_launch_count(BallenvHandle* h) { return h ? h->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,15 @@
+// One explicit instantiation of the fused kernel per translation unit (compiled once per
+// -DBALLENV_T / -DBALLENV_W pair so the instantiations build in parallel).
+#include <cuda_runtime.h>
+
+#include "ballenv_kernels.cuh"
+
+#ifndef BALLENV_T
+#error "compile with -DBALLENV_T=float|double -DBALLENV_W=0|5|10 -DBALLENV_NAME=..."
+#endif
+
+namespace ballenv {
+void BALLENV_NAME(const Params& p, unsigned grid, cudaStream_t s) {
+  ballenv_kernel<BALLENV_T, BALLENV_W><<<grid, kBlock, 0, s>>>(p);
+}
+}  // namespace ballenv

@@ -1,0 +1,264 @@
+"""N-environment vector wrapper over the fused CUDA step+observe kernel.
+
+New relative to the reference (which steps one Python env per process): ``BallVecEnv`` advances
+N independent ball environments per launch and returns torch CUDA tensors.  Semantics of a single
+environment are those of the reference's ``BallEnv`` (gym_ballenv/envs/ballenv_env.py:37-289) or,
+with ``ruleset="pygame"``, ``createBoard`` (ballenv_pygame.py:314-706); the observation is
+``prep_state4(state, WINDOW)`` of examples/ball_cnn_ac3.py:384-412.  Added: the TimeLimit(1000)
+of the gym registration (gym_ballenv/__init__.py:7) as a ``truncated`` flag OR-ed into ``done``, and
+auto-reset of finished environments inside the same launch (the returned observation is the first
+observation of the new episode; reward/done belong to the finished one).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib as L
+from ._lib import LIB, check
+from .config import EnvConfig
+
+# agent action table of the training loops (examples/ball_cnn_ac3.py:530)
+MOVE_LIST = [(1, 1), (1, -1), (1, 0), (0, 1), (0, -1), (0, 0), (-1, 1), (-1, 0), (-1, -1)]
+
+_RULESETS = {"gym": L.RULESET_GYM, "pygame": L.RULESET_PYGAME}
+_OBS_FORMATS = {torch.float32: L.OBS_F32, torch.uint8: L.OBS_U8, "bits": L.OBS_BITS}
+
+
+class BallVecEnv:
+    """N ball environments resident on one GPU.
+
+    step(actions) accepts
+      * int64 / int32 / uint8 ``[N]`` indices into ``MOVE_LIST``, or
+      * float32 / float64 ``[N, 2]`` raw ``(dx, dy)`` (what ``BallEnv.step`` indexes, ballenv_env.py:247-248)
+    and returns ``(obs [N, 4 + W*W], reward [N], done [N] bool, info)``.  The returned tensors are views of
+    env-owned double buffers: they stay valid until the step after next (``clone()`` to keep them).
+    """
+
+    def __init__(self, num_envs: int, window: int = 5, config: Optional[EnvConfig] = None, ruleset: str = "gym",
+                 device="cuda", seed: int = 0, obs_dtype=torch.float32, parity: bool = False,
+                 auto_reset: bool = True, max_episode_steps: Optional[int] = None, global_env_offset: int = 0):
+        if not torch.cuda.is_available():
+            raise RuntimeError("gym_ballenv_b200 needs a CUDA device (there is no CPU fallback)")
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise ValueError("device must be a CUDA device")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.num_envs = int(num_envs)
+        self.window = int(window)
+        self.ruleset = ruleset
+        if config is None:
+            config = EnvConfig() if ruleset == "gym" else EnvConfig.pygame_default()
+        self.config = config
+        self.parity = bool(parity)
+        self.seed = int(seed)
+        self.global_env_offset = int(global_env_offset)
+        if max_episode_steps is None:
+            max_episode_steps = 1000 if ruleset == "gym" else 0
+        self.max_episode_steps = int(max_episode_steps)
+        self.auto_reset = bool(auto_reset)
+        self.obs_dtype = obs_dtype
+        self._ccfg = config.to_c(window, _RULESETS[ruleset], L.F64 if parity else L.F32, _OBS_FORMATS[obs_dtype],
+                                 self.max_episode_steps, self.auto_reset)
+        nbytes = check(LIB.ballenv_state_bytes(C.byref(self._ccfg), self.num_envs))
+        with torch.cuda.device(self.device):
+            self._arena = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
+            torch.cuda.synchronize(self.device)
+        h = C.c_void_p()
+        check(LIB.ballenv_create(C.byref(self._ccfg), self.num_envs, self.global_env_offset, self.device.index,
+                                 C.c_uint64(self.seed & (2 ** 64 - 1)), C.c_void_p(self._arena.data_ptr()), C.byref(h)))
+        self._h = h
+        self._ptrs = L.BallenvStatePtrs()
+        check(LIB.ballenv_state_ptrs(self._h, C.byref(self._ptrs)))
+        self._real = torch.float64 if parity else torch.float32
+        self._make_views()
+        self.obs_row = int(self._ptrs.obs_row_elems)
+        obs_t = torch.int32 if obs_dtype == "bits" else obs_dtype
+        n = self.num_envs
+        self._bufs = [dict(obs=torch.empty((n, self.obs_row), dtype=obs_t, device=self.device),
+                           reward=torch.empty(n, dtype=self._real, device=self.device),
+                           done=torch.empty(n, dtype=torch.uint8, device=self.device)) for _ in range(2)]
+        self._flip = 0
+        self._tape_refs = None
+
+    # ------------------------------------------------------------------ plumbing
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _view(self, ptr, nbytes, dtype, shape):
+        off = ptr - self._arena.data_ptr()
+        return self._arena[off:off + nbytes].view(dtype).view(shape)
+
+    def _make_views(self):
+        p, S, n = self._ptrs, int(self._ptrs.n_stride), self.num_envs
+        rb = int(p.real_bytes)
+        ks, kd = self.config.static_obstacles, self.config.dynamic_obstacles
+        v = {}
+        for name in ("agent_x", "agent_y", "goal_x", "goal_y"):
+            v[name] = self._view(getattr(p, name), rb * S, self._real, (S,))[:n]
+        for name in ("dist", "total_distance", "acc_reward"):
+            v[name] = self._view(getattr(p, name), 8 * S, torch.float64, (S,))[:n]
+        for name in ("ep_len", "episode", "tick"):
+            v[name] = self._view(getattr(p, name), 4 * S, torch.int32, (S,))[:n]
+        for name, k in (("static_x", ks), ("static_y", ks), ("dynamic_x", kd), ("dynamic_y", kd)):
+            v[name] = (self._view(getattr(p, name), rb * S * k, self._real, (k, S))[:, :n] if k
+                       else torch.empty((0, n), dtype=self._real, device=self.device))
+        v["dynamic_meta"] = (self._view(p.dynamic_meta, 4 * S * kd, torch.int32, (kd, S))[:, :n] if kd
+                             else torch.empty((0, n), dtype=torch.int32, device=self.device))
+        v["flags"] = self._view(p.flags, S, torch.uint8, (S,))[:n]
+        v["stats"] = self._view(p.stats, 8 * L.NUM_STATS, torch.float64, (L.NUM_STATS,))
+        self.state_views: Dict[str, torch.Tensor] = v
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            LIB.ballenv_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ API
+    @property
+    def observation_size(self):
+        return 4 + self.window * self.window
+
+    def reset(self, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Reset all environments (or those where ``mask`` is non-zero) -> observation [N, 4 + W*W]."""
+        buf = self._next_buf()
+        mptr = None
+        if mask is not None:
+            mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+            assert mask.shape == (self.num_envs,)
+            mptr = C.c_void_p(mask.data_ptr())
+        check(LIB.ballenv_reset(self._h, mptr, C.c_void_p(buf["obs"].data_ptr()), self._stream()))
+        return buf["obs"]
+
+    def observe(self) -> torch.Tensor:
+        """prep_state4 of the current state, without stepping."""
+        buf = self._next_buf()
+        check(LIB.ballenv_observe(self._h, C.c_void_p(buf["obs"].data_ptr()), self._stream()))
+        return buf["obs"]
+
+    def _next_buf(self):
+        self._flip ^= 1
+        return self._bufs[self._flip]
+
+    @staticmethod
+    def _action_kind(actions: torch.Tensor, n: int):
+        if actions.dim() == 1:
+            kinds = {torch.int64: L.ACT_INDEX_I64, torch.int32: L.ACT_INDEX_I32, torch.uint8: L.ACT_INDEX_U8}
+            if actions.dtype not in kinds or actions.shape[0] != n:
+                raise ValueError("index actions must be int64/int32/uint8 [N]")
+            return kinds[actions.dtype]
+        if actions.dim() == 2 and actions.shape == (n, 2):
+            kinds = {torch.float32: L.ACT_XY_F32, torch.float64: L.ACT_XY_F64}
+            if actions.dtype not in kinds:
+                raise ValueError("raw actions must be float32/float64 [N, 2]")
+            return kinds[actions.dtype]
+        raise ValueError("actions must be [N] indices or [N, 2] raw (dx, dy)")
+
+    def step(self, actions: torch.Tensor):
+        if actions.device != self.device:
+            raise ValueError("actions must live on %s" % self.device)
+        kind = self._action_kind(actions, self.num_envs)
+        actions = actions.contiguous()
+        buf = self._next_buf()
+        check(LIB.ballenv_step(self._h, C.c_void_p(actions.data_ptr()), kind, C.c_void_p(buf["obs"].data_ptr()),
+                               C.c_void_p(buf["reward"].data_ptr()), C.c_void_p(buf["done"].data_ptr()),
+                               self._stream()))
+        info = {"flags": self.state_views["flags"], "state": self.state_views}
+        return buf["obs"], buf["reward"], buf["done"].view(torch.bool), info
+
+    def step_many(self, actions: torch.Tensor, keep_all_obs: bool = False):
+        """T steps in one call; actions [T, N] indices or [T, N, 2] raw.
+        -> (obs [T, N, row] or [N, row], reward [T, N], done [T, N] bool)."""
+        T = actions.shape[0]
+        kind = self._action_kind(actions[0], self.num_envs)
+        actions = actions.contiguous()
+        n = self.num_envs
+        obs = torch.empty(((T, n, self.obs_row) if keep_all_obs else (n, self.obs_row)),
+                          dtype=self._bufs[0]["obs"].dtype, device=self.device)
+        reward = torch.empty((T, n), dtype=self._real, device=self.device)
+        done = torch.empty((T, n), dtype=torch.uint8, device=self.device)
+        check(LIB.ballenv_step_many(self._h, C.c_void_p(actions.data_ptr()), kind, T, C.c_void_p(obs.data_ptr()),
+                                    1 if keep_all_obs else 0, C.c_void_p(reward.data_ptr()),
+                                    C.c_void_p(done.data_ptr()), self._stream()))
+        return obs, reward, done.view(torch.bool)
+
+    def step_host(self, actions, obs_out, reward_out, done_out):
+        """Host-buffer step through the C ABI (ballenv_step_host): ``actions`` and the three outputs are CPU
+        tensors (pinned for speed); copies both ways happen inside the call, which returns synchronised."""
+        kind = self._action_kind(actions, self.num_envs)
+        check(LIB.ballenv_step_host(self._h, C.c_void_p(actions.data_ptr()), kind, C.c_void_p(obs_out.data_ptr()),
+                                    C.c_void_p(reward_out.data_ptr()), C.c_void_p(done_out.data_ptr()),
+                                    self._stream()))
+        return obs_out, reward_out, done_out
+
+    # ------------------------------------------------------------------ state injection / inspection
+    def get_state(self) -> Dict[str, torch.Tensor]:
+        """Copies of the SoA state.  Obstacles are [K, N]; ``dynamic_goal`` / ``dynamic_counter`` unpack dynamic_meta."""
+        out = {k: v.clone() for k, v in self.state_views.items() if k != "stats"}
+        meta = out.pop("dynamic_meta")
+        out["dynamic_goal"] = meta & 0xff
+        out["dynamic_counter"] = meta >> 8
+        return out
+
+    def set_state(self, **fields):
+        """Overwrite state arrays (same names/shapes as get_state()).  Used for parity injection."""
+        fields = dict(fields)
+        if "dynamic_goal" in fields or "dynamic_counter" in fields:
+            meta = self.state_views["dynamic_meta"]
+            goal = fields.pop("dynamic_goal", meta & 0xff)
+            cnt = fields.pop("dynamic_counter", meta >> 8)
+            goal = torch.as_tensor(goal, device=self.device).to(torch.int32)
+            cnt = torch.as_tensor(cnt, device=self.device).to(torch.int32)
+            meta.copy_(goal | (cnt << 8))
+        for k, val in fields.items():
+            dst = self.state_views[k]
+            dst.copy_(torch.as_tensor(val, device=self.device).to(dst.dtype))
+
+    def set_draw_tape(self, step_tape=None, reset_tape=None, attempts: int = 1):
+        """Parity mode: inject the random words (uint32, held as int64/uint32 CPU tensors or numpy arrays).
+        step_tape [T, N, Kd, 2]; reset_tape [E, N, 4 + 2*attempts*Ks + 2*Kd]; None clears."""
+        import numpy as np
+        st = rt = None
+        sp = rp = None
+        T = E = 0
+        if step_tape is not None:
+            st = np.ascontiguousarray(np.asarray(step_tape), dtype=np.uint32)
+            assert st.shape[1:] == (self.num_envs, self.config.dynamic_obstacles, 2), st.shape
+            T, sp = st.shape[0], st.ctypes.data_as(C.c_void_p)
+        if reset_tape is not None:
+            rt = np.ascontiguousarray(np.asarray(reset_tape), dtype=np.uint32)
+            width = 4 + 2 * attempts * self.config.static_obstacles + 2 * self.config.dynamic_obstacles
+            assert rt.shape[1:] == (self.num_envs, width), (rt.shape, width)
+            E, rp = rt.shape[0], rt.ctypes.data_as(C.c_void_p)
+        check(LIB.ballenv_set_draw_tape(self._h, sp, T, rp, E, attempts))
+
+    def stats(self) -> Dict[str, float]:
+        out = (C.c_double * L.NUM_STATS)()
+        check(LIB.ballenv_stats(self._h, out, self._stream()))
+        return {name: out[i] for i, name in enumerate(L.STAT_NAMES)}
+
+    @property
+    def stats_tensor(self) -> torch.Tensor:
+        """Device view of the statistics vector (float64 [16]); all-reduce this across GPUs."""
+        return self.state_views["stats"]
+
+    def reset_stats(self):
+        check(LIB.ballenv_stats_reset(self._h, self._stream()))
+
+    def error_flags(self) -> int:
+        out = C.c_uint32(0)
+        check(LIB.ballenv_error_flags(self._h, C.byref(out), self._stream()))
+        return int(out.value)
+
+    @property
+    def launch_count(self) -> int:
+        return int(LIB.ballenv_launch_count(self._h))

@@ -1,0 +1,220 @@
+/*
+ * ballenv.h - C ABI of the B200-native batched gym-ballenv step()/reset()/observe hot path.
+ *
+ * This is the drop-in boundary: plain C, raw pointers and sizes, no C++/torch types.
+ * The reference (ranok92/gym-ballenv) is pure Python and has no FFI; each entry point
+ * below names the reference interface it replaces (paths relative to the reference root).
+ * INTEGRATION.md shows the ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative BALLENV_E* code; the message for the
+ *     last failure on the calling thread is ballenv_last_error().  Nothing throws.
+ *   - nothing synchronises the device unless documented; work is enqueued on `stream`
+ *     (a cudaStream_t passed as void*; NULL = the legacy default stream).
+ *   - "device pointer" arguments must live on the handle's device.
+ *   - a handle is confined to one host thread / stream at a time; distinct handles are independent.
+ *
+ * State layout (struct-of-arrays, resident in HBM, owned by the handle or by a caller arena):
+ *   per-env scalars are arrays of n_stride elements; per-obstacle fields are [K][n_stride]
+ *   (obstacle-major, environment-minor) so that one warp reading obstacle k of 32 consecutive
+ *   environments touches one 128-byte line.
+ */
+#ifndef BALLENV_H_
+#define BALLENV_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BALLENV_ABI_VERSION 1
+
+#define BALLENV_MAX_DYNAMIC 64
+#define BALLENV_MAX_GOALS 64
+#define BALLENV_MAX_STATIC 1024
+#define BALLENV_MAX_WINDOW 32
+
+/* error codes */
+#define BALLENV_OK 0
+#define BALLENV_EINVAL (-1)   /* bad argument / config */
+#define BALLENV_ECUDA (-2)    /* a CUDA call failed (see ballenv_last_error) */
+#define BALLENV_ENOMEM (-3)
+#define BALLENV_ESTATE (-4)   /* call not valid in the handle's current state (e.g. tape exhausted) */
+
+/* BallenvConfig.ruleset */
+#define BALLENV_RULESET_GYM 0     /* gym_ballenv/envs/ballenv_env.py : BallEnv (500x500, moving obstacles) */
+#define BALLENV_RULESET_PYGAME 1  /* ballenv_pygame.py : createBoard (100x100, float coordinates) */
+
+/* BallenvConfig.precision : type the positions are stored and compared in */
+#define BALLENV_F32 0   /* production: fp32 positions, fp64 distance/reward arithmetic in registers */
+#define BALLENV_F64 1   /* parity mode: everything fp64, operation order of the reference */
+
+/* BallenvConfig.obs_format : element type of the observation rows */
+#define BALLENV_OBS_F32 0   /* float32 [n][4 + W*W]  - what prep_state4 returns (examples/ball_cnn_ac3.py:412) */
+#define BALLENV_OBS_U8 1    /* uint8   [n][4 + W*W] */
+#define BALLENV_OBS_BITS 2  /* uint32  [n][ceil((4 + W*W) / 32)], bit b of the row = element b */
+#define BALLENV_OBS_FEAT20 3 /* float32 [n][20] - featureExtractor.py:247-265 (pygame ruleset's sensor_readings) */
+
+/* action_kind of ballenv_step */
+#define BALLENV_ACT_INDEX_I64 0 /* int64 [n]  index into the agent move table of examples/ball_cnn_ac3.py:530 */
+#define BALLENV_ACT_INDEX_I32 1
+#define BALLENV_ACT_INDEX_U8 2
+#define BALLENV_ACT_XY_F32 3    /* float32 [n][2] raw (dx, dy), what BallEnv.step(action) indexes (ballenv_env.py:247-248) */
+#define BALLENV_ACT_XY_F64 4
+
+/* bits of the per-env flags byte / of done */
+#define BALLENV_FLAG_GOAL 1
+#define BALLENV_FLAG_HIT 2
+#define BALLENV_FLAG_TRUNCATED 4
+#define BALLENV_FLAG_HIT_DYNAMIC 8   /* the first obstacle hit (list order) is a dynamic one */
+
+/* device-side error bits (ballenv_error_flags) */
+#define BALLENV_DEVERR_BAD_ACTION 1       /* action index outside [0, 9) : treated as (0, 0) */
+#define BALLENV_DEVERR_TAPE_EXHAUSTED 2   /* a tape had no slot for a requested draw : Philox used instead */
+#define BALLENV_DEVERR_RESET_STUCK 4      /* an obstacle placement was rejected 4096 times (the reference would spin) */
+
+/* slots of the episode-statistics vector (doubles) */
+#define BALLENV_STAT_EPISODES 0
+#define BALLENV_STAT_RETURN_SUM 1
+#define BALLENV_STAT_LENGTH_SUM 2
+#define BALLENV_STAT_GOALS 3
+#define BALLENV_STAT_HITS_STATIC 4
+#define BALLENV_STAT_HITS_DYNAMIC 5
+#define BALLENV_STAT_TIMEOUTS 6
+#define BALLENV_STAT_STEPS 7
+#define BALLENV_NUM_STATS 16
+
+/*
+ * Environment configuration; one config is shared by all environments of a handle.
+ * Field names follow the argparse Namespace consumed by BallEnv.customize_environment
+ * (gym_ballenv/envs/ballenv_env.py:87-109; defaults examples/ball_cnn_ac3.py:40-51).
+ */
+typedef struct BallenvConfig {
+  int32_t abi_version;        /* BALLENV_ABI_VERSION */
+  int32_t ruleset;            /* BALLENV_RULESET_* */
+  int32_t window;             /* WINDOW of examples/ball_cnn_ac3.py:493 (1..32) */
+  int32_t static_obstacles;   /* args.static_obstacles */
+  int32_t dynamic_obstacles;  /* args.dynamic_obstacles (gym ruleset only) */
+  int32_t n_goals;            /* len(args.obs_goal_position) ; >= dynamic_obstacles ; >= 2 distinct if any dynamic */
+  int32_t time_step_for_change; /* args.time_step_for_change */
+  int32_t rd_th_obs;          /* args.rd_th_obs */
+  int32_t max_episode_steps;  /* TimeLimit of gym_ballenv/__init__.py:7 (1000) ; 0 = none */
+  int32_t auto_reset;         /* 1: done envs are reset inside the step launch (vector wrapper) */
+  int32_t precision;          /* BALLENV_F32 / BALLENV_F64 */
+  int32_t obs_format;         /* BALLENV_OBS_* */
+  double static_penalty;      /* args.static_penalty[1]  (ballenv_env.py:138,223) */
+  double dynamic_penalty;     /* args.dynamic_penalty[1] (ballenv_env.py:158,223) */
+  double agent_radius;            /* pygame ruleset ctor (ballenv_pygame.py:316) */
+  double static_obstacle_radius;  /* pygame ruleset ctor */
+  double obstacle_speed[BALLENV_MAX_DYNAMIC]; /* args.obstacle_speed */
+  double obs_goal_x[BALLENV_MAX_GOALS];       /* args.obs_goal_position, parsed */
+  double obs_goal_y[BALLENV_MAX_GOALS];
+} BallenvConfig;
+
+/* Device pointers of the SoA state (ballenv_state_ptrs).  Real = float or double per config.precision. */
+typedef struct BallenvStatePtrs {
+  int64_t n_envs;
+  int64_t n_stride;     /* element stride between obstacle rows (>= n_envs) */
+  int32_t real_bytes;   /* 4 or 8 */
+  int32_t obs_row_elems; /* elements per observation row in the configured obs_format */
+  void *agent_x, *agent_y;    /* Real [n_stride]            state[0] */
+  void *goal_x, *goal_y;      /* Real [n_stride]            state[1] */
+  double *dist;               /* [n_stride]                 state[2] (becomes old_dist of the next step) */
+  double *total_distance;     /* [n_stride]                 self.total_distance */
+  double *acc_reward;         /* [n_stride]                 self.total_reward_accumulated */
+  int32_t *ep_len;            /* [n_stride]                 steps since reset (TimeLimit counter) */
+  uint32_t *episode;          /* [n_stride]                 index of the current episode (reset-draw address) */
+  uint32_t *tick;             /* [n_stride]                 steps since creation (step-draw address) */
+  void *static_x, *static_y;  /* Real [static_obstacles][n_stride]   state[3 : 3 + Ks] */
+  void *dynamic_x, *dynamic_y;/* Real [dynamic_obstacles][n_stride]  state[3 + Ks :] */
+  uint32_t *dynamic_meta;     /* [dynamic_obstacles][n_stride]  curr_goal index | curr_counter << 8 */
+  uint8_t *flags;             /* [n_stride]                 BALLENV_FLAG_* of the last step */
+  double *stats;              /* [BALLENV_NUM_STATS]        episode statistics (all-reduce these across GPUs) */
+  uint32_t *error_flags;      /* [1]                        BALLENV_DEVERR_* */
+} BallenvStatePtrs;
+
+typedef struct BallenvHandle BallenvHandle;
+typedef void *ballenv_stream_t; /* cudaStream_t */
+
+int ballenv_abi_version(void);
+const char *ballenv_last_error(void);
+
+/* Fill *cfg with the defaults of examples/ball_cnn_ac3.py:40-51 (gym) or createBoard() (pygame). */
+int ballenv_config_default(BallenvConfig *cfg, int ruleset);
+
+/* Bytes of device memory one handle needs for n_envs environments (to size a caller-owned arena). */
+int64_t ballenv_state_bytes(const BallenvConfig *cfg, int64_t n_envs);
+
+/*
+ * Replaces: gym.make('gymball-v0') + env.unwrapped.customize_environment(args)
+ *           (gym_ballenv/__init__.py:4-11, ballenv_env.py:43-109)  /  createBoard(...) (ballenv_pygame.py:316).
+ * global_env_offset : id of environment 0 in the whole (multi-GPU) job; Philox streams are keyed by the
+ *                     global id so trajectories do not depend on the sharding.
+ * arena             : device memory of >= ballenv_state_bytes() bytes (256-byte aligned) or NULL to let the
+ *                     library cudaMalloc it.
+ */
+int ballenv_create(const BallenvConfig *cfg, int64_t n_envs, int64_t global_env_offset, int device,
+                   uint64_t seed, void *arena, BallenvHandle **out);
+int ballenv_destroy(BallenvHandle *h);
+int ballenv_state_ptrs(BallenvHandle *h, BallenvStatePtrs *out);
+
+/*
+ * Replaces: BallEnv.reset() (ballenv_env.py:113-167) / createBoard.reset() (ballenv_pygame.py:460-513),
+ * followed by prep_state4(state, WINDOW) (examples/ball_cnn_ac3.py:384-412).
+ * mask : device uint8 [n] (non-zero = reset this env) or NULL for all.  obs_out : device rows or NULL.
+ */
+int ballenv_reset(BallenvHandle *h, const uint8_t *mask, void *obs_out, ballenv_stream_t stream);
+
+/*
+ * Replaces: BallEnv.step(action) (ballenv_env.py:232-289) incl. move_obstacles (:323-353) and
+ * calculate_reward (:200-229) / createBoard.step (ballenv_pygame.py:650-706), the TimeLimit wrapper,
+ * and the prep_state4 call of the training loop (examples/ball_cnn_ac3.py:560) - one fused launch.
+ * actions    : device, layout per action_kind
+ * obs_out    : device rows in cfg.obs_format (post-reset observation for envs that finished), or NULL
+ * reward_out : device float32 [n] (BALLENV_F32) or float64 [n] (BALLENV_F64), or NULL
+ * done_out   : device uint8 [n] (goal | hit | truncated), or NULL
+ */
+int ballenv_step(BallenvHandle *h, const void *actions, int action_kind, void *obs_out, void *reward_out,
+                 uint8_t *done_out, ballenv_stream_t stream);
+
+/*
+ * T consecutive steps in one call (synthetic rollouts).  actions [T][n], reward_out [T][n], done_out [T][n];
+ * obs_out [T][n][row] if obs_all_steps != 0, else [n][row] holding the last step's observation.
+ */
+int ballenv_step_many(BallenvHandle *h, const void *actions, int action_kind, int32_t n_steps, void *obs_out,
+                      int32_t obs_all_steps, void *reward_out, uint8_t *done_out, ballenv_stream_t stream);
+
+/* prep_state4 on the current state without stepping (examples/ball_cnn_ac3.py:384-412). */
+int ballenv_observe(BallenvHandle *h, void *obs_out, ballenv_stream_t stream);
+
+/*
+ * Same as ballenv_step but with HOST buffers (pinned or pageable): copies actions host->device, steps,
+ * copies obs/reward/done device->host and synchronises `stream` before returning.  This is the call the
+ * end-to-end number of bench.py is measured through.
+ */
+int ballenv_step_host(BallenvHandle *h, const void *actions_host, int action_kind, void *obs_host,
+                      void *reward_host, uint8_t *done_host, ballenv_stream_t stream);
+
+/*
+ * Parity mode: replace Philox words by injected ones (copied to the device; NULL clears a tape).
+ * step_tape  : host uint32 [n_steps][n][dynamic_obstacles][2]; step s of the tape answers the s-th
+ *              ballenv_step call after this call.
+ * reset_tape : host uint32 [n_episodes][n][4 + 2*attempts*static_obstacles + 2*dynamic_obstacles];
+ *              row e answers the resets of episode index e (gym ruleset).
+ */
+int ballenv_set_draw_tape(BallenvHandle *h, const uint32_t *step_tape, int64_t n_steps,
+                          const uint32_t *reset_tape, int64_t n_episodes, int32_t attempts);
+
+/* Copy the statistics vector to host (synchronises `stream`). */
+int ballenv_stats(BallenvHandle *h, double *out /* [BALLENV_NUM_STATS] host */, ballenv_stream_t stream);
+int ballenv_stats_reset(BallenvHandle *h, ballenv_stream_t stream);
+/* Read and clear the device error bits (synchronises `stream`). */
+int ballenv_error_flags(BallenvHandle *h, uint32_t *out /* host */, ballenv_stream_t stream);
+/* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
+int64_t ballenv_launch_count(BallenvHandle *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BALLENV_H_ */

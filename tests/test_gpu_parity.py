@@ -1,0 +1,286 @@
+"""GPU parity: the CUDA path (through the C ABI, via gym_ballenv_b200) against
+ (a) the golden fixtures recorded from the reference's own code, and
+ (b) the CPU oracle on the same seeded inputs.
+Integer/flag/grid results must be bit-exact; rewards agree to 1e-5 relative in fp32 mode (they are computed
+in fp64 and rounded once, so the observed error is ~6e-8) and exactly in fp64 parity mode."""
+import numpy as np
+import pytest
+
+from helpers import load_golden, oracle_config, parse_goals, tapes_from_golden
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+def _env_config(cfg):
+    from gym_ballenv_b200 import EnvConfig
+    return EnvConfig(static_obstacles=cfg["static_obstacles"], dynamic_obstacles=cfg["dynamic_obstacles"],
+                     obstacle_speed=cfg["obstacle_speed"], obs_goal_position=cfg["obs_goal_position"],
+                     time_step_for_change=cfg["time_step_for_change"], rd_th_obs=cfg["rd_th_obs"],
+                     static_penalty=cfg["static_penalty"], dynamic_penalty=cfg["dynamic_penalty"])
+
+
+def _rows_from_obs(obs, w):
+    """obs [N, 4 + w*w] (any numeric dtype) -> (quadrant [N], rows [N, w] bitmasks)."""
+    o = obs.detach().cpu().numpy().astype(np.int64)
+    assert set(np.unique(o)) <= {0, 1}
+    assert np.all(o[:, :4].sum(1) == 1)
+    q = o[:, :4].argmax(1)
+    grid = o[:, 4:].reshape(-1, w, w)
+    rows = (grid << np.arange(w)[None, None, :]).sum(2)
+    return q, rows
+
+
+def _check_state(env, z, prefix, idx, ks, kd, exact_dist=True):
+    s = env.get_state()
+    n = env.num_envs
+    agent = np.stack([s["agent_x"].cpu().numpy(), s["agent_y"].cpu().numpy()], 1)
+    goal = np.stack([s["goal_x"].cpu().numpy(), s["goal_y"].cpu().numpy()], 1)
+    exp_agent = z[prefix + "agent"][idx] if idx is not None else z[prefix + "agent"]
+    exp_goal = z[prefix + "goal"][idx] if idx is not None else z[prefix + "goal"]
+    assert np.array_equal(agent, exp_agent.astype(np.float64))
+    assert np.array_equal(goal, exp_goal.astype(np.float64))
+    obst = np.concatenate([np.stack([s["static_x"].cpu().numpy(), s["static_y"].cpu().numpy()], 2),
+                           np.stack([s["dynamic_x"].cpu().numpy(), s["dynamic_y"].cpu().numpy()], 2)], 0)
+    exp_obst = z[prefix + "obst"][idx] if idx is not None else z[prefix + "obst"]
+    assert np.array_equal(obst.transpose(1, 0, 2), exp_obst.astype(np.float64))
+    exp_dist = z[prefix + "dist"][idx] if idx is not None else z[prefix + "dist"]
+    exp_total = z[prefix + "total_distance"][idx] if idx is not None else z[prefix + "total_distance"]
+    assert np.array_equal(s["dist"].cpu().numpy(), exp_dist)
+    assert np.array_equal(s["total_distance"].cpu().numpy(), exp_total)
+    return s
+
+
+@pytest.mark.parametrize("parity", [False, True])
+@pytest.mark.parametrize("name", ["rollout_philox_default", "rollout_philox_busy", "rollout_philox_dense",
+                                  "rollout_mt_default"])
+def test_golden_rollout(name, parity):
+    from gym_ballenv_b200 import BallVecEnv
+    z, meta = load_golden(name)
+    cfg = meta["cfg"]
+    ks, kd = cfg["static_obstacles"], cfg["dynamic_obstacles"]
+    n, T, g0 = meta["n_envs"], meta["T"], meta["g0"]
+    for w in meta["windows"]:
+        env = BallVecEnv(n, window=w, config=_env_config(cfg), seed=meta["seed"], parity=parity,
+                         max_episode_steps=meta["max_episode_steps"], global_env_offset=g0)
+        if meta["mode"] == "mt":
+            step, reset = tapes_from_golden(z, meta)
+            env.set_draw_tape(step, reset, meta["tape_attempts"])
+        obs = env.reset()
+        _check_state(env, z, "init_", None, ks, kd)
+        q, rows = _rows_from_obs(obs, w)
+        assert np.array_equal(q, z["init_quadrant"]) and np.array_equal(rows, z["init_rows%d" % w])
+        for t in range(T):
+            a = torch.from_numpy(z["rec_actions"][t].astype(np.int64)).cuda()
+            obs, rew, done, info = env.step(a)
+            assert np.array_equal(done.cpu().numpy().astype(np.uint8), z["rec_done"][t]), (t, w)
+            assert np.array_equal(info["flags"].cpu().numpy(), z["rec_flags"][t]), (t, w)
+            if parity:
+                assert np.array_equal(rew.cpu().numpy(), z["rec_reward"][t]), (t, w)
+            else:
+                np.testing.assert_allclose(rew.cpu().numpy(), z["rec_reward"][t], rtol=1e-5, atol=0)
+            s = _check_state(env, z, "rec_", t, ks, kd)
+            assert np.array_equal(s["acc_reward"].cpu().numpy(), z["rec_acc"][t]), (t, w)
+            assert np.array_equal(s["ep_len"].cpu().numpy(), z["rec_ep_len"][t])
+            assert np.array_equal(s["dynamic_goal"].cpu().numpy().T, z["rec_dyn_goal"][t])
+            assert np.array_equal(s["dynamic_counter"].cpu().numpy().T, z["rec_dyn_counter"][t])
+            q, rows = _rows_from_obs(obs, w)
+            assert np.array_equal(q, z["rec_quadrant"][t]), (t, w)
+            assert np.array_equal(rows, z["rec_rows%d" % w][t]), (t, w)
+        st = env.stats()
+        for k, v in meta["stats"].items():
+            assert st[k] == pytest.approx(v, rel=1e-9), k
+        assert env.error_flags() == 0
+        env.close()
+
+
+@pytest.mark.parametrize("parity", [False, True])
+def test_edge_cases(parity):
+    from gym_ballenv_b200 import BallVecEnv
+    z, meta = load_golden("edge_gym")
+    cfg = meta["cfg"]
+    n = len(meta["names"])
+    for w in (5, 10):
+        env = BallVecEnv(n, window=w, config=_env_config(cfg), parity=parity, auto_reset=False, max_episode_steps=0)
+        env.reset()
+        env.set_state(agent_x=z["in_agent"][:, 0], agent_y=z["in_agent"][:, 1], goal_x=z["in_goal"][:, 0],
+                      goal_y=z["in_goal"][:, 1], dist=z["in_dist"], total_distance=z["in_total"],
+                      acc_reward=np.full(n, meta["in_acc"]),
+                      static_x=z["in_obst"][:, :2, 0].T, static_y=z["in_obst"][:, :2, 1].T,
+                      dynamic_x=z["in_obst"][:, 2:, 0].T, dynamic_y=z["in_obst"][:, 2:, 1].T,
+                      dynamic_goal=z["in_goal_idx"].T.astype(np.int32), dynamic_counter=z["in_counter"].T)
+        env.set_draw_tape(z["words"][None])
+        a = torch.from_numpy(z["action"]).cuda()
+        obs, rew, done, info = env.step(a if parity else a.float())
+        s = env.get_state()
+        names = np.array(meta["names"])
+
+        def same(got, exp, what):
+            bad = np.nonzero(~np.all(np.asarray(got).reshape(n, -1) == np.asarray(exp).reshape(n, -1), axis=1))[0]
+            assert len(bad) == 0, (what, list(names[bad]))
+
+        same(np.stack([s["agent_x"].cpu().numpy(), s["agent_y"].cpu().numpy()], 1), z["out_agent"], "agent")
+        same(s["dist"].cpu().numpy(), z["out_dist"], "dist")
+        obst = np.concatenate([np.stack([s["static_x"].cpu().numpy(), s["static_y"].cpu().numpy()], 2),
+                               np.stack([s["dynamic_x"].cpu().numpy(), s["dynamic_y"].cpu().numpy()], 2)], 0)
+        same(obst.transpose(1, 0, 2), z["out_obst"], "obstacles")
+        same(s["dynamic_goal"].cpu().numpy().T, z["out_goal_idx"], "goal idx")
+        same(s["dynamic_counter"].cpu().numpy().T, z["out_counter"], "counter")
+        same(done.cpu().numpy().astype(np.uint8), z["out_done"], "done")
+        same(info["flags"].cpu().numpy(), z["out_flags"], "flags")
+        if parity:
+            same(rew.cpu().numpy(), z["out_reward"], "reward")
+            same(s["acc_reward"].cpu().numpy(), z["out_acc"], "acc")
+        else:
+            np.testing.assert_allclose(rew.cpu().numpy(), z["out_reward"], rtol=1e-5, atol=0)
+        q, rows = _rows_from_obs(obs, w)
+        same(q, z["out_quadrant"], "quadrant")
+        same(rows, z["out_rows%d" % w], "rows")
+        env.close()
+
+
+@pytest.mark.parametrize("parity", [False, True])
+@pytest.mark.parametrize("w", [5, 10, 21])
+def test_window_kat(w, parity):
+    from gym_ballenv_b200 import BallVecEnv, EnvConfig
+    z, meta = load_golden("window_kat")
+    n, kmax = z["obst"].shape[0], z["obst"].shape[1]
+    cfg = EnvConfig(static_obstacles=kmax, dynamic_obstacles=0, obstacle_speed=(), obs_goal_position=())
+    env = BallVecEnv(n, window=w, config=cfg, parity=parity, auto_reset=False, max_episode_steps=0)
+    env.set_state(agent_x=z["agent"][:, 0], agent_y=z["agent"][:, 1], goal_x=z["goal"][:, 0], goal_y=z["goal"][:, 1],
+                  static_x=z["obst"][:, :, 0].T, static_y=z["obst"][:, :, 1].T)   # unused slots sit at (10000, 10000)
+    q, rows = _rows_from_obs(env.observe(), w)
+    assert np.array_equal(q, z["quadrant"])
+    assert np.array_equal(rows, z["rows%d" % w])
+    env.close()
+
+
+@pytest.mark.parametrize("obs_dtype", ["f32", "u8", "bits"])
+def test_obs_formats_agree(obs_dtype):
+    from gym_ballenv_b200 import BallVecEnv
+    dt = {"f32": torch.float32, "u8": torch.uint8, "bits": "bits"}[obs_dtype]
+    n = 1000   # not a multiple of the block size: exercises the ragged tail of the coalesced store
+    for w in (5, 10, 7):
+        ref = BallVecEnv(n, window=w, seed=5, obs_dtype=torch.float32)
+        env = BallVecEnv(n, window=w, seed=5, obs_dtype=dt)
+        o_ref, o = ref.reset(), env.reset()
+        g = torch.Generator().manual_seed(0)
+        for t in range(30):
+            a = torch.randint(0, 9, (n,), generator=g).cuda()
+            o_ref = ref.step(a)[0]
+            o = env.step(a)[0]
+        if obs_dtype == "bits":
+            nb = 4 + w * w
+            words = o.cpu().numpy().astype(np.int64) & 0xffffffff
+            bits = ((words[:, :, None] >> np.arange(32)[None, None, :]) & 1).reshape(n, -1)[:, :nb]
+            assert np.array_equal(bits, o_ref.cpu().numpy().astype(np.int64))
+        else:
+            assert np.array_equal(o.cpu().numpy().astype(np.float32), o_ref.cpu().numpy())
+        ref.close()
+        env.close()
+
+
+@pytest.mark.parametrize("w,cfgname", [(5, "default"), (10, "dense")])
+def test_oracle_rollout(w, cfgname):
+    """Config 2 shape at a size the Python oracle finishes in seconds; the 4096-env x 200-step case runs against
+    the C oracle in test_gpu_parity_c.py."""
+    from gym_ballenv_b200 import BallVecEnv, EnvConfig
+    from oracle import draws as D
+    from oracle.ballenv_oracle import OracleVec
+    from oracle.gen_golden import CFG_DEFAULT, CFG_DENSE
+    cfg = CFG_DEFAULT if cfgname == "default" else CFG_DENSE
+    n, T, seed, g0 = 192, 40, 77, 123456
+    env = BallVecEnv(n, window=w, config=_env_config(cfg), seed=seed, max_episode_steps=25, global_env_offset=g0)
+    vec = OracleVec(oracle_config(cfg, w, 25), D.PhiloxDraws(seed), n, g0)
+    obs = env.reset()
+    vec.reset()
+    assert np.array_equal(obs.cpu().numpy(), np.array(vec.observe(), dtype=np.float32))
+    g = torch.Generator().manual_seed(3)
+    for t in range(T):
+        a = torch.randint(0, 9, (n,), generator=g)
+        obs, rew, done, info = env.step(a.cuda())
+        r, d, f = vec.step(a.tolist())
+        assert np.array_equal(obs.cpu().numpy(), np.array(vec.observe(), dtype=np.float32)), t
+        assert np.array_equal(done.cpu().numpy(), np.array(d)), t
+        assert np.array_equal(info["flags"].cpu().numpy(), np.array(f, dtype=np.uint8)), t
+        np.testing.assert_allclose(rew.cpu().numpy(), np.array(r), rtol=1e-5, atol=0)
+    st = env.stats()
+    for k, v in vec.stats.items():
+        assert st[k] == pytest.approx(v, rel=1e-9), k
+    env.close()
+
+
+def test_shard_invariance():
+    """Same global env id -> same trajectory regardless of how the envs are split into handles."""
+    from gym_ballenv_b200 import BallVecEnv
+    n, T = 512, 60
+    whole = BallVecEnv(n, window=5, seed=9, max_episode_steps=20)
+    parts = [BallVecEnv(n // 4, window=5, seed=9, max_episode_steps=20, global_env_offset=i * (n // 4)) for i in range(4)]
+    o = whole.reset()
+    op = torch.cat([p.reset() for p in parts])
+    assert torch.equal(o, op)
+    g = torch.Generator().manual_seed(2)
+    for t in range(T):
+        a = torch.randint(0, 9, (n,), generator=g).cuda()
+        o, r, d, _ = whole.step(a)
+        outs = [p.step(a[i * (n // 4):(i + 1) * (n // 4)]) for i, p in enumerate(parts)]
+        assert torch.equal(o, torch.cat([x[0] for x in outs]))
+        assert torch.equal(r, torch.cat([x[1] for x in outs]))
+        assert torch.equal(d, torch.cat([x[2] for x in outs]))
+    tot = whole.stats()
+    summed = {k: sum(p.stats()[k] for p in parts) for k in tot}
+    for k in tot:
+        assert summed[k] == pytest.approx(tot[k], rel=1e-9)
+
+
+def test_single_env_facade():
+    """gym-style API (reset/step/state list) against the oracle's state list."""
+    import gym_ballenv_b200 as gb
+    from argparse import Namespace
+    from oracle import draws as D
+    from oracle.ballenv_oracle import OracleConfig, OracleEnv
+    from oracle.gen_golden import CFG_DEFAULT
+    args = Namespace(rd_th_agent=80, static_thresholds=[0, 0], dynamic_thresholds=[10, 10], **CFG_DEFAULT)
+    env = gb.make('gymball-v0', seed=21)
+    env.unwrapped.customize_environment(args)
+    prep_state2, prep_state4 = gb.make_prep_state(env)
+    ocfg = oracle_config(CFG_DEFAULT, 5, 0, False)
+    ref = OracleEnv(ocfg, D.PhiloxDraws(21), 0)
+    state = env.reset()
+    assert list(state) == ref.reset()
+    rng = np.random.RandomState(0)
+    for t in range(50):
+        obs = prep_state4(state, 5)
+        assert obs.shape == (1, 29) and obs.dtype == torch.float32 and obs.is_cuda
+        assert obs.cpu().numpy().reshape(-1).tolist() == ref.observe(5)
+        a = gb.MOVE_LIST[rng.randint(9)]
+        state, reward, done, info = env.step(a)
+        r, d = ref.step(a)
+        assert list(state) == ref.state() and reward == r and done == d
+        assert env.unwrapped.total_reward_accumulated == ref.acc
+        if done:
+            break
+    # arbitrary-state observation at another window size
+    st = [(82, 82), (400, 490), 0.0, (100, 100)]
+    o10 = prep_state4(st, 10).cpu().numpy().reshape(-1)
+    from oracle.ballenv_oracle import window_obs
+    assert o10.tolist() == window_obs(st[0], st[1], st[3:], 10)
+    env.close()
+
+
+def test_bad_action_flag_and_errors():
+    from gym_ballenv_b200 import BallVecEnv, BallenvError, EnvConfig
+    env = BallVecEnv(64, window=5)
+    env.reset()
+    a = torch.full((64,), 11, dtype=torch.int64, device="cuda")
+    env.step(a)
+    assert env.error_flags() & 1
+    assert env.error_flags() == 0     # read-and-clear
+    with pytest.raises(ValueError):
+        env.step(torch.zeros(63, dtype=torch.int64, device="cuda"))
+    with pytest.raises(BallenvError):
+        BallVecEnv(8, window=40)
+    with pytest.raises(BallenvError):   # a single distinct obstacle goal: the reference raises at the first change step
+        BallVecEnv(8, config=EnvConfig(dynamic_obstacles=2, obstacle_speed=[1, 1], obs_goal_position=['5,5', '5,5']))
+    env.close()
