@@ -175,17 +175,31 @@ class BallVecEnv:
         info = {"flags": self.state_views["flags"], "state": self.state_views}
         return buf["obs"], buf["reward"], buf["done"].view(torch.bool), info
 
-    def step_many(self, actions: torch.Tensor, keep_all_obs: bool = False):
-        """T steps in one call; actions [T, N] indices or [T, N, 2] raw.
-        -> (obs [T, N, row] or [N, row], reward [T, N], done [T, N] bool)."""
-        T = actions.shape[0]
-        kind = self._action_kind(actions[0], self.num_envs)
-        actions = actions.contiguous()
+    def alloc_rollout(self, T: int, keep_all_obs: bool = False):
+        """Rollout buffers for step_many(out=...): (obs [T, N, row] or [N, row], reward [T, N], done [T, N] uint8)."""
         n = self.num_envs
         obs = torch.empty(((T, n, self.obs_row) if keep_all_obs else (n, self.obs_row)),
                           dtype=self._bufs[0]["obs"].dtype, device=self.device)
         reward = torch.empty((T, n), dtype=self._real, device=self.device)
         done = torch.empty((T, n), dtype=torch.uint8, device=self.device)
+        return obs, reward, done
+
+    def step_many(self, actions: torch.Tensor, keep_all_obs: bool = False, out=None):
+        """T steps in one call; actions [T, N] indices or [T, N, 2] raw.
+        -> (obs [T, N, row] or [N, row], reward [T, N], done [T, N] bool).  ``out`` = alloc_rollout(T, ...)
+        buffers to write into (a training loop's rollout storage) instead of fresh tensors."""
+        T = actions.shape[0]
+        kind = self._action_kind(actions[0], self.num_envs)
+        if actions.device != self.device:
+            raise ValueError("actions must live on %s" % self.device)
+        actions = actions.contiguous()
+        obs, reward, done = out if out is not None else self.alloc_rollout(T, keep_all_obs)
+        if out is not None:
+            want = (T, self.num_envs, self.obs_row) if keep_all_obs else (self.num_envs, self.obs_row)
+            if (tuple(obs.shape) != want or tuple(reward.shape) != (T, self.num_envs)
+                    or tuple(done.shape) != (T, self.num_envs) or done.dtype != torch.uint8
+                    or not (obs.is_contiguous() and reward.is_contiguous() and done.is_contiguous())):
+                raise ValueError("out buffers do not match alloc_rollout(%d, %s)" % (T, keep_all_obs))
         check(LIB.ballenv_step_many(self._h, C.c_void_p(actions.data_ptr()), kind, T, C.c_void_p(obs.data_ptr()),
                                     1 if keep_all_obs else 0, C.c_void_p(reward.data_ptr()),
                                     C.c_void_p(done.data_ptr()), self._stream()))
