@@ -10,7 +10,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libballenv_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_DYNAMIC = 64
 MAX_GOALS = 64
 MAX_STATIC = 1024
@@ -41,7 +41,8 @@ class BallenvConfig(C.Structure):
 
 class BallenvStatePtrs(C.Structure):
     _fields_ = [
-        ("n_envs", C.c_int64), ("n_stride", C.c_int64), ("real_bytes", C.c_int32), ("obs_row_elems", C.c_int32),
+        ("n_envs", C.c_int64), ("n_stride", C.c_int64), ("static_stride", C.c_int64),
+        ("dynamic_stride", C.c_int64), ("real_bytes", C.c_int32), ("obs_row_elems", C.c_int32),
         ("agent_x", C.c_void_p), ("agent_y", C.c_void_p), ("goal_x", C.c_void_p), ("goal_y", C.c_void_p),
         ("dist", C.c_void_p), ("total_distance", C.c_void_p), ("acc_reward", C.c_void_p),
         ("ep_len", C.c_void_p), ("episode", C.c_void_p), ("tick", C.c_void_p),
@@ -90,7 +91,7 @@ def _bind(lib):
 def load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(
-            "gym_ballenv_b200: %s is missing - build it with `python -m gym_ballenv_b200.build` "
+            "gym_ballenv_b200: %s is missing - build it with `python __graft_entry__.py` or `python gym_ballenv_b200/build.py` "
             "(nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
     lib = _bind(C.CDLL(LIB_PATH))
     if lib.ballenv_abi_version() != ABI_VERSION:

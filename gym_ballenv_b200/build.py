@@ -1,6 +1,6 @@
 """Build libballenv_b200.so in-tree with nvcc for sm_100a (no torch headers involved).
 
-    python -m gym_ballenv_b200.build [--force]
+    python gym_ballenv_b200/build.py [--force]
 
 The kernel instantiations (precision x window) are separate translation units compiled in
 parallel; the objects land in gym_ballenv_b200/csrc/_obj/ and the library next to this file
@@ -20,18 +20,23 @@ LIB = os.path.join(HERE, "libballenv_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+if os.environ.get("BALLENV_MINBLOCKS"):   # tuning experiments: resident blocks per SM the kernels are compiled for
+    FLAGS.append("-DBALLENV_MINBLOCKS=" + os.environ["BALLENV_MINBLOCKS"])
 
-INSTANCES = [("float", 5, "launch_f32_w5"), ("float", 10, "launch_f32_w10"), ("float", 0, "launch_f32_wany"),
-             ("double", 5, "launch_f64_w5"), ("double", 10, "launch_f64_w10"), ("double", 0, "launch_f64_wany")]
+# (positions type, window (0 = any), fast specialisation, launcher name)
+INSTANCES = [("float", 5, 0, "launch_f32_w5"), ("float", 10, 0, "launch_f32_w10"), ("float", 0, 0, "launch_f32_wany"),
+             ("double", 5, 0, "launch_f64_w5"), ("double", 10, 0, "launch_f64_w10"), ("double", 0, 0, "launch_f64_wany"),
+             ("float", 5, 1, "launch_f32_w5_fast"), ("float", 10, 1, "launch_f32_w10_fast"),
+             ("float", 0, 1, "launch_f32_wany_fast")]
 
 
 def _sources():
     deps = [os.path.join(CSRC, f) for f in ("ballenv_kernels.cuh", "ballenv_rng.cuh")]
     deps.append(os.path.join(os.path.dirname(HERE), "include", "ballenv.h"))
     jobs = [(os.path.join(CSRC, "ballenv_capi.cu"), os.path.join(OBJ, "ballenv_capi.o"), [])]
-    for t, w, name in INSTANCES:
+    for t, w, fast, name in INSTANCES:
         jobs.append((os.path.join(CSRC, "ballenv_inst.cu"), os.path.join(OBJ, name + ".o"),
-                     ["-DBALLENV_T=" + t, "-DBALLENV_W=%d" % w, "-DBALLENV_NAME=" + name]))
+                     ["-DBALLENV_T=" + t, "-DBALLENV_W=%d" % w, "-DBALLENV_FAST=%d" % fast, "-DBALLENV_NAME=" + name]))
     return deps, jobs
 
 
@@ -58,7 +63,7 @@ def build(force=False, verbose=False):
     os.makedirs(OBJ, exist_ok=True)
     deps, jobs = _sources()
     log = []
-    with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
+    with ThreadPoolExecutor(max_workers=min(10, len(jobs))) as ex:
         objs = list(ex.map(lambda j: _compile(j, deps, force, log), jobs))
     if force or _stale(LIB, objs):
         cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + objs

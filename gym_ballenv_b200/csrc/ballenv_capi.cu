@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -18,6 +19,9 @@ void launch_f32_wany(const Params&, unsigned, cudaStream_t);
 void launch_f64_w5(const Params&, unsigned, cudaStream_t);
 void launch_f64_w10(const Params&, unsigned, cudaStream_t);
 void launch_f64_wany(const Params&, unsigned, cudaStream_t);
+void launch_f32_w5_fast(const Params&, unsigned, cudaStream_t);
+void launch_f32_w10_fast(const Params&, unsigned, cudaStream_t);
+void launch_f32_wany_fast(const Params&, unsigned, cudaStream_t);
 }  // namespace ballenv
 
 namespace {
@@ -122,7 +126,7 @@ int validate(const BallenvConfig* c) {
 struct Layout {
   size_t agent_x, agent_y, goal_x, goal_y, dist, total, acc, ep_len, episode, tick;
   size_t stat_x, stat_y, dyn_x, dyn_y, dyn_meta, flags, stats, errors, bytes;
-  long long stride;
+  long long stride, stat_stride, dyn_stride;
 };
 
 Layout make_layout(const BallenvConfig& c, long long n) {
@@ -130,6 +134,8 @@ Layout make_layout(const BallenvConfig& c, long long n) {
   const size_t rb = c.precision == BALLENV_F64 ? 8 : 4;
   const long long S = (long long)align_up((size_t)n, 128);
   L.stride = S;
+  L.stat_stride = (long long)align_up((size_t)c.static_obstacles, 4);   // environment-major rows of 128-bit quads
+  L.dyn_stride = (long long)align_up((size_t)c.dynamic_obstacles, 4);
   size_t off = 0;
   auto take = [&](size_t bytes) {
     size_t at = off;
@@ -146,11 +152,11 @@ Layout make_layout(const BallenvConfig& c, long long n) {
   L.ep_len = take(4 * S);
   L.episode = take(4 * S);
   L.tick = take(4 * S);
-  L.stat_x = take(rb * S * c.static_obstacles);
-  L.stat_y = take(rb * S * c.static_obstacles);
-  L.dyn_x = take(rb * S * c.dynamic_obstacles);
-  L.dyn_y = take(rb * S * c.dynamic_obstacles);
-  L.dyn_meta = take(4 * S * c.dynamic_obstacles);
+  L.stat_x = take(rb * S * L.stat_stride);
+  L.stat_y = take(rb * S * L.stat_stride);
+  L.dyn_x = take(rb * S * L.dyn_stride);
+  L.dyn_y = take(rb * S * L.dyn_stride);
+  L.dyn_meta = take(4 * S * L.dyn_stride);
   L.flags = take(S);
   L.stats = take(8 * BALLENV_NUM_STATS);
   L.errors = take(256);
@@ -178,13 +184,37 @@ struct BallenvHandle {
   size_t stage_bytes = 0;
   size_t stage_act = 0, stage_obs = 0, stage_rew = 0, stage_done = 0;
   long long launches = 0;
+  bool no_rollout = false;      // BALLENV_NO_ROLLOUT=1: ballenv_step_many launches one kernel per step (tests, profiling)
+  bool force_generic = false;   // BALLENV_FORCE_GENERIC=1 in the environment: never pick the fast specialisation (tests)
 };
 
 namespace {
 
+// production specialisation (see ballenv_kernel<.., kFast>): everything the generic kernel tests per launch
+bool fast_eligible(const BallenvHandle* h, const Params& p) {
+  return h->cfg.precision == BALLENV_F32 && p.mode == kModeStep && p.cfg.ruleset == BALLENV_RULESET_GYM &&
+         p.step_tape == nullptr && p.reset_tape == nullptr && (p.cfg.goals_distinct || p.cfg.kd == 0) &&
+         p.obs != nullptr && p.cfg.obs_format == BALLENV_OBS_F32 &&
+         (p.action_kind == BALLENV_ACT_INDEX_I64 || p.action_kind == BALLENV_ACT_INDEX_I32 ||
+          p.action_kind == BALLENV_ACT_INDEX_U8) &&
+         !h->force_generic;
+}
+
 int launch(BallenvHandle* h, const Params& p, cudaStream_t s) {
-  const unsigned grid = (unsigned)((p.n + kBlock - 1) / kBlock);
+  const unsigned grid = (unsigned)((p.n + kEnvsPerBlock - 1) / kEnvsPerBlock);
   const bool f64 = h->cfg.precision == BALLENV_F64;
+  const bool fast = fast_eligible(h, p);
+  if (!fast && p.n_steps != 1) return fail(BALLENV_EINVAL, "internal: multi-step launch needs the fast kernel");
+  if (fast) {
+    switch (h->cfg.window) {
+      case 5: launch_f32_w5_fast(p, grid, s); break;
+      case 10: launch_f32_w10_fast(p, grid, s); break;
+      default: launch_f32_wany_fast(p, grid, s); break;
+    }
+    h->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    return BALLENV_OK;
+  }
   switch (h->cfg.window) {
     case 5: f64 ? launch_f64_w5(p, grid, s) : launch_f32_w5(p, grid, s); break;
     case 10: f64 ? launch_f64_w10(p, grid, s) : launch_f32_w10(p, grid, s); break;
@@ -227,6 +257,15 @@ void fill_dev_config(const BallenvConfig& c, DevConfig* d) {
     d->reset_agent_thresh = 15.0; // :494
     d->reset_goal_thresh = 5.0;
   }
+  d->margin = d->radius_sum + (d->step_x > d->step_y ? d->step_x : d->step_y) * (double)(c.window / 2) + 2.0;
+  d->f_world_w = (float)d->world_w;
+  d->f_world_h = (float)d->world_h;
+  d->f_step_x = (float)d->step_x;
+  d->f_step_y = (float)d->step_y;
+  d->f_margin = (float)d->margin;
+  const uint32_t qs = (uint32_t)(c.static_obstacles + 3) / 4, qd = (uint32_t)(c.dynamic_obstacles + 3) / 4;
+  d->rcp_qs = qs > 1 ? (uint32_t)(((1ull << 32) + qs - 1) / qs) : 0u;
+  d->rcp_qd = qd > 1 ? (uint32_t)(((1ull << 32) + qd - 1) / qd) : 0u;
   bool distinct = true;
   for (int i = 0; i < d->n_goals; ++i) {
     d->goal_x[i] = c.obs_goal_x[i];
@@ -235,7 +274,11 @@ void fill_dev_config(const BallenvConfig& c, DevConfig* d) {
       distinct &= c.obs_goal_x[k] != c.obs_goal_x[i] || c.obs_goal_y[k] != c.obs_goal_y[i];
   }
   d->goals_distinct = distinct ? 1 : 0;
-  for (int j = 0; j < c.dynamic_obstacles; ++j) d->speed[j] = c.obstacle_speed[j];
+  for (int i = 0; i < d->n_goals; ++i) d->f_goal[i] = make_float2((float)c.obs_goal_x[i], (float)c.obs_goal_y[i]);
+  for (int j = 0; j < c.dynamic_obstacles; ++j) {
+    d->speed[j] = c.obstacle_speed[j];
+    d->f_speed[j] = (float)c.obstacle_speed[j];
+  }
 }
 
 int ensure_stage(BallenvHandle* h, int action_kind) {
@@ -331,6 +374,10 @@ int ballenv_create(const BallenvConfig* cfg, int64_t n_envs, int64_t global_env_
   h->device = device;
   h->seed = seed;
   h->L = make_layout(*cfg, n_envs);
+  const char* fg = getenv("BALLENV_FORCE_GENERIC");
+  h->force_generic = fg != nullptr && fg[0] == '1';
+  const char* nr = getenv("BALLENV_NO_ROLLOUT");
+  h->no_rollout = nr != nullptr && nr[0] == '1';
   if (arena != nullptr) {
     if (((uintptr_t)arena & 255) != 0) {
       delete h;
@@ -358,9 +405,13 @@ int ballenv_create(const BallenvConfig* cfg, int64_t n_envs, int64_t global_env_
   const Layout& L = h->L;
   p.n = n_envs;
   p.stride = L.stride;
+  p.stat_stride = L.stat_stride;
+  p.dyn_stride = L.dyn_stride;
   p.g0 = (uint32_t)global_env_offset;
   p.k0 = (uint32_t)(seed & 0xffffffffu);
   p.k1 = (uint32_t)(seed >> 32);
+  const char* dbg = getenv("BALLENV_DEBUG_SKIP");
+  p.debug = dbg != nullptr ? atoi(dbg) : 0;
   char* a = h->arena;
   p.agent_x = a + L.agent_x;
   p.agent_y = a + L.agent_y;
@@ -402,6 +453,8 @@ int ballenv_state_ptrs(BallenvHandle* h, BallenvStatePtrs* out) {
   memset(out, 0, sizeof(*out));
   out->n_envs = h->n;
   out->n_stride = h->L.stride;
+  out->static_stride = h->L.stat_stride;
+  out->dynamic_stride = h->L.dyn_stride;
   out->real_bytes = h->cfg.precision == BALLENV_F64 ? 8 : 4;
   out->obs_row_elems = obs_row_elems(h->cfg);
   out->agent_x = p.agent_x;
@@ -430,6 +483,7 @@ int ballenv_reset(BallenvHandle* h, const uint8_t* mask, void* obs_out, ballenv_
   DeviceGuard guard(h->device);
   Params p = h->base;
   p.mode = kModeReset;
+  p.n_steps = 1;
   p.reset_mask = mask;
   p.obs = obs_out;
   p.reset_tape = h->reset_tape;
@@ -441,6 +495,7 @@ int ballenv_observe(BallenvHandle* h, void* obs_out, ballenv_stream_t stream) {
   DeviceGuard guard(h->device);
   Params p = h->base;
   p.mode = kModeObserve;
+  p.n_steps = 1;
   p.obs = obs_out;
   return launch(h, p, (cudaStream_t)stream);
 }
@@ -452,6 +507,8 @@ int ballenv_step(BallenvHandle* h, const void* actions, int action_kind, void* o
   DeviceGuard guard(h->device);
   Params p = h->base;
   p.mode = kModeStep;
+  p.n_steps = 1;
+  p.obs_all_steps = 0;
   p.actions = actions;
   p.action_kind = action_kind;
   p.obs = obs_out;
@@ -476,6 +533,23 @@ int ballenv_step_many(BallenvHandle* h, const void* actions, int action_kind, in
   const size_t n = (size_t)h->n;
   const size_t obs_row = (size_t)obs_row_elems(h->cfg) * obs_elem_bytes(h->cfg);
   const size_t rew_b = h->cfg.precision == BALLENV_F64 ? 8 : 4;
+  if (n_steps == 0) return BALLENV_OK;
+  {
+    // Open-loop rollout: one launch advances all n_steps with the state held on chip (ballenv_kernel's loop).
+    DeviceGuard guard(h->device);
+    Params p = h->base;
+    p.mode = kModeStep;
+    p.n_steps = n_steps;
+    p.obs_all_steps = obs_all_steps ? 1 : 0;
+    p.actions = actions;
+    p.action_kind = action_kind;
+    p.obs = obs_out;
+    p.reward = reward_out;
+    p.done = done_out;
+    p.reset_tape = h->reset_tape;
+    p.step_tape = h->step_tape;
+    if (!h->no_rollout && fast_eligible(h, p)) return launch(h, p, (cudaStream_t)stream);
+  }
   for (int t = 0; t < n_steps; ++t) {
     void* obs_t = nullptr;
     if (obs_out != nullptr) {

@@ -5,11 +5,14 @@
 #include "ballenv_kernels.cuh"
 
 #ifndef BALLENV_T
-#error "compile with -DBALLENV_T=float|double -DBALLENV_W=0|5|10 -DBALLENV_NAME=..."
+#error "compile with -DBALLENV_T=float|double -DBALLENV_W=0|5|10 -DBALLENV_FAST=0|1 -DBALLENV_NAME=..."
+#endif
+#ifndef BALLENV_FAST
+#define BALLENV_FAST 0
 #endif
 
 namespace ballenv {
 void BALLENV_NAME(const Params& p, unsigned grid, cudaStream_t s) {
-  ballenv_kernel<BALLENV_T, BALLENV_W><<<grid, kBlock, 0, s>>>(p);
+  ballenv_kernel<BALLENV_T, BALLENV_W, (BALLENV_FAST != 0)><<<grid, kBlock, 0, s>>>(p);
 }
 }  // namespace ballenv

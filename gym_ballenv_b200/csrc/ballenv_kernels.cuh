@@ -10,13 +10,27 @@
 //   WINDOW x WINDOW occupancy + goal   examples/ball_cnn_ac3.py:330-352, 384-412 (incl. the row-offset quirk :409)
 //   quadrant observation
 //
-// Mapping: one thread per environment.  State is struct-of-arrays ([K][n] for per-obstacle fields) so every
-// state load/store of a warp is one fully used 128-byte line.  The observation rows are produced as bit
-// vectors in registers, staged in shared memory and expanded by the whole block into 128-bit coalesced
-// stores over the block's contiguous [envs][4 + W*W] output span.  Most obstacles are far from the agent:
-// a bounding-box test rejects them in a handful of instructions and only the rare near ones are rasterised
-// cell by cell with exactly the reference's arithmetic (dx*dx + dy*dy against the radius sum), so the grid is
-// bit-exact by construction.  Nothing here is a dense contraction: no tensor cores.
+// Mapping (B200: 148 SMs want several hundred thousand threads in flight; 64 K environments alone are too few):
+//   * a block of 288 threads owns 32 consecutive environments.  Warp 0 is the scalar warp: thread t owns
+//     environment t's scalars (agent, goal, distance, reward, counters), struct-of-arrays, so every load and
+//     store of the warp is one full 128-byte line.  Warps 1..8 are obstacle lanes, 8 consecutive lanes per
+//     environment.
+//   * obstacles live env-major, [n][K padded to 4]: lane l of an environment owns obstacle quads l, l+8, ...
+//     and moves them with one 128-bit load and one 128-bit store per field (x, y, meta).  A warp touches
+//     4 environments x K contiguous elements per field, i.e. whole 128-byte lines.  One Philox4x32-10 block
+//     feeds the four obstacles of a quad.  Loads, draws, moves and write-back do not depend on the agent and
+//     overlap the scalar warp's load -> move -> clamp chain.
+//   * most obstacles are far from the agent.  Each lane bounding-box tests its obstacles; the rare near ones
+//     are appended to a shared-memory list, and the obstacle warps then rasterise the list one
+//     (obstacle, window row) item per thread with exactly the reference's arithmetic (dx*dx + dy*dy against the
+//     radius sum), OR-ing row masks into the per-environment observation bit-stream in shared memory.  The
+//     grid is therefore bit-exact by construction and the work is balanced no matter where obstacles cluster.
+//     Meanwhile the scalar warp computes distance, reward, flags, done and the episode statistics.
+//   * the block's observation span [32 envs][4 + W*W] is contiguous and 128-byte aligned in global memory; all
+//     threads expand bits into 128-bit coalesced streaming stores.
+//   * environments that finish are reset in the same launch by their own 8 lanes (rejection sampling runs
+//     per obstacle, quads in parallel), followed by a second list raster; blocks without a reset skip this.
+// Nothing here is a dense contraction: no tensor cores.
 #pragma once
 #include <stdint.h>
 
@@ -25,8 +39,18 @@
 
 namespace ballenv {
 
-constexpr int kBlock = 128;  // threads (= environments) per block
-constexpr int kMaxResetAttempts = 4096;  // the reference would loop forever on an unsatisfiable layout
+constexpr int kLanes = 8;                          // lanes per environment
+constexpr int kEnvsPerBlock = 32;                  // = one warp in the thread-per-env scalar phase
+constexpr int kLaneThreads = kLanes * kEnvsPerBlock;   // 256 obstacle threads (warps 1..8)
+constexpr int kBlock = 32 + kLaneThreads;          // + warp 0, the scalar warp: 288 threads
+#ifndef BALLENV_MINBLOCKS
+#define BALLENV_MINBLOCKS 4
+#endif
+template <typename T>
+constexpr int kMinBlocks = sizeof(T) == 4 ? BALLENV_MINBLOCKS : 2; // resident blocks per SM the register budget is held to
+constexpr int kListCap = 768;                      // near-obstacle list entries per block (overflow: in-lane raster)
+constexpr int kMaxResetAttempts = 4096;            // the reference would loop forever on an unsatisfiable layout
+constexpr int kNoHit = 0x7fffffff;
 
 enum Mode : int { kModeStep = 0, kModeReset = 1, kModeObserve = 2 };
 
@@ -36,15 +60,48 @@ struct DevConfig {
   double static_penalty, dynamic_penalty;
   double world_w, world_h, radius_sum, goal_threshold, step_x, step_y;
   double reset_agent_thresh, reset_goal_thresh;  // pygame reset clearances (ballenv_pygame.py:494)
+  double margin;   // bounding-box half-size beyond which an obstacle cannot touch the window or the agent
   double speed[BALLENV_MAX_DYNAMIC];
   double goal_x[BALLENV_MAX_GOALS], goal_y[BALLENV_MAX_GOALS];
+  // fp32 copies so that the production instantiation never converts in the hot loop
+  float f_world_w, f_world_h, f_step_x, f_step_y, f_margin;
+  uint32_t rcp_qs, rcp_qd;   // ceil(2^32 / quads per environment) (0 when there is one quad: identity)
+  float f_speed[BALLENV_MAX_DYNAMIC];
+  float2 f_goal[BALLENV_MAX_GOALS];
+};
+
+template <typename T>
+struct CfgV;
+template <>
+struct CfgV<float> {
+  static __device__ __forceinline__ float world_w(const DevConfig& c) { return c.f_world_w; }
+  static __device__ __forceinline__ float world_h(const DevConfig& c) { return c.f_world_h; }
+  static __device__ __forceinline__ float step_x(const DevConfig& c) { return c.f_step_x; }
+  static __device__ __forceinline__ float step_y(const DevConfig& c) { return c.f_step_y; }
+  static __device__ __forceinline__ float margin(const DevConfig& c) { return c.f_margin; }
+  static __device__ __forceinline__ float speed(const DevConfig& c, int j) { return c.f_speed[j]; }
+  static __device__ __forceinline__ float2 goal(const DevConfig& c, int i) { return c.f_goal[i]; }
+};
+template <>
+struct CfgV<double> {
+  static __device__ __forceinline__ double world_w(const DevConfig& c) { return c.world_w; }
+  static __device__ __forceinline__ double world_h(const DevConfig& c) { return c.world_h; }
+  static __device__ __forceinline__ double step_x(const DevConfig& c) { return c.step_x; }
+  static __device__ __forceinline__ double step_y(const DevConfig& c) { return c.step_y; }
+  static __device__ __forceinline__ double margin(const DevConfig& c) { return c.margin; }
+  static __device__ __forceinline__ double speed(const DevConfig& c, int j) { return c.speed[j]; }
+  static __device__ __forceinline__ double2 goal(const DevConfig& c, int i) { return make_double2(c.goal_x[i], c.goal_y[i]); }
 };
 
 struct Params {
   DevConfig cfg;
-  long long n, stride;
+  long long n, stride;           // environments, element stride of the per-env scalar arrays
+  long long stat_stride, dyn_stride;  // elements per environment row of the obstacle arrays (K padded to 4)
   uint32_t g0, k0, k1;
   int mode, action_kind;
+  int n_steps;        // steps advanced by this launch (rollout loop; > 1 only with the fast specialisation)
+  int obs_all_steps;  // rollout: observation rows of every step ([T][n][row]) or only of the last one ([n][row])
+  int debug;   // BALLENV_DEBUG_SKIP (profiling experiments only): 1 exit, 2 no moves, 4 no near tests, 8 no store, 16 no fp64
   void *agent_x, *agent_y, *goal_x, *goal_y;
   double *dist, *total, *acc;
   int *ep_len;
@@ -105,83 +162,148 @@ struct Overlap<double> {
 template <int W>
 struct Win {
   static constexpr int kMax = W ? W : BALLENV_MAX_WINDOW;
-  static constexpr int kWords = (4 + kMax * kMax + 31) / 32;
+  static constexpr int kWords = (4 + kMax * kMax + 31) / 32;   // per environment, BALLENV_OBS_BITS rows
+  static constexpr int kBlockWords = 4 + kMax * kMax;         // 32 environments x (4 + W*W) bits = 4 + W*W words
   __device__ static __forceinline__ int w(int rt) { return W ? W : rt; }
 };
 
-// ---- window raster of one obstacle (examples/ball_cnn_ac3.py:396-409) ----------------------------------------
-// Column c samples x = start_x + step_x * c.  Row 0 and row 1 both sample start_y; row r >= 1 samples
-// start_y + step_y * (r - 1) because the reference advances cur_y after the column loop with the current r.
-template <typename T, int W>
-__device__ __forceinline__ void raster_obstacle(T ox, T oy, T start_x, T start_y, T step_x, T step_y, int w,
-                                                const Overlap<T>& ov, uint32_t* rows) {
-  if constexpr (W == 0) {  // any window size up to 32: plain loops
-    for (int r = (w > 1 ? 1 : 0); r < w; ++r) {
-      const T dy = r_sub(r_add(start_y, r_mul(step_y, (T)(r > 0 ? r - 1 : 0))), oy);
-      uint32_t m = 0;
-      for (int c = 0; c < w; ++c) {
-        const T dx = r_sub(r_add(start_x, r_mul(step_x, (T)c)), ox);
-        m |= (ov(dx, dy) ? 1u : 0u) << c;
-      }
-      rows[r] |= m;
-      if (r <= 1) rows[0] |= m;
-    }
-  } else {                 // W = 5 / 10: fully unrolled, rows stay in registers
-    T dxs[W];
-#pragma unroll
-    for (int c = 0; c < W; ++c) dxs[c] = r_sub(r_add(start_x, r_mul(step_x, (T)c)), ox);
-#pragma unroll
-    for (int r = 1; r < W; ++r) {
-      const T dy = r_sub(r_add(start_y, r_mul(step_y, (T)(r - 1))), oy);
-      uint32_t m = 0;
-#pragma unroll
-      for (int c = 0; c < W; ++c) m |= (ov(dxs[c], dy) ? 1u : 0u) << c;
-      rows[r] |= m;
-      if (r == 1) rows[0] |= m;
-    }
-  }
+// ---- 128-bit quad access -------------------------------------------------------------------------------------
+__device__ __forceinline__ void load4(const float* p, float (&v)[4]) {
+  const float4 t = *reinterpret_cast<const float4*>(p);
+  v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+__device__ __forceinline__ void load4(const double* p, double (&v)[4]) {
+  const double2 a = reinterpret_cast<const double2*>(p)[0], b = reinterpret_cast<const double2*>(p)[1];
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+__device__ __forceinline__ void load4(const uint32_t* p, uint32_t (&v)[4]) {
+  const uint4 t = *reinterpret_cast<const uint4*>(p);
+  v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+__device__ __forceinline__ void store4(float* p, const float (&v)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void store4(double* p, const double (&v)[4]) {
+  reinterpret_cast<double2*>(p)[0] = make_double2(v[0], v[1]);
+  reinterpret_cast<double2*>(p)[1] = make_double2(v[2], v[3]);
+}
+__device__ __forceinline__ void store4(uint32_t* p, const uint32_t (&v)[4]) {
+  *reinterpret_cast<uint4*>(p) = make_uint4(v[0], v[1], v[2], v[3]);
 }
 
-// Per-thread view of one environment while it is being processed.
+// ---- window raster (examples/ball_cnn_ac3.py:396-409) ----------------------------------------------------------
+// Column c samples x = start_x + step_x * c.  Output row 0 and row 1 both sample y index 0 (start_y); row r >= 1
+// samples start_y + step_y * (r - 1), because the reference advances cur_y after the column loop with the
+// current r.  One "item" is (obstacle, y index yi): its column mask goes to row yi + 1 and, for yi = 0, row 0.
 template <typename T, int W>
-struct EnvCtx {
-  T ax, ay, gx, gy;          // agent / goal
-  T start_x, start_y;        // window origin
-  T step_x, step_y;          // cell pitch = agent speed (examples/ball_cnn_ac3.py:390-391)
-  T margin;                  // bounding-box half-size beyond which an obstacle cannot touch the window
-  uint32_t rows[Win<W>::kMax];
-  int hit_first;             // index (list order) of the first obstacle hit, or INT_MAX
-};
-
-template <typename T, int W>
-__device__ __forceinline__ void ctx_set_agent(EnvCtx<T, W>& c, const DevConfig& cfg, T ax, T ay) {
-  const int w = Win<W>::w(cfg.window);
-  const int h = w / 2;
-  c.ax = ax;
-  c.ay = ay;
-  c.step_x = (T)cfg.step_x;
-  c.step_y = (T)cfg.step_y;
-  c.start_x = r_sub(ax, r_mul(c.step_x, (T)h));
-  c.start_y = r_sub(ay, r_mul(c.step_y, (T)h));
-  const double st = cfg.step_x > cfg.step_y ? cfg.step_x : cfg.step_y;
-  c.margin = (T)(cfg.radius_sum + st * (double)h + 2.0);
+__device__ __forceinline__ uint32_t raster_row(T ox, T oy, T start_x, T start_y, T step_x, T step_y, int yi, int w,
+                                               const Overlap<T>& ov) {
+  const T dy = r_sub(r_add(start_y, r_mul(step_y, (T)yi)), oy);
+  uint32_t m = 0;
   if constexpr (W == 0) {
-    for (int r = 0; r < w; ++r) c.rows[r] = 0;
+    for (int c = 0; c < w; ++c) m |= (ov(r_sub(r_add(start_x, r_mul(step_x, (T)c)), ox), dy) ? 1u : 0u) << c;
   } else {
 #pragma unroll
-    for (int r = 0; r < W; ++r) c.rows[r] = 0;
+    for (int c = 0; c < W; ++c) m |= (ov(r_sub(r_add(start_x, r_mul(step_x, (T)c)), ox), dy) ? 1u : 0u) << c;
   }
-  c.hit_first = 0x7fffffff;
+  return m;
 }
 
-// Test one obstacle (list index k) against the agent and, if it can touch the window, rasterise it.
+// OR a row mask of w bits into the bit-stream at bit offset off (shared memory, concurrent writers).
+__device__ __forceinline__ void emit_bits(uint32_t* words, int off, int w, uint32_t m) {
+  if (m == 0) return;
+  const int sh = off & 31;
+  atomicOr(&words[off >> 5], m << sh);
+  if (sh + w > 32) {
+    const uint32_t hi = m >> (32 - sh);
+    if (hi) atomicOr(&words[(off >> 5) + 1], hi);
+  }
+}
+
+// words is the block's bit-stream (environment el owns bits [el * nb, (el + 1) * nb)); base = el * nb.
 template <typename T, int W>
-__device__ __forceinline__ void ctx_obstacle(EnvCtx<T, W>& c, const DevConfig& cfg, const Overlap<T>& ov, T ox,
-                                             T oy, int k) {
-  const T ddx = r_sub(c.ax, ox), ddy = r_sub(c.ay, oy);
-  if (r_abs(ddx) <= c.margin && r_abs(ddy) <= c.margin) {
-    if (ov(ddx, ddy) && k < c.hit_first) c.hit_first = k;
-    raster_obstacle<T, W>(ox, oy, c.start_x, c.start_y, c.step_x, c.step_y, Win<W>::w(cfg.window), ov, c.rows);
+__device__ __forceinline__ void raster_item(uint32_t* words, int base, T ox, T oy, T ax, T ay, T step_x, T step_y,
+                                            int yi, int w, const Overlap<T>& ov) {
+  const int h = w / 2;
+  const T start_x = r_sub(ax, r_mul(step_x, (T)h)), start_y = r_sub(ay, r_mul(step_y, (T)h));
+  const uint32_t m = raster_row<T, W>(ox, oy, start_x, start_y, step_x, step_y, yi, w, ov);
+  if (yi + 1 < w) emit_bits(words, base + 4 + (yi + 1) * w, w, m);
+  if (yi == 0) emit_bits(words, base + 4, w, m);
+}
+
+template <typename T>
+struct Vec2;
+template <>
+struct Vec2<float> { typedef float2 type; };
+template <>
+struct Vec2<double> { typedef double2 type; };
+
+// Shared-memory state of one block.
+template <typename T, int W>
+struct BlockShared {
+  // observation bits of the block as ONE stream: environment el owns bits [el * nb, (el + 1) * nb), nb = 4 + W*W
+  // (4 goal-quadrant bits, then the W*W cells), so output element f of the block's span is bit f.
+  uint32_t words[2][Win<W>::kBlockWords];           // double-buffered by step parity (see the rollout loop)
+  T ax[kEnvsPerBlock], ay[kEnvsPerBlock];            // agent position the window is centred on
+  int hit[kEnvsPerBlock];                            // list index of the first obstacle hit, or kNoHit
+  int reset[kEnvsPerBlock];
+  T near_x[kListCap], near_y[kListCap];              // near-obstacle list
+  uint8_t near_env[kListCap];
+  int count;
+  typename Vec2<T>::type goal[BALLENV_MAX_GOALS];    // obstacle goals (args.obs_goal_position)
+  typename Vec2<T>::type mv[12];                     // obstacle move table (ballenv_env.py:324)
+  float4 lut[16];                                    // 4 observation bits -> 4 floats
+  // scalar-warp state parked between its two stages (keeps it out of the obstacle threads' register budget)
+  T s_gx[kEnvsPerBlock], s_gy[kEnvsPerBlock], s_oax[kEnvsPerBlock], s_oay[kEnvsPerBlock];
+  double s_old[kEnvsPerBlock], s_total[kEnvsPerBlock], s_acc[kEnvsPerBlock];
+  int s_len[kEnvsPerBlock];
+  uint32_t s_tick[kEnvsPerBlock];
+};
+
+// Rare path of the bounding-box test: hit-test the obstacle and queue it for the raster.
+template <typename T, int W>
+__device__ __noinline__ void near_push(BlockShared<T, W>& sh, uint32_t* words, const DevConfig& cfg, int el, T ax, T ay,
+                                       T ox, T oy, int k, bool want_hit, bool want_obs, int nb) {
+  const Overlap<T> ov(cfg.radius_sum);
+  if (want_hit && ov(r_sub(ax, ox), r_sub(ay, oy))) atomicMin(&sh.hit[el], k);
+  if (want_obs) {
+    const int idx = atomicAdd(&sh.count, 1);
+    if (idx < kListCap) {
+      sh.near_x[idx] = ox;
+      sh.near_y[idx] = oy;
+      sh.near_env[idx] = (uint8_t)el;
+    } else {  // list full (obstacles piled up on the agents of this block): rasterise in-lane
+      const int w = Win<W>::w(cfg.window);
+      const int nyi = w > 1 ? w - 1 : 1;
+      for (int yi = 0; yi < nyi; ++yi)
+        raster_item<T, W>(words, el * nb, ox, oy, ax, ay, CfgV<T>::step_x(cfg), CfgV<T>::step_y(cfg), yi, w, ov);
+    }
+  }
+}
+
+// Bounding-box test of one obstacle against the agent (a handful of instructions; almost always false).
+template <typename T, int W>
+__device__ __forceinline__ void near_test(BlockShared<T, W>& sh, uint32_t* words, const DevConfig& cfg, int el, T ax,
+                                          T ay, T margin, T ox, T oy, int k, bool want_hit, bool want_obs, int nb) {
+  if (r_abs(r_sub(ax, ox)) <= margin && r_abs(r_sub(ay, oy)) <= margin)
+    near_push<T, W>(sh, words, cfg, el, ax, ay, ox, oy, k, want_hit, want_obs, nb);
+}
+
+// Obstacle threads (lt = 0 .. kLaneThreads-1): rasterise the queued (obstacle, row) items.
+template <typename T, int W>
+__device__ __forceinline__ void raster_list(BlockShared<T, W>& sh, uint32_t* words, const DevConfig& cfg, int lt,
+                                            int nb) {
+  const int cnt = sh.count < kListCap ? sh.count : kListCap;
+  if (cnt == 0) return;
+  const Overlap<T> ov(cfg.radius_sum);
+  const int w = Win<W>::w(cfg.window);
+  const int nyi = w > 1 ? w - 1 : 1;
+  const int items = cnt * nyi;
+  const T step_x = CfgV<T>::step_x(cfg), step_y = CfgV<T>::step_y(cfg);
+  for (int it = lt; it < items; it += kLaneThreads) {
+    const int en = it / nyi, yi = it - en * nyi;
+    const int el = sh.near_env[en];
+    raster_item<T, W>(words, el * nb, sh.near_x[en], sh.near_y[en], sh.ax[el], sh.ay[el], step_x, step_y, yi, w, ov);
   }
 }
 
@@ -231,92 +353,73 @@ struct DrawCtx {
   }
 };
 
-template <typename T>
-__device__ __forceinline__ T* col(void* base, long long k, long long stride) {
-  return reinterpret_cast<T*>(base) + k * stride;
-}
-
 // ---- reset (ballenv_env.py:113-167 / ballenv_pygame.py:460-513) ------------------------------------------------
-// Writes the new obstacle set of env e to global memory, rasterises it into ctx and returns the scalars.
-template <typename T, int W>
-__device__ __forceinline__ void reset_env(const Params& p, const DrawCtx& dc, const Overlap<T>& ov, uint32_t episode,
-                                       EnvCtx<T, W>& c, double& dist, double& total) {
+// Head of a reset: goal and agent position, state[2] and total_distance.  Every lane of the environment
+// evaluates it (same address, same words), so no exchange is needed.
+template <typename T>
+struct ResetHead {
+  T gx, gy, ax, ay;
+  double dist, total;
+};
+
+template <typename T>
+__device__ __noinline__ ResetHead<T> reset_head_draw(const Params& p, const DrawCtx& dc, uint32_t episode) {
   const DevConfig& cfg = p.cfg;
-  const long long e = dc.e, S = p.stride;
+  ResetHead<T> r;
   if (cfg.ruleset == BALLENV_RULESET_GYM) {
     const uint4 hw = dc.reset_head(episode, 0);
-    const T gx = (T)__umulhi(hw.x, 500u), gy = (T)(480u + __umulhi(hw.y, 20u));  // :115-116
-    const T ax = (T)__umulhi(hw.z, 500u), ay = (T)__umulhi(hw.w, 10u);           // :117-118
+    r.gx = (T)__umulhi(hw.x, 500u);                                              // :115-116
+    r.gy = (T)(480u + __umulhi(hw.y, 20u));
+    r.ax = (T)__umulhi(hw.z, 500u);                                              // :117-118
+    r.ay = (T)__umulhi(hw.w, 10u);
     // The redraw-while-closer-than-50 loop (:121-126) cannot trigger: goal_y - agent_y >= 471.
-    dist = dist64((double)gx, (double)gy, (double)ax, (double)ay);               // :119
-    total = dist;                                                                // :166 (same points)
-    c.gx = gx;
-    c.gy = gy;
-    ctx_set_agent<T, W>(c, cfg, ax, ay);
-    for (int i = 0; i < cfg.ks; ++i) {                                           // :131-149
-      T x, y;
-      for (int attempt = 0;; ++attempt) {
-        const uint2 w2 = dc.reset_static(episode, i, attempt);
-        x = (T)__umulhi(w2.x, 500u);                                             // :24
-        y = (T)(20u + __umulhi(w2.y, 460u));                                     // :25
-        // check_overlap_rect (:193-197): |dx| < 20 + 5 and |dy| < 20/2 + 5
-        const bool ra = fabs((double)x - (double)ax) < 25.0 && fabs((double)y - (double)ay) < 15.0;
-        const bool rg = fabs((double)x - (double)gx) < 25.0 && fabs((double)y - (double)gy) < 15.0;
-        if (!ra && !rg) break;
-        if (attempt >= kMaxResetAttempts) {
-          atomicOr(p.errors, (uint32_t)BALLENV_DEVERR_RESET_STUCK);
-          break;
-        }
-      }
-      col<T>(p.stat_x, i, S)[e] = x;
-      col<T>(p.stat_y, i, S)[e] = y;
-      ctx_obstacle<T, W>(c, cfg, ov, x, y, i);
-    }
-    for (int j = 0; j < cfg.kd; ++j) {                                           // :153-164
-      const uint2 w2 = dc.reset_dynamic(episode, j);
-      const T x = (T)__umulhi(w2.x, 500u), y = (T)(20u + __umulhi(w2.y, 460u));
-      col<T>(p.dyn_x, j, S)[e] = x;
-      col<T>(p.dyn_y, j, S)[e] = y;
-      p.dyn_meta[(long long)j * S + e] = (uint32_t)j;  // curr_goal = goal_list[j], curr_counter = 0
-      ctx_obstacle<T, W>(c, cfg, ov, x, y, cfg.ks + j);
-    }
+    r.dist = dist64((double)r.gx, (double)r.gy, (double)r.ax, (double)r.ay);     // :119
+    r.total = r.dist;                                                            // :166 (same points)
   } else {
     // pygame ruleset: uniform float positions (ballenv_pygame.py:468-482, 454-457)
     uint4 hw = dc.reset_head(episode, 0);
-    const double gxd = 0.0 + ranf_from_words(hw.x, hw.y) * (cfg.world_w - 0.0);
-    const double gyd = 0.0 + ranf_from_words(hw.z, hw.w) * (cfg.world_h - 0.0);
+    r.gx = (T)(0.0 + ranf_from_words(hw.x, hw.y) * (cfg.world_w - 0.0));
+    r.gy = (T)(0.0 + ranf_from_words(hw.z, hw.w) * (cfg.world_h - 0.0));
     hw = dc.reset_head(episode, 1);
-    double axd = 0.0 + ranf_from_words(hw.x, hw.y) * (cfg.world_w - 0.0);
-    double ayd = 0.0 + ranf_from_words(hw.z, hw.w) * (cfg.world_h - 0.0);
-    const T gx = (T)gxd, gy = (T)gyd;
-    T ax = (T)axd, ay = (T)ayd;
-    dist = dist64((double)gx, (double)gy, (double)ax, (double)ay);               // :474, kept even if redrawn (:482)
-    for (uint32_t attempt = 0; dist64((double)gx, (double)gy, (double)ax, (double)ay) < 50.0; ++attempt) {  // :476-481
+    r.ax = (T)(0.0 + ranf_from_words(hw.x, hw.y) * (cfg.world_w - 0.0));
+    r.ay = (T)(0.0 + ranf_from_words(hw.z, hw.w) * (cfg.world_h - 0.0));
+    r.dist = dist64((double)r.gx, (double)r.gy, (double)r.ax, (double)r.ay);     // :474, kept even if redrawn (:482)
+    for (uint32_t attempt = 0; dist64((double)r.gx, (double)r.gy, (double)r.ax, (double)r.ay) < 50.0; ++attempt) {  // :476-481
       hw = dc.reset_block(episode, (kResetAgentRedraw << 28) | attempt);
-      ax = (T)(0.0 + ranf_from_words(hw.x, hw.y) * (cfg.world_w - 0.0));
-      ay = (T)(0.0 + ranf_from_words(hw.z, hw.w) * (cfg.world_h - 0.0));
+      r.ax = (T)(0.0 + ranf_from_words(hw.x, hw.y) * (cfg.world_w - 0.0));
+      r.ay = (T)(0.0 + ranf_from_words(hw.z, hw.w) * (cfg.world_h - 0.0));
     }
-    total = dist64((double)ax, (double)ay, (double)gx, (double)gy);              // :511
-    c.gx = gx;
-    c.gy = gy;
-    ctx_set_agent<T, W>(c, cfg, ax, ay);
-    for (int i = 0; i < cfg.ks; ++i) {                                           // :489-498
-      T x, y;
-      for (int attempt = 0;; ++attempt) {
-        const uint2 w2 = dc.reset_static(episode, i, attempt);
-        x = (T)__umulhi(w2.x, (uint32_t)cfg.world_w);                            // :27
-        y = (T)__umulhi(w2.y, (uint32_t)cfg.world_h);                            // :32
-        const bool oa = !(dist64((double)x, (double)y, (double)ax, (double)ay) - cfg.reset_agent_thresh > cfg.radius_sum);
-        const bool og = !(dist64((double)x, (double)y, (double)gx, (double)gy) - cfg.reset_goal_thresh > cfg.radius_sum);
-        if (!oa && !og) break;                                                   // :494
-        if (attempt >= kMaxResetAttempts) {
-          atomicOr(p.errors, (uint32_t)BALLENV_DEVERR_RESET_STUCK);
-          break;
-        }
-      }
-      col<T>(p.stat_x, i, S)[e] = x;
-      col<T>(p.stat_y, i, S)[e] = y;
-      ctx_obstacle<T, W>(c, cfg, ov, x, y, i);
+    r.total = dist64((double)r.ax, (double)r.ay, (double)r.gx, (double)r.gy);    // :511
+  }
+  return r;
+}
+
+// Static obstacle i: redraw until it clears the agent and the goal (ballenv_env.py:131-149 | ballenv_pygame.py:489-498).
+template <typename T>
+__device__ __noinline__ void reset_static_draw(const Params& p, const DrawCtx& dc, uint32_t episode, int i,
+                                               const ResetHead<T>& h, T& x, T& y) {
+  const DevConfig& cfg = p.cfg;
+  for (int attempt = 0;; ++attempt) {
+    const uint2 w2 = dc.reset_static(episode, i, attempt);
+    bool ok;
+    if (cfg.ruleset == BALLENV_RULESET_GYM) {
+      x = (T)__umulhi(w2.x, 500u);                                               // :24
+      y = (T)(20u + __umulhi(w2.y, 460u));                                       // :25
+      // check_overlap_rect (:193-197): |dx| < 20 + 5 and |dy| < 20/2 + 5
+      const bool ra = fabs((double)x - (double)h.ax) < 25.0 && fabs((double)y - (double)h.ay) < 15.0;
+      const bool rg = fabs((double)x - (double)h.gx) < 25.0 && fabs((double)y - (double)h.gy) < 15.0;
+      ok = !ra && !rg;
+    } else {
+      x = (T)__umulhi(w2.x, (uint32_t)cfg.world_w);                              // ballenv_pygame.py:27
+      y = (T)__umulhi(w2.y, (uint32_t)cfg.world_h);                              // :32
+      const bool oa = !(dist64((double)x, (double)y, (double)h.ax, (double)h.ay) - cfg.reset_agent_thresh > cfg.radius_sum);
+      const bool og = !(dist64((double)x, (double)y, (double)h.gx, (double)h.gy) - cfg.reset_goal_thresh > cfg.radius_sum);
+      ok = !oa && !og;                                                           // :494
+    }
+    if (ok) return;
+    if (attempt >= kMaxResetAttempts) {
+      atomicOr(p.errors, (uint32_t)BALLENV_DEVERR_RESET_STUCK);
+      return;
     }
   }
 }
@@ -334,13 +437,13 @@ constexpr uint32_t kAgentDy = 2u | 0u << 2 | 1u << 4 | 2u << 6 | 0u << 8 | 1u <<
 __device__ __forceinline__ int table2(uint32_t packed, uint32_t i) { return (int)((packed >> (2 * i)) & 3u) - 1; }
 
 template <typename T>
-__device__ __forceinline__ void move_obstacle(const DevConfig& cfg, const double* s_goal_x, const double* s_goal_y,
-                                              int j, uint32_t w1, uint32_t w2_tape, bool has_tape, T& x, T& y,
-                                              uint32_t& meta) {
+__device__ __noinline__ void move_obstacle(const DevConfig& cfg, const typename Vec2<T>::type* s_goal, int j,
+                                           uint32_t w1, uint32_t w2_tape, bool has_tape, T& x, T& y,
+                                           uint32_t& meta) {
   uint32_t gi = meta & 0xffu, cnt = meta >> 8;
   const T s = (T)cfg.speed[j];
   if ((int)cnt < cfg.change_step) {                                   // :327
-    const T tx = r_sub((T)s_goal_x[gi], x), ty = r_sub((T)s_goal_y[gi], y);   // :329-330
+    const T tx = r_sub(s_goal[gi].x, x), ty = r_sub(s_goal[gi].y, y); // :329-330
     int mx, my;
     if (tx != (T)0 && ty != (T)0) {                                   // :331
       if ((int)__umulhi(w1, 100u) < cfg.rd_th) {                      // :332
@@ -365,12 +468,12 @@ __device__ __forceinline__ void move_obstacle(const DevConfig& cfg, const double
       const uint32_t m = __umulhi(w1, (uint32_t)(cfg.n_goals - 1));
       gi = m + (m >= gi ? 1u : 0u);
     } else {
-      const double cx = s_goal_x[gi], cy = s_goal_y[gi];
+      const T cx = s_goal[gi].x, cy = s_goal[gi].y;
       int others = 0;
-      for (int k = 0; k < cfg.n_goals; ++k) others += (s_goal_x[k] != cx || s_goal_y[k] != cy) ? 1 : 0;
+      for (int k = 0; k < cfg.n_goals; ++k) others += (s_goal[k].x != cx || s_goal[k].y != cy) ? 1 : 0;
       int m = (int)__umulhi(w1, (uint32_t)others);
       for (int k = 0; k < cfg.n_goals; ++k) {
-        if (s_goal_x[k] != cx || s_goal_y[k] != cy) {
+        if (s_goal[k].x != cx || s_goal[k].y != cy) {
           if (m == 0) {
             gi = (uint32_t)k;
             break;
@@ -384,320 +487,677 @@ __device__ __forceinline__ void move_obstacle(const DevConfig& cfg, const double
   meta = gi | (cnt << 8);
 }
 
-// ---- observation store ------------------------------------------------------------------------------------------
-// words_s holds, per env of the block, the 4 + W*W observation bits in output order.  The block's output span
-// [e0, e0 + cnt) x row is contiguous in global memory and starts 16-byte aligned (e0 is a multiple of 128).
-template <int W>
-__device__ __forceinline__ void store_obs(const Params& p, const uint32_t* words_s, long long e0, int cnt) {
-  constexpr int NWc = Win<W>::kWords;
-  const int w = Win<W>::w(p.cfg.window);
-  const int nb = 4 + w * w;
-  const int nw = W ? NWc : (nb + 31) / 32;
-  const int tid = threadIdx.x;
-  if (p.cfg.obs_format == BALLENV_OBS_F32) {
-    float* base = reinterpret_cast<float*>(p.obs) + e0 * nb;
-    const int total = cnt * nb, nvec = total >> 2;
-    float4* dst = reinterpret_cast<float4*>(base);
-    for (int v = tid; v < nvec; v += kBlock) {
-      const int f0 = v * 4;
-      float4 o;
-      if (W != 0 && ((4 + W * W) % 4 == 0)) {
-        const int env = f0 / nb, b0 = f0 - env * nb;  // the 4 bits share a word (b0 % 4 == 0)
-        const uint32_t nib = words_s[env * nw + (b0 >> 5)] >> (b0 & 31);
-        o.x = (nib & 1u) ? 1.0f : 0.0f;
-        o.y = (nib & 2u) ? 1.0f : 0.0f;
-        o.z = (nib & 4u) ? 1.0f : 0.0f;
-        o.w = (nib & 8u) ? 1.0f : 0.0f;
-      } else {
-        float t[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int f = f0 + k, env = f / nb, b = f - env * nb;
-          t[k] = ((words_s[env * nw + (b >> 5)] >> (b & 31)) & 1u) ? 1.0f : 0.0f;
-        }
-        o = make_float4(t[0], t[1], t[2], t[3]);
-      }
-      dst[v] = o;
-    }
-    for (int f = nvec * 4 + tid; f < total; f += kBlock) {
-      const int env = f / nb, b = f - env * nb;
-      base[f] = ((words_s[env * nw + (b >> 5)] >> (b & 31)) & 1u) ? 1.0f : 0.0f;
-    }
-  } else if (p.cfg.obs_format == BALLENV_OBS_U8) {
-    uint8_t* base = reinterpret_cast<uint8_t*>(p.obs) + e0 * nb;
-    const int total = cnt * nb, nvec = total >> 2;
-    uint32_t* dst = reinterpret_cast<uint32_t*>(base);  // e0 * nb is a multiple of 4
-    for (int v = tid; v < nvec; v += kBlock) {
-      uint32_t o = 0;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int f = v * 4 + k, env = f / nb, b = f - env * nb;
-        o |= ((words_s[env * nw + (b >> 5)] >> (b & 31)) & 1u) << (8 * k);
-      }
-      dst[v] = o;
-    }
-    for (int f = nvec * 4 + tid; f < total; f += kBlock) {
-      const int env = f / nb, b = f - env * nb;
-      base[f] = (uint8_t)((words_s[env * nw + (b >> 5)] >> (b & 31)) & 1u);
-    }
-  } else {  // BALLENV_OBS_BITS
-    uint32_t* base = reinterpret_cast<uint32_t*>(p.obs) + e0 * nw;
-    for (int i = tid; i < cnt * nw; i += kBlock) base[i] = words_s[i];
+// Hot-path form of move_obstacle for distinct goals: select instead of branch; x + m * s as one FMA, which
+// rounds like r_add(x, r_mul(m, s)) because m is -1, 0 or 1 and the product is therefore exact.
+template <typename T, int W>
+__device__ __forceinline__ void move_lean(const DevConfig& cfg, const BlockShared<T, W>& sh, int j, uint32_t w1,
+                                          uint32_t w2, T& x, T& y, uint32_t& meta) {
+  const uint32_t gi = meta & 0xffu;
+  const typename Vec2<T>::type gl = sh.goal[gi];
+  const T tx = r_sub(gl.x, x), ty = r_sub(gl.y, y);                    // :329-330
+  const bool diag = tx != (T)0 && ty != (T)0;                          // :331
+  const bool seek = diag && (int)__umulhi(w1, 100u) < cfg.rd_th;       // :332
+  const uint32_t i = __umulhi(diag ? w2 : w1, 9u);                     // :340 / :345
+  const typename Vec2<T>::type mv = sh.mv[i];
+  T mx = mv.x, my = mv.y;
+  if (seek) {                                                          // :334-335  tempx / abs(tempx)
+    mx = tx > (T)0 ? (T)1 : (T)-1;
+    my = ty > (T)0 ? (T)1 : (T)-1;
+  }
+  if ((int)(meta >> 8) < cfg.change_step) {                            // :327
+    const T s = CfgV<T>::speed(cfg, j);
+    x = fma(mx, s, x);
+    y = fma(my, s, y);
+    meta += 256u;                                                      // :348
+  } else {                                                             // :349-353 pick another goal, do not move
+    const uint32_t m = __umulhi(w1, (uint32_t)(cfg.n_goals - 1));
+    meta = m + (m >= gi ? 1u : 0u);
   }
 }
 
-// ---- the kernel ---------------------------------------------------------------------------------------------------
+// ---- observation store ------------------------------------------------------------------------------------------
+// The block's output span [e0, e0 + cnt) x (4 + W*W) elements is contiguous in global memory, starts 128-byte
+// aligned (e0 is a multiple of 32), and element f of it is bit f of the block's bit-stream.  Four consecutive
+// elements are therefore one aligned nibble: a 16-entry float4 table turns it into one 128-bit streaming store.
+__device__ __forceinline__ uint32_t stream_bits(const uint32_t* words, int bit, int nbits_total_words) {
+  // 32 bits of the stream starting at `bit` (reads at most one word past the start word, clamped)
+  const int wi = bit >> 5, sh = bit & 31;
+  const uint32_t lo = words[wi], hi = (wi + 1 < nbits_total_words) ? words[wi + 1] : 0u;
+  return __funnelshift_r(lo, hi, sh);
+}
+
+template <int W, bool kFast>
+__device__ __forceinline__ void store_obs(const Params& p, void* obs, const uint32_t* words, const float4* lut,
+                                          long long e0, int cnt) {
+  const int w = Win<W>::w(p.cfg.window);
+  const int nb = 4 + w * w;
+  const int tid = threadIdx.x;
+  const int total = cnt * nb, nvec = total >> 2;
+  if (kFast || p.cfg.obs_format == BALLENV_OBS_F32) {
+    float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(obs) + e0 * nb);
+    for (int v = tid; v < nvec; v += kBlock)   // streaming store: the rollout buffer is not re-read by this kernel
+      __stcs(dst + v, lut[(words[v >> 3] >> ((v & 7) << 2)) & 15u]);
+    for (int f = (nvec << 2) + tid; f < total; f += kBlock)   // only when the last block ends on an odd boundary
+      reinterpret_cast<float*>(obs)[e0 * nb + f] = (words[f >> 5] >> (f & 31)) & 1u ? 1.0f : 0.0f;
+  } else if (p.cfg.obs_format == BALLENV_OBS_U8) {
+    uint32_t* dst = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(obs) + e0 * nb);
+    for (int v = tid; v < nvec; v += kBlock) {
+      const uint32_t nib = (words[v >> 3] >> ((v & 7) << 2)) & 15u;
+      dst[v] = (nib & 1u) | (nib & 2u) << 7 | (nib & 4u) << 14 | (nib & 8u) << 21;
+    }
+    for (int f = (nvec << 2) + tid; f < total; f += kBlock)
+      reinterpret_cast<uint8_t*>(obs)[e0 * nb + f] = (uint8_t)((words[f >> 5] >> (f & 31)) & 1u);
+  } else {  // BALLENV_OBS_BITS: [n][ceil(nb / 32)] words, bit b of row e = element b of environment e
+    const int nw = (nb + 31) >> 5;
+    uint32_t* base = reinterpret_cast<uint32_t*>(obs) + e0 * nw;
+    for (int i = tid; i < cnt * nw; i += kBlock) {
+      const int en = i / nw, k = i - en * nw;
+      uint32_t v = stream_bits(words, en * nb + 32 * k, nb);
+      const int left = nb - 32 * k;
+      if (left < 32) v &= (1u << left) - 1u;
+      base[i] = v;
+    }
+  }
+}
+
+__device__ __forceinline__ int goal_quadrant_bit(bool dx_neg, bool dy_neg) {
+  // prep_state2 (examples/ball_cnn_ac3.py:341-350): idx1 dx>=0,dy>=0 ; idx0 dx<0,dy>=0 ; idx3 dx<0,dy<0 ; idx2 else
+  return (!dx_neg && !dy_neg) ? 1 : ((dx_neg && !dy_neg) ? 0 : ((dx_neg && dy_neg) ? 3 : 2));
+}
+
+// Dynamic quad at element offset off: 128-bit loads of x, y (and meta when stepping) ...
+template <typename T>
+__device__ __forceinline__ void dynamic_load(const Params& p, uint32_t off, bool stepping, T (&x)[4], T (&y)[4],
+                                             uint32_t (&meta)[4]) {
+  load4(reinterpret_cast<const T*>(p.dyn_x) + off, x);
+  load4(reinterpret_cast<const T*>(p.dyn_y) + off, y);
+  if (stepping) load4(p.dyn_meta + off, meta);
+}
+
+// ... then one Philox block and four moves, in registers (ballenv_env.py:262-264, 323-353) ...
+// kFast: Philox draws (no tape) and distinct goals - the production case, with the uniform tests hoisted out of
+// the per-obstacle code.
+template <typename T, int W, bool kFast>
+__device__ __forceinline__ void dynamic_move(const Params& p, const BlockShared<T, W>& sh, long long e, int jq,
+                                             uint32_t tick, T (&x)[4], T (&y)[4], uint32_t (&meta)[4]) {
+  const DevConfig& cfg = p.cfg;
+  const bool has_tape = !kFast && p.step_tape != nullptr;
+  uint4 blk = make_uint4(0, 0, 0, 0);
+  if (!has_tape) blk = philox4x32_10(p.g0 + (uint32_t)e, tick, (uint32_t)jq, kStreamStep, p.k0, p.k1);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int j = 4 * jq + i;
+    if (kFast) {
+      const uint32_t w1 = pick_word(blk, i);
+      if (j < cfg.kd) move_lean<T, W>(cfg, sh, j, w1, w1 * 100u, x[i], y[i], meta[i]);
+    } else if (j < cfg.kd) {
+      uint32_t w1 = pick_word(blk, i), w2 = w1 * 100u;   // second draw: unused low half of w1 * 100
+      if (has_tape) {
+        const uint2 tw = reinterpret_cast<const uint2*>(p.step_tape)[e * cfg.kd + j];
+        w1 = tw.x;
+        w2 = tw.y;
+      }
+      if (cfg.goals_distinct) move_lean<T, W>(cfg, sh, j, w1, w2, x[i], y[i], meta[i]);
+      else {   // out-of-line generic path: temporaries keep the quad arrays themselves in registers
+        T tx = x[i], ty = y[i];
+        uint32_t tm = meta[i];
+        move_obstacle<T>(cfg, sh.goal, j, w1, w2, true, tx, ty, tm);
+        x[i] = tx;
+        y[i] = ty;
+        meta[i] = tm;
+      }
+    }
+  }
+}
+
+// ... and the 128-bit write-back.
+template <typename T>
+__device__ __forceinline__ void dynamic_store(const Params& p, uint32_t off, const T (&x)[4], const T (&y)[4],
+                                              const uint32_t (&meta)[4]) {
+  store4(reinterpret_cast<T*>(p.dyn_x) + off, x);
+  store4(reinterpret_cast<T*>(p.dyn_y) + off, y);
+  store4(p.dyn_meta + off, meta);
+}
+
+// slot / per for slot * per < 2^32, per >= 1, with rcp = ceil(2^32 / per) (rcp == 0 encodes per == 1)
+__device__ __forceinline__ int div_slot(int slot, uint32_t rcp) {
+  return rcp == 0 ? slot : (int)__umulhi((uint32_t)slot, rcp);
+}
+
+// ---- stage D of the kernel (rare): (auto-)reset ---------------------------------------------------------------------
+// Kept out of line so that its register needs (Philox blocks, rejection loops, fp64 distances) do not count
+// against the per-step path.  Every obstacle thread takes quads of resetting environments (same slot space as
+// the step); the observation of a finished environment becomes the first observation of its next episode.
 template <typename T, int W>
-__global__ void __launch_bounds__(kBlock) ballenv_kernel(const __grid_constant__ Params p) {
-  constexpr int NWc = Win<W>::kWords;
-  __shared__ uint32_t words_s[kBlock * NWc];
-  __shared__ double s_goal_x[BALLENV_MAX_GOALS], s_goal_y[BALLENV_MAX_GOALS];
+__device__ __noinline__ void reset_stage(const Params& p, BlockShared<T, W>& sh, uint32_t* words, long long e0,
+                                         int cnt_env, bool want_obs) {
   const DevConfig& cfg = p.cfg;
   const int tid = threadIdx.x;
-  const long long e0 = (long long)blockIdx.x * kBlock;
-  const long long e = e0 + tid;
-  const long long S = p.stride;
+  const bool is_scalar = tid < 32;
+  const int lt = tid - 32;
   const int w = Win<W>::w(cfg.window);
   const int nb = 4 + w * w;
-  const int nw = W ? NWc : (nb + 31) / 32;
+  const int ks = cfg.ks, kd = cfg.kd;
+  const int qs = (ks + 3) >> 2, qd = (kd + 3) >> 2;
+  const int n_stat = kEnvsPerBlock * qs, n_slot = kEnvsPerBlock * (qs + qd);
+  const T margin = CfgV<T>::margin(cfg);
+  const uint32_t stat0 = (uint32_t)e0 * (uint32_t)p.stat_stride, dyn0 = (uint32_t)e0 * (uint32_t)p.dyn_stride;
+  T* agent_x = reinterpret_cast<T*>(p.agent_x);
+  T* agent_y = reinterpret_cast<T*>(p.agent_y);
+  T* goal_x = reinterpret_cast<T*>(p.goal_x);
+  T* goal_y = reinterpret_cast<T*>(p.goal_y);
 
-  if (tid < cfg.n_goals) {
-    s_goal_x[tid] = cfg.goal_x[tid];
-    s_goal_y[tid] = cfg.goal_y[tid];
+  if (is_scalar && tid < cnt_env && sh.reset[tid] != 0) {   // clear this environment's bits of the stream
+    for (int b = tid * nb, end = b + nb; b < end;) {
+      const int sh_ = b & 31, take = min(32 - sh_, end - b);
+      const uint32_t mask = (take == 32 ? 0xffffffffu : ((1u << take) - 1u)) << sh_;
+      atomicAnd(&words[b >> 5], ~mask);
+      b += take;
+    }
+  }
+  if (tid == 0) sh.count = 0;
+  __syncthreads();
+  if (!is_scalar) {
+    T* dyn_x = reinterpret_cast<T*>(p.dyn_x);
+    T* dyn_y = reinterpret_cast<T*>(p.dyn_y);
+    T* wstat_x = reinterpret_cast<T*>(p.stat_x);
+    T* wstat_y = reinterpret_cast<T*>(p.stat_y);
+    for (int slot = lt; slot < n_slot; slot += kLaneThreads) {
+      const bool dyn = slot >= n_stat;
+      const int sl = dyn ? slot - n_stat : slot;
+      const int per = dyn ? qd : qs;
+      const int el = div_slot(sl, dyn ? cfg.rcp_qd : cfg.rcp_qs), qq = sl - el * per;
+      if (el >= cnt_env || sh.reset[el] == 0) continue;
+      const long long e = e0 + el;
+      const DrawCtx dc{&p, e, p.g0 + (uint32_t)e};
+      const uint32_t episode = p.episode[e] + 1;
+      const ResetHead<T> head = reset_head_draw<T>(p, dc, episode);
+      T x[4] = {(T)0, (T)0, (T)0, (T)0}, y[4] = {(T)0, (T)0, (T)0, (T)0};
+      if (!dyn) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {                                              // :131-149
+          const int k = 4 * qq + i;
+          if (k < ks) {
+            reset_static_draw<T>(p, dc, episode, k, head, x[i], y[i]);
+            near_test<T, W>(sh, words, cfg, el, head.ax, head.ay, margin, x[i], y[i], k, false, want_obs, nb);
+          }
+        }
+        store4(wstat_x + stat0 + 4u * (uint32_t)sl, x);
+        store4(wstat_y + stat0 + 4u * (uint32_t)sl, y);
+      } else {
+        uint32_t meta[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {                                              // :153-164
+          const int j = 4 * qq + i;
+          if (j < kd) {
+            const uint2 w2 = dc.reset_dynamic(episode, j);
+            x[i] = (T)__umulhi(w2.x, 500u);
+            y[i] = (T)(20u + __umulhi(w2.y, 460u));
+            meta[i] = (uint32_t)j;   // curr_goal = goal_list[j], curr_counter = 0
+            near_test<T, W>(sh, words, cfg, el, head.ax, head.ay, margin, x[i], y[i], ks + j, false, want_obs, nb);
+          }
+        }
+        const uint32_t off = dyn0 + 4u * (uint32_t)sl;
+        store4(dyn_x + off, x);
+        store4(dyn_y + off, y);
+        store4(p.dyn_meta + off, meta);
+      }
+    }
+  } else if (tid < cnt_env && sh.reset[tid] != 0) {
+    // the scalar thread of a resetting environment draws the same head and owns the scalar state
+    const long long e = e0 + tid;
+    const DrawCtx dc{&p, e, p.g0 + (uint32_t)e};
+    const uint32_t episode = p.episode[e] + 1;
+    const ResetHead<T> head = reset_head_draw<T>(p, dc, episode);
+    sh.s_gx[tid] = head.gx;   // written back below, after every obstacle thread has read p.episode
+    sh.s_gy[tid] = head.gy;
+    sh.s_oax[tid] = head.ax;
+    sh.s_oay[tid] = head.ay;
+    sh.s_old[tid] = head.dist;
+    sh.s_total[tid] = head.total;
+    sh.s_tick[tid] = episode;
+    if (want_obs) {
+      const T qdx = r_sub(head.gx, head.ax), qdy = r_sub(head.gy, head.ay);
+      const int b = tid * nb + goal_quadrant_bit(qdx < (T)0, qdy < (T)0);
+      atomicOr(&words[b >> 5], 1u << (b & 31));
+    }
   }
   __syncthreads();
+  if (is_scalar) {
+    if (tid < cnt_env && sh.reset[tid] != 0) {
+      const long long e = e0 + tid;
+      sh.ax[tid] = sh.s_oax[tid];
+      sh.ay[tid] = sh.s_oay[tid];
+      p.episode[e] = sh.s_tick[tid];
+      agent_x[e] = sh.s_oax[tid];
+      agent_y[e] = sh.s_oay[tid];
+      goal_x[e] = sh.s_gx[tid];
+      goal_y[e] = sh.s_gy[tid];
+      p.dist[e] = sh.s_old[tid];
+      p.total[e] = sh.s_total[tid];
+      p.acc[e] = 0.0;
+      p.ep_len[e] = 0;
+    }
+  }
+  __syncthreads();   // sh.ax / sh.ay of the new episodes are published
+  if (!is_scalar && want_obs) raster_list<T, W>(sh, words, cfg, lt, nb);
+  __syncthreads();
+}
 
-  const Overlap<T> ov(cfg.radius_sum);
-  // per-thread contribution to the episode statistics (non-zero only for envs that finished this step)
-  double st_ret = 0.0, st_len = 0.0;
-  uint32_t st_cnt = 0;  // packed one-bit counters: episode | goal << 1 | hit_static << 2 | hit_dynamic << 3 | timeout << 4
-  if (e < p.n) {
+// ---- named barriers (PTX barrier.*, the forms that tolerate intra-warp divergence): the two thread roles below synchronise as producer / consumer ------------------
+//   kBarAgent : the scalar warp ARRIVES (does not wait) once the agent positions are published; obstacle
+//               threads SYNC on it before their bounding-box tests.  Count = all 288 threads.
+//   kBarNear  : everybody syncs: hits and the near list are complete.
+//   kBarDone  : everybody syncs with an OR-reduction of "some environment of the block resets".
+constexpr int kBarAgent = 1, kBarNear = 2, kBarDone = 3;
+__device__ __forceinline__ void bar_sync(int id) {
+  asm volatile("barrier.sync %0, %1;" ::"r"(id), "n"(kBlock) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(int id) {
+  asm volatile("barrier.arrive %0, %1;" ::"r"(id), "n"(kBlock) : "memory");
+}
+__device__ __forceinline__ bool bar_or(int id, bool pred) {
+  int r;
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %2, 0;\n\tbarrier.red.or.pred q, %1, %3, p;\n\tselp.b32 %0, 1, 0, q;\n\t}"
+      : "=r"(r)
+      : "r"(id), "r"(pred ? 1 : 0), "n"(kBlock)
+      : "memory");
+  return r != 0;
+}
+
+// ---- the kernel -----------------------------------------------------------------------------------------------------
+// A block owns 32 consecutive environments for the whole launch: it loads their state once, advances them
+// p.n_steps steps with the state held in registers, and writes it back once.  ballenv_step() launches it with
+// n_steps = 1; ballenv_step_many() (open-loop rollouts: the actions of all T steps are given up front) launches it
+// once for all T steps, so only actions, observations, rewards and dones touch HBM inside the loop.
+//
+// Thread roles: warp 0 = scalar warp, thread t owns environment e0 + t (agent move, reward, flags, statistics);
+// threads 32 .. 287 = obstacle threads.  The block's obstacle quads form one linear slot space - first the
+// 32 * qs static quads, then the 32 * qd dynamic quads, each environment-major exactly as they lie in memory - so
+// slot s of a kind sits at element 4 * s of the block's slice, warps are purely static or purely dynamic, and
+// consecutive threads issue consecutive 128-bit accesses.  Thread lt keeps slot lt in registers; configurations
+// with more than 8 quads per environment go through global memory for the slots beyond 256.
+//
+// The roles run as two independent instruction streams that meet at named barriers, so neither waits for the
+// other's memory latency.  Per step:
+//   scalar warp   : action -> move + clamp agent -> publish -> ARRIVE(agent) -> distance, progress reward,
+//                   goal / truncation flags (fp64) -> SYNC(near) -> apply hit -> publish reset decision + quadrant
+//                   bits -> SYNC(done) -> reward / done out, statistics -> [reset] -> store observations
+//   obstacle thr. : (dynamic) Philox, 4 moves -> SYNC(agent) -> clear the other bit-stream buffer -> 4 bounding-box
+//                   tests -> SYNC(near) -> raster a share of the near list -> SYNC(done) -> [reset] -> store obs.
+//
+// kFast: the production specialisation - Step mode, gym ruleset, Philox draws (no tapes), distinct obstacle goals,
+// index actions, fp32 observation rows requested.  Every uniform test of the generic kernel folds away; the host
+// (ballenv_capi.cu) selects it when all of that holds.
+template <typename T, int W, bool kFast>
+__global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __grid_constant__ Params p) {
+  __shared__ BlockShared<T, W> sh;
+  const DevConfig& cfg = p.cfg;
+  const int tid = threadIdx.x;
+  const long long e0 = (long long)blockIdx.x * kEnvsPerBlock;
+  const int cnt_env = (p.n - e0) < kEnvsPerBlock ? (int)(p.n - e0) : kEnvsPerBlock;   // environments of this block
+  const int w = Win<W>::w(cfg.window);
+  const int nb = 4 + w * w;
+  const int ks = cfg.ks, kd = cfg.kd;
+  const bool stepping = kFast || p.mode == kModeStep;
+  const int n_steps = kFast ? p.n_steps : 1;
+  const size_t obs_step_bytes = (size_t)p.n * (size_t)cfg.obs_row_elems * (cfg.obs_format == BALLENV_OBS_U8 ? 1u : 4u);
+  if (p.debug & 1) return;
+
+  if (tid < 32) {
+    // =============================== scalar warp: one thread per environment =====================================
+    const bool gym = kFast || cfg.ruleset == BALLENV_RULESET_GYM;
     T* agent_x = reinterpret_cast<T*>(p.agent_x);
     T* agent_y = reinterpret_cast<T*>(p.agent_y);
     T* goal_x = reinterpret_cast<T*>(p.goal_x);
     T* goal_y = reinterpret_cast<T*>(p.goal_y);
-    EnvCtx<T, W> c;
-    DrawCtx dc{&p, e, p.g0 + (uint32_t)e};
-    bool do_reset = false;
-    c.gx = goal_x[e];
-    c.gy = goal_y[e];
+    const long long e = e0 + tid;
+    const bool mine = tid < cnt_env;
+    bool reset_req = false;
+    // ---- state of the environment, in registers for the whole launch
+    T ax = (T)0, ay = (T)0, gx = (T)0, gy = (T)0;
+    double dist = 0.0, total = 1.0, acc = 0.0;
+    int len = 0;
+    uint32_t tick = 0, flags = 0;
+    if (mine) {
+      if (!kFast && p.mode == kModeReset) reset_req = p.reset_mask == nullptr || p.reset_mask[e] != 0;
+      if (!reset_req) {
+        ax = agent_x[e];
+        ay = agent_y[e];
+        gx = goal_x[e];
+        gy = goal_y[e];
+      }
+      if (stepping) {
+        dist = p.dist[e];
+        total = p.total[e];
+        acc = p.acc[e];
+        len = p.ep_len[e];
+        tick = p.tick[e];
+      }
+    }
+    if (tid < 16)
+      sh.lut[tid] = make_float4(tid & 1 ? 1.0f : 0.0f, tid & 2 ? 1.0f : 0.0f, tid & 4 ? 1.0f : 0.0f, tid & 8 ? 1.0f : 0.0f);
 
-    if (p.mode == kModeStep) {
-      // -------- agent move + clamp (ballenv_env.py:247-259 | ballenv_pygame.py:654-664)
-      const T oax = agent_x[e], oay = agent_y[e];
-      T adx, ady;
-      if (p.action_kind == BALLENV_ACT_XY_F32) {
-        const float2 a = reinterpret_cast<const float2*>(p.actions)[e];
-        adx = (T)a.x;
-        ady = (T)a.y;
-      } else if (p.action_kind == BALLENV_ACT_XY_F64) {
-        const double2 a = reinterpret_cast<const double2*>(p.actions)[e];
-        adx = (T)a.x;
-        ady = (T)a.y;
-      } else {
-        long long ai;
-        if (p.action_kind == BALLENV_ACT_INDEX_I64) ai = reinterpret_cast<const long long*>(p.actions)[e];
-        else if (p.action_kind == BALLENV_ACT_INDEX_I32) ai = reinterpret_cast<const int*>(p.actions)[e];
-        else ai = reinterpret_cast<const uint8_t*>(p.actions)[e];
-        if (ai < 0 || ai > 8) {
-          atomicOr(p.errors, (uint32_t)BALLENV_DEVERR_BAD_ACTION);
-          ai = 5;  // (0, 0)
+    for (int t = 0; t < n_steps; ++t) {
+      const bool want_obs = kFast ? (p.obs_all_steps != 0 || t == n_steps - 1) : p.obs != nullptr;
+      uint32_t* words = sh.words[t & 1];
+      const long long et = (long long)t * p.n + e;   // index of this environment in the [T][n] arrays
+      T nx = ax, ny = ay;
+      if (mine && stepping) {
+        // agent move + clamp (ballenv_env.py:247-259 | ballenv_pygame.py:654-664)
+        T adx, ady;
+        if (!kFast && p.action_kind == BALLENV_ACT_XY_F32) {
+          const float2 a = reinterpret_cast<const float2*>(p.actions)[et];
+          adx = (T)a.x;
+          ady = (T)a.y;
+        } else if (!kFast && p.action_kind == BALLENV_ACT_XY_F64) {
+          const double2 a = reinterpret_cast<const double2*>(p.actions)[et];
+          adx = (T)a.x;
+          ady = (T)a.y;
+        } else {
+          long long ai;
+          if (p.action_kind == BALLENV_ACT_INDEX_I64) ai = reinterpret_cast<const long long*>(p.actions)[et];
+          else if (p.action_kind == BALLENV_ACT_INDEX_I32) ai = reinterpret_cast<const int*>(p.actions)[et];
+          else ai = reinterpret_cast<const uint8_t*>(p.actions)[et];
+          if (ai < 0 || ai > 8) {
+            atomicOr(p.errors, (uint32_t)BALLENV_DEVERR_BAD_ACTION);
+            ai = 5;  // (0, 0)
+          }
+          adx = (T)table2(kAgentDx, (uint32_t)ai);
+          ady = (T)table2(kAgentDy, (uint32_t)ai);
         }
-        adx = (T)table2(kAgentDx, (uint32_t)ai);
-        ady = (T)table2(kAgentDy, (uint32_t)ai);
+        if (gym) {
+          nx = r_add(ax, r_mul(CfgV<T>::step_x(cfg), adx));   // speedx_ctrl_person * action[0]
+          ny = r_add(ay, r_mul(CfgV<T>::step_y(cfg), ady));
+        } else {
+          nx = r_add(ax, adx);
+          ny = r_add(ay, ady);
+        }
+        if (nx < (T)0) nx = (T)0;
+        if (ny < (T)0) ny = (T)0;
+        if (nx > CfgV<T>::world_w(cfg)) nx = CfgV<T>::world_w(cfg);
+        if (ny > CfgV<T>::world_h(cfg)) ny = CfgV<T>::world_h(cfg);
       }
-      T nx, ny;
-      if (cfg.ruleset == BALLENV_RULESET_GYM) {
-        nx = r_add(oax, r_mul((T)cfg.step_x, adx));   // speedx_ctrl_person * action[0]
-        ny = r_add(oay, r_mul((T)cfg.step_y, ady));
-      } else {
-        nx = r_add(oax, adx);
-        ny = r_add(oay, ady);
-      }
-      if (nx < (T)0) nx = (T)0;
-      if (ny < (T)0) ny = (T)0;
-      if (nx > (T)cfg.world_w) nx = (T)cfg.world_w;
-      if (ny > (T)cfg.world_h) ny = (T)cfg.world_h;
-      ctx_set_agent<T, W>(c, cfg, nx, ny);
+      sh.ax[tid] = nx;
+      sh.ay[tid] = ny;
+      sh.hit[tid] = kNoHit;
+      sh.reset[tid] = reset_req ? 1 : 0;   // Reset mode: stored obstacles of these environments are ignored
+      if (tid == 0) sh.count = 0;
+      bar_arrive(kBarAgent);
 
-      // -------- obstacles: static (read), dynamic (move, write back); hit test + window raster on the fly
-      for (int i = 0; i < cfg.ks; ++i)
-        ctx_obstacle<T, W>(c, cfg, ov, col<T>(p.stat_x, i, S)[e], col<T>(p.stat_y, i, S)[e], i);
-      const uint32_t tick = p.tick[e];
-      const bool has_tape = p.step_tape != nullptr;
-      for (int jb = 0; jb < cfg.kd; jb += 4) {
-        uint4 blk = make_uint4(0, 0, 0, 0);
-        if (!has_tape) blk = philox4x32_10(dc.g, tick, (uint32_t)(jb >> 2), kStreamStep, p.k0, p.k1);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int j = jb + q;
-          if (j < cfg.kd) {
-            T x = col<T>(p.dyn_x, j, S)[e], y = col<T>(p.dyn_y, j, S)[e];
-            uint32_t meta = p.dyn_meta[(long long)j * S + e];
-            uint32_t w1 = pick_word(blk, q), w2 = 0;
-            if (has_tape) {
-              const uint2 tw = reinterpret_cast<const uint2*>(p.step_tape)[e * cfg.kd + j];
-              w1 = tw.x;
-              w2 = tw.y;
+      // distance, progress reward, goal and time-limit flags do not depend on the obstacles: computed while the
+      // obstacle threads move and test (ballenv_env.py:268-286, 200-206 | ballenv_pygame.py:652-706)
+      double d = dist, reward = 0.0;
+      bool goal_flag = false, truncated = false;
+      const int ep_len = len + 1;
+      if (mine && stepping && !(p.debug & 16)) {
+        d = dist64((double)gx, (double)gy, (double)nx, (double)ny);               // :268 | :668
+        truncated = cfg.max_steps > 0 && ep_len >= cfg.max_steps;
+        goal_flag = d < cfg.goal_threshold;                                      // :276 | :690 (pygame: unless hit)
+        if (gym) {
+          reward = (dist - d) / total;                                           // :205-206, old = state[2] (:236)
+        } else {
+          const double od = dist64((double)ax, (double)ay, (double)gx, (double)gy);   // :652
+          reward = (od - d) / total;                                             // :699-706
+        }
+      }
+      bar_sync(kBarNear);
+
+      bool do_reset = false, done_out = false, hit = false, hit_dyn = false, done = false;
+      if (mine) {
+        if (stepping) {
+          const int hit_first = sh.hit[tid];
+          hit = hit_first != kNoHit;
+          hit_dyn = hit && hit_first >= ks;
+          if (gym) {
+            if (hit) reward -= hit_dyn ? cfg.dynamic_penalty : cfg.static_penalty;  // :222-224
+            acc += reward;                                                          // :280
+            done = goal_flag || hit;                                                // :286
+          } else {
+            if (hit) {                                                              // :683-688 (before the goal test)
+              goal_flag = false;
+              reward = -1.0;
+              done = true;
+            } else if (goal_flag) {                                                 // :690-697
+              reward = 1.0;
+              done = true;
             }
-            move_obstacle<T>(cfg, s_goal_x, s_goal_y, j, w1, w2, has_tape, x, y, meta);
-            col<T>(p.dyn_x, j, S)[e] = x;
-            col<T>(p.dyn_y, j, S)[e] = y;
-            p.dyn_meta[(long long)j * S + e] = meta;
-            ctx_obstacle<T, W>(c, cfg, ov, x, y, cfg.ks + j);
+            acc += reward;
+          }
+          done_out = done || truncated;
+          do_reset = done_out && cfg.auto_reset;
+        } else if (!kFast && reset_req) {
+          do_reset = true;
+        }
+        if (do_reset) {
+          sh.reset[tid] = 1;
+        } else if (want_obs) {
+          // 4 goal-quadrant bits (examples/ball_cnn_ac3.py:341-350); the obstacle warps are OR-ing cells concurrently
+          const T qdx = r_sub(gx, nx), qdy = r_sub(gy, ny);
+          const int b = tid * nb + goal_quadrant_bit(qdx < (T)0, qdy < (T)0);
+          atomicOr(&words[b >> 5], 1u << (b & 31));
+        }
+      }
+      const bool any_reset = bar_or(kBarDone, do_reset);
+
+      // outputs of the step and statistics: nobody waits for these
+      double st_ret = 0.0, st_len = 0.0;
+      uint32_t st_cnt = 0;  // episode | goal << 1 | hit_static << 2 | hit_dynamic << 3 | timeout << 4
+      if (mine && stepping) {
+        flags = (goal_flag ? BALLENV_FLAG_GOAL : 0) | (hit ? BALLENV_FLAG_HIT : 0) |
+                (truncated ? BALLENV_FLAG_TRUNCATED : 0) | (hit_dyn ? BALLENV_FLAG_HIT_DYNAMIC : 0);
+        if (p.reward != nullptr) {
+          if (sizeof(T) == 4) reinterpret_cast<float*>(p.reward)[et] = (float)reward;
+          else reinterpret_cast<double*>(p.reward)[et] = reward;
+        }
+        if (p.done != nullptr) p.done[et] = done_out ? 1 : 0;
+        if (done_out) {
+          st_ret = acc;
+          st_len = (double)ep_len;
+          st_cnt = 1u | (goal_flag ? 2u : 0u) | ((hit && !hit_dyn) ? 4u : 0u) | (hit_dyn ? 8u : 0u) |
+                   ((truncated && !done) ? 16u : 0u);
+        }
+        ax = nx;
+        ay = ny;
+        dist = d;
+        len = ep_len;
+        tick += 1;
+      }
+      if (stepping) {
+        // episode statistics (the only thing that is ever all-reduced across GPUs): ballot + shuffle in the scalar
+        // warp, one atomic per counter per block, and only in blocks where an episode ended.
+        const uint32_t fin = __ballot_sync(0xffffffffu, st_cnt != 0);
+        if (fin != 0) {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            st_ret += __shfl_xor_sync(0xffffffffu, st_ret, o);
+            st_len += __shfl_xor_sync(0xffffffffu, st_len, o);
+          }
+          const uint32_t n_goal = __popc(__ballot_sync(0xffffffffu, st_cnt & 2u));
+          const uint32_t n_hs = __popc(__ballot_sync(0xffffffffu, st_cnt & 4u));
+          const uint32_t n_hd = __popc(__ballot_sync(0xffffffffu, st_cnt & 8u));
+          const uint32_t n_to = __popc(__ballot_sync(0xffffffffu, st_cnt & 16u));
+          if (tid == 0) {
+            atomicAdd(&p.stats[BALLENV_STAT_EPISODES], (double)__popc(fin));
+            atomicAdd(&p.stats[BALLENV_STAT_RETURN_SUM], st_ret);
+            atomicAdd(&p.stats[BALLENV_STAT_LENGTH_SUM], st_len);
+            if (n_goal) atomicAdd(&p.stats[BALLENV_STAT_GOALS], (double)n_goal);
+            if (n_hs) atomicAdd(&p.stats[BALLENV_STAT_HITS_STATIC], (double)n_hs);
+            if (n_hd) atomicAdd(&p.stats[BALLENV_STAT_HITS_DYNAMIC], (double)n_hd);
+            if (n_to) atomicAdd(&p.stats[BALLENV_STAT_TIMEOUTS], (double)n_to);
+          }
+        }
+        if (e == 0) atomicAdd(&p.stats[BALLENV_STAT_STEPS], (double)p.n);
+      }
+
+      // (rare) reset through global memory, then take the new episode's scalars into the registers
+      if (any_reset) {
+        reset_stage<T, W>(p, sh, words, e0, cnt_env, want_obs);
+        if (mine && do_reset) {
+          ax = agent_x[e];
+          ay = agent_y[e];
+          gx = goal_x[e];
+          gy = goal_y[e];
+          dist = p.dist[e];
+          total = p.total[e];
+          acc = 0.0;
+          len = 0;
+        }
+      }
+      if (want_obs && !(p.debug & 8)) {
+        const Params& pp = p;
+        store_obs<W, kFast>(pp, reinterpret_cast<char*>(p.obs) + (kFast && p.obs_all_steps ? (size_t)t * obs_step_bytes : 0),
+                            words, sh.lut, e0, cnt_env);
+      }
+    }
+
+    // ---- write the scalar state back
+    if (mine) {
+      if (stepping) {
+        agent_x[e] = ax;
+        agent_y[e] = ay;
+        p.dist[e] = dist;
+        p.acc[e] = acc;
+        p.ep_len[e] = len;
+        p.tick[e] = tick;
+        p.flags[e] = (uint8_t)flags;
+      } else if (reset_req) {
+        p.flags[e] = 0;
+      }
+    }
+  } else {
+    // =============================== obstacle threads: one quad per thread per iteration =========================
+    const int lt = tid - 32;
+    const int qs = (ks + 3) >> 2, qd = (kd + 3) >> 2;         // static / dynamic quads per environment
+    const int n_stat = kEnvsPerBlock * qs, n_slot = kEnvsPerBlock * (qs + qd);
+    const T margin = CfgV<T>::margin(cfg);
+    // element offsets of the block's obstacle slices (n * K fits 31 bits, checked at create time)
+    const uint32_t stat0 = (uint32_t)e0 * (uint32_t)p.stat_stride, dyn0 = (uint32_t)e0 * (uint32_t)p.dyn_stride;
+    const T* stat_x = reinterpret_cast<const T*>(p.stat_x);
+    const T* stat_y = reinterpret_cast<const T*>(p.stat_y);
+
+    // ---- the thread's own quad (slot lt), in registers for the whole launch: issue its loads before anything else
+    T qx[4], qy[4];
+    uint32_t qm[4];
+    uint32_t tick = 0;
+    int q_el = 0, q_k0 = 0, q_kend = 0, q_jq = 0;   // environment (of the block), first list index, end index, dynamic quad
+    bool q_have = false;
+    const bool q_dyn = lt >= n_stat;
+    const uint32_t q_off = q_dyn ? dyn0 + 4u * (uint32_t)(lt - n_stat) : stat0 + 4u * (uint32_t)lt;
+    if (lt < n_slot) {
+      const int sl = q_dyn ? lt - n_stat : lt;          // slot within its kind
+      const int per = q_dyn ? qd : qs;
+      q_el = div_slot(sl, q_dyn ? cfg.rcp_qd : cfg.rcp_qs);
+      const int qq = sl - q_el * per;
+      q_have = q_el < cnt_env;
+      if (!kFast && q_have && p.mode == kModeReset)
+        q_have = p.reset_mask == nullptr ? false : p.reset_mask[e0 + q_el] == 0;
+      if (q_have) {
+        if (!q_dyn) {
+          q_k0 = 4 * qq;
+          q_kend = ks;
+          load4(stat_x + q_off, qx);
+          load4(stat_y + q_off, qy);
+        } else {
+          q_jq = qq;
+          q_k0 = ks + 4 * qq;
+          q_kend = ks + kd;
+          if (stepping) tick = p.tick[e0 + q_el];
+          dynamic_load<T>(p, q_off, stepping, qx, qy, qm);
+        }
+      }
+    }
+    // block setup shared by the obstacle threads: cleared bit-stream; goal and move tables.  Every warp writes the
+    // (identical) table entries it is going to read, so a warp-level sync is all the moves below need.
+    for (int i = lt; i < nb; i += kLaneThreads) sh.words[0][i] = 0;
+    {
+      const int l32 = tid & 31;
+      if (l32 < 9) {
+        sh.mv[l32].x = (T)table2(kObstDx, (uint32_t)l32);
+        sh.mv[l32].y = (T)table2(kObstDy, (uint32_t)l32);
+      }
+      for (int i = l32; i < cfg.n_goals; i += 32) sh.goal[i] = CfgV<T>::goal(cfg, i);
+      __syncwarp();
+    }
+
+    for (int t = 0; t < n_steps; ++t) {
+      const bool want_obs = kFast ? (p.obs_all_steps != 0 || t == n_steps - 1) : p.obs != nullptr;
+      uint32_t* words = sh.words[t & 1];
+      // obstacle motion does not depend on the agent: draw and move while the scalar warp works
+      if (q_have && q_dyn && stepping && !(p.debug & 2)) {
+        if (kFast || (p.step_tape == nullptr && cfg.goals_distinct))
+          dynamic_move<T, W, true>(p, sh, e0 + q_el, q_jq, tick + (uint32_t)t, qx, qy, qm);
+        else
+          dynamic_move<T, W, false>(p, sh, e0 + q_el, q_jq, tick + (uint32_t)t, qx, qy, qm);
+      }
+      bar_sync(kBarAgent);   // agent positions published; everybody is done with the previous step's bit-stream
+      if (t + 1 < n_steps)
+        for (int i = lt; i < nb; i += kLaneThreads) sh.words[(t + 1) & 1][i] = 0;
+
+      // bounding-box test every obstacle against the agent; near ones are hit-tested and queued
+      if (q_have && !(p.debug & 4)) {
+        const T ax = sh.ax[q_el], ay = sh.ay[q_el];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (q_k0 + i < q_kend)
+            near_test<T, W>(sh, words, cfg, q_el, ax, ay, margin, qx[i], qy[i], q_k0 + i, stepping, want_obs, nb);
+      }
+      for (int slot = lt + kLaneThreads; slot < n_slot; slot += kLaneThreads) {   // more than 8 quads per environment
+        const bool dyn = slot >= n_stat;
+        const int sl = dyn ? slot - n_stat : slot;
+        const int per = dyn ? qd : qs;
+        const int el = div_slot(sl, dyn ? cfg.rcp_qd : cfg.rcp_qs), qq = sl - el * per;
+        if (el >= cnt_env || sh.reset[el] != 0) continue;
+        T x[4], y[4];
+        if (!dyn) {
+          load4(stat_x + stat0 + 4u * (uint32_t)sl, x);
+          load4(stat_y + stat0 + 4u * (uint32_t)sl, y);
+        } else {
+          uint32_t m[4];
+          const uint32_t off = dyn0 + 4u * (uint32_t)sl;
+          dynamic_load<T>(p, off, stepping, x, y, m);
+          if (stepping) {
+            dynamic_move<T, W, false>(p, sh, e0 + el, qq, p.tick[e0 + el] + (uint32_t)t, x, y, m);
+            dynamic_store<T>(p, off, x, y, m);
+          }
+        }
+        const int k0 = dyn ? ks + 4 * qq : 4 * qq, kend = dyn ? ks + kd : ks;
+        const T ax = sh.ax[el], ay = sh.ay[el];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (k0 + i < kend)
+            near_test<T, W>(sh, words, cfg, el, ax, ay, margin, x[i], y[i], k0 + i, stepping, want_obs, nb);
+      }
+      bar_sync(kBarNear);
+
+      // block-cooperative raster of the near list
+      if (want_obs) raster_list<T, W>(sh, words, cfg, lt, nb);
+      const bool any_reset = bar_or(kBarDone, false);
+
+      // (rare) reset through global memory, then take the new episode's quad into the registers
+      if (any_reset) {
+        const bool mine_reset = q_have && sh.reset[q_el] != 0;
+        // the quads of the finished episode may be overwritten; everybody else's registers stay authoritative
+        reset_stage<T, W>(p, sh, words, e0, cnt_env, want_obs);
+        if (mine_reset) {
+          if (!q_dyn) {
+            load4(stat_x + q_off, qx);
+            load4(stat_y + q_off, qy);
+          } else {
+            dynamic_load<T>(p, q_off, true, qx, qy, qm);
           }
         }
       }
-
-      // -------- distance, reward, flags (ballenv_env.py:268-286, 200-229 | ballenv_pygame.py:668-706)
-      const double total = p.total[e];
-      double acc = p.acc[e];
-      const bool hit = c.hit_first != 0x7fffffff;
-      const bool hit_dyn = hit && c.hit_first >= cfg.ks;
-      double d, reward;
-      bool goal_flag, done;
-      if (cfg.ruleset == BALLENV_RULESET_GYM) {
-        const double old = p.dist[e];                                             // :236
-        d = dist64((double)c.gx, (double)c.gy, (double)nx, (double)ny);           // :268
-        goal_flag = d < cfg.goal_threshold;                                       // :276
-        reward = (old - d) / total;                                               // :205-206
-        if (hit) reward -= hit_dyn ? cfg.dynamic_penalty : cfg.static_penalty;    // :222-224
-        acc += reward;                                                            // :280
-        done = goal_flag || hit;                                                  // :286
-      } else {
-        const double old = dist64((double)oax, (double)oay, (double)c.gx, (double)c.gy);  // :652
-        d = dist64((double)nx, (double)ny, (double)c.gx, (double)c.gy);                   // :668
-        goal_flag = false;
-        if (hit) {                                                                        // :683-688
-          acc += -1.0;
-          reward = -1.0;
-          done = true;
-        } else if (d < cfg.goal_threshold) {                                              // :690-697
-          goal_flag = true;
-          acc += 1.0;
-          reward = 1.0;
-          done = true;
-        } else {                                                                          // :699-706
-          reward = (old - d) / total;
-          acc += reward;
-          done = false;
-        }
-      }
-      int ep_len = p.ep_len[e] + 1;
-      const bool truncated = cfg.max_steps > 0 && ep_len >= cfg.max_steps;
-      const bool done_out = done || truncated;
-      const uint32_t f = (goal_flag ? BALLENV_FLAG_GOAL : 0) | (hit ? BALLENV_FLAG_HIT : 0) |
-                         (truncated ? BALLENV_FLAG_TRUNCATED : 0) | (hit_dyn ? BALLENV_FLAG_HIT_DYNAMIC : 0);
-      p.flags[e] = (uint8_t)f;
-      p.tick[e] = tick + 1;
-      if (p.reward != nullptr) {
-        if (sizeof(T) == 4) reinterpret_cast<float*>(p.reward)[e] = (float)reward;
-        else reinterpret_cast<double*>(p.reward)[e] = reward;
-      }
-      if (p.done != nullptr) p.done[e] = done_out ? 1 : 0;
-
-      if (done_out) {
-        st_ret = acc;
-        st_len = (double)ep_len;
-        st_cnt = 1u | (goal_flag ? 2u : 0u) | ((hit && !hit_dyn) ? 4u : 0u) | (hit_dyn ? 8u : 0u) |
-                 ((truncated && !done) ? 16u : 0u);
-      }
-      do_reset = done_out && cfg.auto_reset;
-      if (!do_reset) {
-        agent_x[e] = nx;
-        agent_y[e] = ny;
-        p.dist[e] = d;
-        p.acc[e] = acc;
-        p.ep_len[e] = ep_len;
-      }
-    } else if (p.mode == kModeReset && (p.reset_mask == nullptr || p.reset_mask[e] != 0)) {
-      do_reset = true;
-      p.flags[e] = 0;
-    } else {
-      // observe only: raster the stored state
-      ctx_set_agent<T, W>(c, cfg, agent_x[e], agent_y[e]);
-      for (int i = 0; i < cfg.ks; ++i)
-        ctx_obstacle<T, W>(c, cfg, ov, col<T>(p.stat_x, i, S)[e], col<T>(p.stat_y, i, S)[e], i);
-      for (int j = 0; j < cfg.kd; ++j)
-        ctx_obstacle<T, W>(c, cfg, ov, col<T>(p.dyn_x, j, S)[e], col<T>(p.dyn_y, j, S)[e], cfg.ks + j);
-    }
-
-    // -------- (auto-)reset: new episode drawn in place; the observation below is the post-reset one
-    if (do_reset) {
-      const uint32_t episode = p.episode[e] + 1;
-      double rd, rt;
-      reset_env<T, W>(p, dc, ov, episode, c, rd, rt);
-      p.episode[e] = episode;
-      agent_x[e] = c.ax;
-      agent_y[e] = c.ay;
-      goal_x[e] = c.gx;
-      goal_y[e] = c.gy;
-      p.dist[e] = rd;
-      p.total[e] = rt;
-      p.acc[e] = 0.0;
-      p.ep_len[e] = 0;
-    }
-
-    // -------- pack the observation bits: 4 goal-quadrant bits (examples/ball_cnn_ac3.py:341-350) + W*W cells
-    if (p.obs != nullptr) {
-      const T qdx = r_sub(c.gx, c.ax), qdy = r_sub(c.gy, c.ay);
-      const int q = (qdx >= (T)0 && qdy >= (T)0) ? 1 : ((qdx < (T)0 && qdy >= (T)0) ? 0 : ((qdx < (T)0 && qdy < (T)0) ? 3 : 2));
-      if constexpr (W == 0) {
-        for (int i = 0; i < nw; ++i) words_s[tid * nw + i] = 0;
-        words_s[tid * nw] = 1u << q;
-        for (int r = 0; r < w; ++r) {
-          const int off = 4 + r * w;
-          const uint32_t v = c.rows[r];
-          words_s[tid * nw + (off >> 5)] |= v << (off & 31);
-          if ((off & 31) + w > 32) words_s[tid * nw + (off >> 5) + 1] |= v >> (32 - (off & 31));
-        }
-      } else {
-        uint32_t words[NWc];
-#pragma unroll
-        for (int i = 0; i < NWc; ++i) words[i] = 0;
-        words[0] = 1u << q;
-#pragma unroll
-        for (int r = 0; r < W; ++r) {
-          const int off = 4 + r * W;
-          const uint32_t v = c.rows[r];
-          words[off >> 5] |= v << (off & 31);
-          if ((off & 31) + W > 32) words[(off >> 5) + 1] |= v >> (32 - (off & 31));
-        }
-#pragma unroll
-        for (int i = 0; i < NWc; ++i) words_s[tid * NWc + i] = words[i];
+      if (want_obs && !(p.debug & 8)) {
+        const Params& pp = p;
+        store_obs<W, kFast>(pp, reinterpret_cast<char*>(p.obs) + (kFast && p.obs_all_steps ? (size_t)t * obs_step_bytes : 0),
+                            words, sh.lut, e0, cnt_env);
       }
     }
-  }
-  if (p.obs != nullptr) {
-    __syncthreads();
-    const long long rem = p.n - e0;
-    store_obs<W>(p, words_s, e0, rem < kBlock ? (int)rem : kBlock);
-  }
-  if (p.mode == kModeStep) {
-    // episode statistics (the only thing that is ever all-reduced across GPUs): ballot + shuffle per warp,
-    // one atomic per counter per warp, and only in warps where an episode ended.
-    const uint32_t fin = __ballot_sync(0xffffffffu, st_cnt != 0);
-    if (fin != 0) {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        st_ret += __shfl_xor_sync(0xffffffffu, st_ret, o);
-        st_len += __shfl_xor_sync(0xffffffffu, st_len, o);
-      }
-      const uint32_t n_goal = __popc(__ballot_sync(0xffffffffu, st_cnt & 2u));
-      const uint32_t n_hs = __popc(__ballot_sync(0xffffffffu, st_cnt & 4u));
-      const uint32_t n_hd = __popc(__ballot_sync(0xffffffffu, st_cnt & 8u));
-      const uint32_t n_to = __popc(__ballot_sync(0xffffffffu, st_cnt & 16u));
-      if ((tid & 31) == 0) {
-        atomicAdd(&p.stats[BALLENV_STAT_EPISODES], (double)__popc(fin));
-        atomicAdd(&p.stats[BALLENV_STAT_RETURN_SUM], st_ret);
-        atomicAdd(&p.stats[BALLENV_STAT_LENGTH_SUM], st_len);
-        if (n_goal) atomicAdd(&p.stats[BALLENV_STAT_GOALS], (double)n_goal);
-        if (n_hs) atomicAdd(&p.stats[BALLENV_STAT_HITS_STATIC], (double)n_hs);
-        if (n_hd) atomicAdd(&p.stats[BALLENV_STAT_HITS_DYNAMIC], (double)n_hd);
-        if (n_to) atomicAdd(&p.stats[BALLENV_STAT_TIMEOUTS], (double)n_to);
-      }
-    }
-    if (e == 0) atomicAdd(&p.stats[BALLENV_STAT_STEPS], (double)p.n);
+
+    // ---- write the moved quads back
+    if (q_have && q_dyn && stepping) dynamic_store<T>(p, q_off, qx, qy, qm);
   }
 }
 

@@ -133,26 +133,19 @@ class BallEnv(object):
 
     def _pull_state(self):
         v = self._vec
-        host = v._arena.cpu().numpy()            # one small device->host copy of the whole SoA arena (N = 1)
-        base = v._arena.data_ptr()
-        p = v._ptrs
-
-        def f64(ptr, count=1, stride=int(p.n_stride)):
-            off = ptr - base
-            return np.frombuffer(host, dtype=np.float64, count=(count - 1) * stride + 1, offset=off)[::stride]
-
-        ax, ay = f64(p.agent_x)[0], f64(p.agent_y)[0]
-        gx, gy = f64(p.goal_x)[0], f64(p.goal_y)[0]
-        dist = float(f64(p.dist)[0])
-        self.total_distance = float(f64(p.total_distance)[0])
-        self.total_reward_accumulated = float(f64(p.acc_reward)[0])
+        hv = v._views_of(v._arena.cpu())          # one small device->host copy of the whole SoA arena (N = 1)
+        ax, ay = hv["agent_x"][0].item(), hv["agent_y"][0].item()
+        gx, gy = hv["goal_x"][0].item(), hv["goal_y"][0].item()
+        dist = float(hv["dist"][0].item())
+        self.total_distance = float(hv["total_distance"][0].item())
+        self.total_reward_accumulated = float(hv["acc_reward"][0].item())
         ks, kd = self._cfg.static_obstacles, self._cfg.dynamic_obstacles
         state = [(_num(ax), _num(ay)), (_num(gx), _num(gy)), dist]
         if ks:
-            sx, sy = f64(p.static_x, ks), f64(p.static_y, ks)
+            sx, sy = hv["static_x"][:, 0].tolist(), hv["static_y"][:, 0].tolist()
             state += [(_num(x), _num(y)) for x, y in zip(sx, sy)]
         if kd:
-            dx, dy = f64(p.dynamic_x, kd), f64(p.dynamic_y, kd)
+            dx, dy = hv["dynamic_x"][:, 0].tolist(), hv["dynamic_y"][:, 0].tolist()
             state += [(float(x), float(y)) for x, y in zip(dx, dy)]
         self.goal_x, self.goal_y = state[1]
         self.old_dist = dist

@@ -88,29 +88,38 @@ class BallVecEnv:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
-    def _view(self, ptr, nbytes, dtype, shape):
-        off = ptr - self._arena.data_ptr()
-        return self._arena[off:off + nbytes].view(dtype).view(shape)
-
-    def _make_views(self):
+    def _views_of(self, arena: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """Typed views of the SoA state inside ``arena`` (the device arena, or a host copy of it).
+        Obstacle fields are stored environment-major [n_stride][K padded to 4] (include/ballenv.h) and are
+        exposed transposed as [K, N] like the reference's state list order."""
         p, S, n = self._ptrs, int(self._ptrs.n_stride), self.num_envs
+        base = self._arena.data_ptr()
         rb = int(p.real_bytes)
         ks, kd = self.config.static_obstacles, self.config.dynamic_obstacles
+        ss, ds = int(p.static_stride), int(p.dynamic_stride)
+
+        def view(ptr, nbytes, dtype, shape):
+            off = ptr - base
+            return arena[off:off + nbytes].view(dtype).view(shape)
+
         v = {}
         for name in ("agent_x", "agent_y", "goal_x", "goal_y"):
-            v[name] = self._view(getattr(p, name), rb * S, self._real, (S,))[:n]
+            v[name] = view(getattr(p, name), rb * S, self._real, (S,))[:n]
         for name in ("dist", "total_distance", "acc_reward"):
-            v[name] = self._view(getattr(p, name), 8 * S, torch.float64, (S,))[:n]
+            v[name] = view(getattr(p, name), 8 * S, torch.float64, (S,))[:n]
         for name in ("ep_len", "episode", "tick"):
-            v[name] = self._view(getattr(p, name), 4 * S, torch.int32, (S,))[:n]
-        for name, k in (("static_x", ks), ("static_y", ks), ("dynamic_x", kd), ("dynamic_y", kd)):
-            v[name] = (self._view(getattr(p, name), rb * S * k, self._real, (k, S))[:, :n] if k
-                       else torch.empty((0, n), dtype=self._real, device=self.device))
-        v["dynamic_meta"] = (self._view(p.dynamic_meta, 4 * S * kd, torch.int32, (kd, S))[:, :n] if kd
-                             else torch.empty((0, n), dtype=torch.int32, device=self.device))
-        v["flags"] = self._view(p.flags, S, torch.uint8, (S,))[:n]
-        v["stats"] = self._view(p.stats, 8 * L.NUM_STATS, torch.float64, (L.NUM_STATS,))
-        self.state_views: Dict[str, torch.Tensor] = v
+            v[name] = view(getattr(p, name), 4 * S, torch.int32, (S,))[:n]
+        for name, k, st in (("static_x", ks, ss), ("static_y", ks, ss), ("dynamic_x", kd, ds), ("dynamic_y", kd, ds)):
+            v[name] = (view(getattr(p, name), rb * S * st, self._real, (S, st))[:n, :k].t() if k
+                       else torch.empty((0, n), dtype=self._real, device=arena.device))
+        v["dynamic_meta"] = (view(p.dynamic_meta, 4 * S * ds, torch.int32, (S, ds))[:n, :kd].t() if kd
+                             else torch.empty((0, n), dtype=torch.int32, device=arena.device))
+        v["flags"] = view(p.flags, S, torch.uint8, (S,))[:n]
+        v["stats"] = view(p.stats, 8 * L.NUM_STATS, torch.float64, (L.NUM_STATS,))
+        return v
+
+    def _make_views(self):
+        self.state_views: Dict[str, torch.Tensor] = self._views_of(self._arena)
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:

@@ -15,9 +15,10 @@
  *   - a handle is confined to one host thread / stream at a time; distinct handles are independent.
  *
  * State layout (struct-of-arrays, resident in HBM, owned by the handle or by a caller arena):
- *   per-env scalars are arrays of n_stride elements; per-obstacle fields are [K][n_stride]
- *   (obstacle-major, environment-minor) so that one warp reading obstacle k of 32 consecutive
- *   environments touches one 128-byte line.
+ *   per-env scalars are arrays of n_stride elements (one thread per environment reads them: a warp
+ *   touches whole 128-byte lines); per-obstacle fields are environment-major rows [n_stride][K padded
+ *   to a multiple of 4] so that the 8 lanes that own one environment move its obstacles as 128-bit
+ *   quads and a warp (4 environments) touches 4 * K contiguous elements per field.
  */
 #ifndef BALLENV_H_
 #define BALLENV_H_
@@ -28,7 +29,7 @@
 extern "C" {
 #endif
 
-#define BALLENV_ABI_VERSION 1
+#define BALLENV_ABI_VERSION 2
 
 #define BALLENV_MAX_DYNAMIC 64
 #define BALLENV_MAX_GOALS 64
@@ -115,7 +116,9 @@ typedef struct BallenvConfig {
 /* Device pointers of the SoA state (ballenv_state_ptrs).  Real = float or double per config.precision. */
 typedef struct BallenvStatePtrs {
   int64_t n_envs;
-  int64_t n_stride;     /* element stride between obstacle rows (>= n_envs) */
+  int64_t n_stride;     /* allocated environments per array (>= n_envs, multiple of 128) */
+  int64_t static_stride;  /* elements per environment row of static_x / static_y  (static_obstacles rounded up to 4) */
+  int64_t dynamic_stride; /* elements per environment row of dynamic_x / dynamic_y / dynamic_meta */
   int32_t real_bytes;   /* 4 or 8 */
   int32_t obs_row_elems; /* elements per observation row in the configured obs_format */
   void *agent_x, *agent_y;    /* Real [n_stride]            state[0] */
@@ -126,9 +129,9 @@ typedef struct BallenvStatePtrs {
   int32_t *ep_len;            /* [n_stride]                 steps since reset (TimeLimit counter) */
   uint32_t *episode;          /* [n_stride]                 index of the current episode (reset-draw address) */
   uint32_t *tick;             /* [n_stride]                 steps since creation (step-draw address) */
-  void *static_x, *static_y;  /* Real [static_obstacles][n_stride]   state[3 : 3 + Ks] */
-  void *dynamic_x, *dynamic_y;/* Real [dynamic_obstacles][n_stride]  state[3 + Ks :] */
-  uint32_t *dynamic_meta;     /* [dynamic_obstacles][n_stride]  curr_goal index | curr_counter << 8 */
+  void *static_x, *static_y;  /* Real [n_stride][static_stride]    state[3 : 3 + Ks] of env e at row e */
+  void *dynamic_x, *dynamic_y;/* Real [n_stride][dynamic_stride]   state[3 + Ks :] */
+  uint32_t *dynamic_meta;     /* [n_stride][dynamic_stride]  curr_goal index | curr_counter << 8 */
   uint8_t *flags;             /* [n_stride]                 BALLENV_FLAG_* of the last step */
   double *stats;              /* [BALLENV_NUM_STATS]        episode statistics (all-reduce these across GPUs) */
   uint32_t *error_flags;      /* [1]                        BALLENV_DEVERR_* */

@@ -284,3 +284,72 @@ def test_bad_action_flag_and_errors():
     with pytest.raises(BallenvError):   # a single distinct obstacle goal: the reference raises at the first change step
         BallVecEnv(8, config=EnvConfig(dynamic_obstacles=2, obstacle_speed=[1, 1], obs_goal_position=['5,5', '5,5']))
     env.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,cfgname,n", [(5, "default", 1000), (10, "dense", 777), (7, "default", 100)])
+def test_fast_and_generic_kernels_agree(w, cfgname, n, monkeypatch):
+    """The production specialisation (ballenv_kernel<..., kFast=true>) and the generic kernel are the same
+    function: bit-identical observations, rewards, flags and state over a rollout with auto-resets, including a
+    ragged last block (n not a multiple of 32)."""
+    from gym_ballenv_b200 import BallVecEnv
+    from oracle.gen_golden import CFG_DEFAULT, CFG_DENSE
+    cfg = CFG_DEFAULT if cfgname == "default" else CFG_DENSE
+    fast = BallVecEnv(n, window=w, config=_env_config(cfg), seed=5, max_episode_steps=15)
+    monkeypatch.setenv("BALLENV_FORCE_GENERIC", "1")
+    slow = BallVecEnv(n, window=w, config=_env_config(cfg), seed=5, max_episode_steps=15)
+    monkeypatch.delenv("BALLENV_FORCE_GENERIC")
+    assert torch.equal(fast.reset(), slow.reset())
+    g = torch.Generator().manual_seed(11)
+    for t in range(50):
+        a = torch.randint(0, 9, (n,), generator=g).cuda()
+        of, rf, df, inf = fast.step(a)
+        os_, rs, ds, ins = slow.step(a)
+        assert torch.equal(of, os_), t
+        assert torch.equal(rf, rs), t
+        assert torch.equal(df, ds), t
+        assert torch.equal(inf["flags"], ins["flags"]), t
+    sf, ss = fast.get_state(), slow.get_state()
+    for k in sf:
+        assert torch.equal(sf[k], ss[k]), k
+    stf, sts = fast.stats(), slow.stats()
+    for k in stf:   # sums of doubles are accumulated with atomics: order, hence the last bits, may differ
+        assert stf[k] == pytest.approx(sts[k], rel=1e-12), k
+    fast.close()
+    slow.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,cfgname,n,keep", [(5, "default", 1000, True), (10, "dense", 777, True), (5, "default", 96, False)])
+def test_rollout_kernel_matches_per_step_launches(w, cfgname, n, keep, monkeypatch):
+    """ballenv_step_many as ONE launch (state held on chip for all T steps) == T single-step launches: every
+    observation, reward, done, the final state and the statistics, with auto-resets inside the rollout."""
+    from gym_ballenv_b200 import BallVecEnv
+    from oracle.gen_golden import CFG_DEFAULT, CFG_DENSE
+    cfg = CFG_DEFAULT if cfgname == "default" else CFG_DENSE
+    T = 64
+    one = BallVecEnv(n, window=w, config=_env_config(cfg), seed=21, max_episode_steps=17)
+    monkeypatch.setenv("BALLENV_NO_ROLLOUT", "1")
+    per = BallVecEnv(n, window=w, config=_env_config(cfg), seed=21, max_episode_steps=17)
+    monkeypatch.delenv("BALLENV_NO_ROLLOUT")
+    assert torch.equal(one.reset(), per.reset())
+    g = torch.Generator().manual_seed(5)
+    for chunk in range(2):
+        a = torch.randint(0, 9, (T, n), generator=g).cuda()
+        o1, r1, d1 = one.step_many(a, keep_all_obs=keep)
+        l0 = per.launch_count
+        o2, r2, d2 = per.step_many(a, keep_all_obs=keep)
+        assert per.launch_count - l0 == T
+        assert torch.equal(o1, o2)
+        assert torch.equal(r1, r2)
+        assert torch.equal(d1, d2)
+    assert one.launch_count == 1 + 2          # reset + one launch per step_many call
+    s1, s2 = one.get_state(), per.get_state()
+    for k in s1:
+        assert torch.equal(s1[k], s2[k]), k
+    st1, st2 = one.stats(), per.stats()
+    for k in st1:
+        assert st1[k] == pytest.approx(st2[k], rel=1e-12), k
+    assert one.error_flags() == 0 and per.error_flags() == 0
+    one.close()
+    per.close()
