@@ -3,10 +3,12 @@
 
     python bench.py --gpus N --steps K --warmup W [--workload c3|w5] [--impl reference]
 
-One bench "step" = one rollout chunk: every environment of the job advances CHUNK env-steps
-(CHUNK fused step+observe launches through ``ballenv_step_many``), writing the whole chunk's
-observations / rewards / dones into a rollout buffer.  ``value`` = env-steps of all ranks / max-over-ranks
-device time.  See DESIGN.md (Measurement) for the byte model behind ``roofline``.
+One bench "step" = one rollout chunk: every environment of the job advances CHUNK env-steps through ONE
+``ballenv_step_many`` call (one launch of the rollout kernel: the block keeps its 32 environments on chip for
+the whole chunk), writing the whole chunk's observations / rewards / dones into a rollout buffer.
+``value`` = env-steps of all ranks / max-over-ranks device time.  ``closed_loop`` repeats the measurement with one
+launch per env-step (``ballenv_step``, what a policy-in-the-loop trainer calls).  See DESIGN.md (Measurement) for
+the byte model behind ``roofline``.
 
 Workloads:
   c3  65 536 envs/GPU, WINDOW=10, 8 static + 24 moving obstacles ("dense moving")   <- headline
@@ -57,6 +59,14 @@ def alg_bytes_per_env_step(spec):
     return reads + writes
 
 
+def moved_bytes_per_env_step(spec, chunk):
+    """Bytes that must cross HBM per env-step in the rollout kernel: action in; observation, reward, done out;
+    the state once per launch (read + write) amortised over the chunk."""
+    w = spec["window"]
+    io = 8 + 4 * (4 + w * w) + 4 + 1
+    return io + (alg_bytes_per_env_step(spec) - io) / float(chunk)
+
+
 def env_config(spec):
     from gym_ballenv_b200 import EnvConfig
     return EnvConfig(static_obstacles=spec["static_obstacles"], dynamic_obstacles=spec["dynamic_obstacles"],
@@ -81,7 +91,7 @@ def config_dict(spec, n, world, chunk):
 class ClockSampler(threading.Thread):
     """Samples SM clock + throttle reasons of one GPU through NVML while a timed region runs."""
 
-    def __init__(self, uuid, index, period=0.004):
+    def __init__(self, uuid, index, period=0.001):
         super().__init__(daemon=True)
         self.period = period
         self.samples = []
@@ -98,6 +108,8 @@ class ClockSampler(threading.Thread):
             except Exception:
                 self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
             self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+            pynvml.nvmlDeviceGetClockInfo(self._h, pynvml.NVML_CLOCK_SM)      # prime the (slow) first query
+            pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
         except Exception as e:  # pragma: no cover
             self.err = repr(e)
 
@@ -202,6 +214,7 @@ def run_reference(args, spec):
 # ----------------------------------------------------------------------------------------- GPU arm
 def measure(env, torch, spec, n, steps, warmup, chunk, dist, world, sampler=None):
     """Device-timed rollout: returns (elapsed_ms max over ranks, launches in the timed region)."""
+    from gym_ballenv_b200 import allreduce_stats
     dev = env.device
     g = torch.Generator(device=dev).manual_seed(1 + env.global_env_offset)
     ring = min(ACTION_RING, steps + warmup)
@@ -222,8 +235,7 @@ def measure(env, torch, spec, n, steps, warmup, chunk, dist, world, sampler=None
     for k in range(steps):
         env.step_many(actions[(warmup + k) % ring], keep_all_obs=True, out=out)
         if world > 1:   # the job's only collective: episode statistics, off the critical path
-            stats_buf = env.stats_tensor.clone()
-            stats_work = dist.all_reduce(stats_buf, op=dist.ReduceOp.SUM, async_op=True)
+            _, stats_work = allreduce_stats(env.stats_tensor, async_op=True)
     ev1.record()
     torch.cuda.synchronize(dev)
     if stats_work is not None:
@@ -288,17 +300,19 @@ def run_gpu(args, spec):
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-    from gym_ballenv_b200 import BallVecEnv
+    from gym_ballenv_b200 import make_sharded_env
     n = args.envs_per_gpu
     chunk = args.chunk
 
-    def make_env(sp):
-        e = BallVecEnv(n, window=sp["window"], config=env_config(sp), seed=0, device=dev,
-                       global_env_offset=rank * n)
+    def make_env(sp):   # weak scaling: n envs per GPU, global ids [rank * n, (rank + 1) * n)
+        e = make_sharded_env(world * n, rank=rank, world=world, device=dev, window=sp["window"],
+                             config=env_config(sp), seed=0)
+        assert e.num_envs == n and e.global_env_offset == rank * n
         e.reset()
         return e
 
     env = make_env(spec)
+    assert env.launch_count == 1
     props = torch.cuda.get_device_properties(dev)
     uuid = "GPU-%s" % props.uuid if hasattr(props, "uuid") else ""
     sampler = ClockSampler(uuid, local)
@@ -312,13 +326,30 @@ def run_gpu(args, spec):
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    kernel_us = ms * 1e3 / (args.steps * chunk)            # average launch-to-launch duration of the step kernel
-    achieved = balg * n / (kernel_us * 1e-6) / 1e9
+    kernel_us = ms * 1e3 / args.steps                      # average duration of one rollout launch (CHUNK env-steps)
+    achieved = balg * n * chunk / (kernel_us * 1e-6) / 1e9
+    moved = moved_bytes_per_env_step(spec, chunk)
     traffic = None
     try:   # per-launch DRAM bytes of the step kernel from the committed ncu capture (profiles/)
         traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(spec["name"])
     except Exception:
         pass
+
+    launches_per_step = launches / float(world * args.steps)
+    # closed loop: the same rollout with one launch per env-step (ballenv_step), i.e. what a trainer with the policy
+    # in the loop pays; bounded to a few chunks
+    closed = None
+    if args.closed_loop_steps > 0:
+        os.environ["BALLENV_NO_ROLLOUT"] = "1"
+        env_c = make_env(spec)
+        os.environ["BALLENV_NO_ROLLOUT"] = "0"
+        cs = args.closed_loop_steps
+        msc, lc, _, _ = measure(env_c, torch, spec, n, cs, 3, chunk, dist, world)
+        us = msc * 1e3 / (cs * chunk)
+        closed = {"value": float(world) * n * chunk * cs / (msc * 1e-3), "unit": UNIT, "avg_launch_us": us,
+                  "gpu_launches": lc, "kernel": "ballenv_kernel<float,%d,fast,single-step>" % spec["window"],
+                  "roofline_frac": balg * n / (us * 1e-6) / 1e9 / peak, "alg_bytes_per_env_step": balg}
+        env_c.close()
 
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     ems, h2d, d2h, e2e_launches = measure_e2e(env, torch, n, e2e_steps, chunk, dist, world)
@@ -335,7 +366,8 @@ def run_gpu(args, spec):
         v2 = float(world) * n * chunk * max(3, args.steps // 4) / (ms2 * 1e-3)
         b2 = alg_bytes_per_env_step(sp2)
         secondary = {"workload": sp2["text"], "value": v2, "unit": UNIT,
-                     "roofline_frac": (v2 / world) * b2 / 1e9 / peak, "alg_bytes_per_env_step": b2}
+                     "roofline_frac": (v2 / world) * b2 / 1e9 / peak, "alg_bytes_per_env_step": b2,
+                     "frac_moved": (v2 / world) * moved_bytes_per_env_step(sp2, chunk) / 1e9 / peak}
         env2.close()
 
     base = None
@@ -351,8 +383,15 @@ def run_gpu(args, spec):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650",
-                         "kernel": "ballenv_kernel<float,%d>" % spec["window"],
-                         "alg_bytes_per_env_step": balg, "envs_per_launch": n, "avg_launch_us": kernel_us},
+                         "kernel": "ballenv_kernel<float,%d,fast,rollout>" % spec["window"],
+                         "alg_bytes_per_env_step": balg, "env_steps_per_launch": n * chunk,
+                         "avg_launch_us": kernel_us, "launches_per_bench_step": launches_per_step,
+                         "note": "achieved = SURVEY 8(d) algorithmic bytes x env-steps per launch / launch time; the "
+                                 "rollout kernel keeps the state on chip, so only hbm_bytes_per_env_step_moved must "
+                                 "cross HBM per env-step (frac_moved is that stream against the same peak)",
+                         "hbm_bytes_per_env_step_moved": moved,
+                         "frac_moved": moved * n * chunk / (kernel_us * 1e-6) / 1e9 / peak},
+            "closed_loop": closed,
             "cpu_baseline": base,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "api": "ballenv_step_host (C ABI), pinned host buffers, fp32 obs to host "
@@ -373,13 +412,14 @@ def run_gpu(args, spec):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3", choices=["c3", "w5"])
     ap.add_argument("--envs-per-gpu", type=int, default=65536)
     ap.add_argument("--chunk", type=int, default=CHUNK)
     ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--closed-loop-steps", type=int, default=5)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--secondary", type=int, default=1)

@@ -5,6 +5,7 @@ Public surface
   BallEnv, make           the registered gym env's API on the same kernels (env.py)
   EnvConfig               the reference's argparse fields as a dataclass (config.py)
   make_prep_state         prep_state2 / prep_state4 of examples/ball_cnn_ac3.py, GPU-evaluated
+  make_sharded_env, shard_bounds, allreduce_stats   one process per GPU, envs partitioned by global id (distributed.py)
 Importing this package loads libballenv_b200.so (built by ``python -m gym_ballenv_b200.build``);
 there is no CPU fallback.
 """
@@ -13,9 +14,10 @@ from ._lib import (LIB, BallenvError, FLAG_GOAL, FLAG_HIT, FLAG_HIT_DYNAMIC, FLA
 from .config import EnvConfig
 from .env import BallEnv, TimeLimit, make, make_prep_state
 from .vec_env import MOVE_LIST, BallVecEnv
+from .distributed import allreduce_stats, make_sharded_env, shard_bounds
 
 __all__ = ["BallVecEnv", "BallEnv", "TimeLimit", "make", "make_prep_state", "EnvConfig", "MOVE_LIST",
-           "BallenvError", "FLAG_GOAL", "FLAG_HIT", "FLAG_TRUNCATED", "FLAG_HIT_DYNAMIC", "STAT_NAMES", "LIB_PATH"]
+           "allreduce_stats", "make_sharded_env", "shard_bounds", "BallenvError", "FLAG_GOAL", "FLAG_HIT", "FLAG_TRUNCATED", "FLAG_HIT_DYNAMIC", "STAT_NAMES", "LIB_PATH"]
 
 
 def _register_with_gym():

@@ -13,6 +13,11 @@
 
 namespace ballenv {
 void BALLENV_NAME(const Params& p, unsigned grid, cudaStream_t s) {
-  ballenv_kernel<BALLENV_T, BALLENV_W, (BALLENV_FAST != 0)><<<grid, kBlock, 0, s>>>(p);
+#if BALLENV_FAST
+  if (p.n_steps > 1) ballenv_kernel<BALLENV_T, BALLENV_W, true, true><<<grid, kBlock, 0, s>>>(p);
+  else ballenv_kernel<BALLENV_T, BALLENV_W, true, false><<<grid, kBlock, 0, s>>>(p);
+#else
+  ballenv_kernel<BALLENV_T, BALLENV_W, false, false><<<grid, kBlock, 0, s>>>(p);
+#endif
 }
 }  // namespace ballenv

@@ -262,7 +262,7 @@ struct BlockShared {
 
 // Rare path of the bounding-box test: hit-test the obstacle and queue it for the raster.
 template <typename T, int W>
-__device__ __noinline__ void near_push(BlockShared<T, W>& sh, uint32_t* words, const DevConfig& cfg, int el, T ax, T ay,
+__device__ __forceinline__ void near_push(BlockShared<T, W>& sh, uint32_t* words, const DevConfig& cfg, int el, T ax, T ay,
                                        T ox, T oy, int k, bool want_hit, bool want_obs, int nb) {
   const Overlap<T> ov(cfg.radius_sum);
   if (want_hit && ov(r_sub(ax, ox), r_sub(ay, oy))) atomicMin(&sh.hit[el], k);
@@ -437,7 +437,7 @@ constexpr uint32_t kAgentDy = 2u | 0u << 2 | 1u << 4 | 2u << 6 | 0u << 8 | 1u <<
 __device__ __forceinline__ int table2(uint32_t packed, uint32_t i) { return (int)((packed >> (2 * i)) & 3u) - 1; }
 
 template <typename T>
-__device__ __noinline__ void move_obstacle(const DevConfig& cfg, const typename Vec2<T>::type* s_goal, int j,
+__device__ __forceinline__ void move_obstacle(const DevConfig& cfg, const typename Vec2<T>::type* s_goal, int j,
                                            uint32_t w1, uint32_t w2_tape, bool has_tape, T& x, T& y,
                                            uint32_t& meta) {
   uint32_t gi = meta & 0xffu, cnt = meta >> 8;
@@ -598,14 +598,7 @@ __device__ __forceinline__ void dynamic_move(const Params& p, const BlockShared<
         w2 = tw.y;
       }
       if (cfg.goals_distinct) move_lean<T, W>(cfg, sh, j, w1, w2, x[i], y[i], meta[i]);
-      else {   // out-of-line generic path: temporaries keep the quad arrays themselves in registers
-        T tx = x[i], ty = y[i];
-        uint32_t tm = meta[i];
-        move_obstacle<T>(cfg, sh.goal, j, w1, w2, true, tx, ty, tm);
-        x[i] = tx;
-        y[i] = ty;
-        meta[i] = tm;
-      }
+      else move_obstacle<T>(cfg, sh.goal, j, w1, w2, true, x[i], y[i], meta[i]);
     }
   }
 }
@@ -790,7 +783,8 @@ __device__ __forceinline__ bool bar_or(int id, bool pred) {
 // kFast: the production specialisation - Step mode, gym ruleset, Philox draws (no tapes), distinct obstacle goals,
 // index actions, fp32 observation rows requested.  Every uniform test of the generic kernel folds away; the host
 // (ballenv_capi.cu) selects it when all of that holds.
-template <typename T, int W, bool kFast>
+// kRollout: p.n_steps may exceed 1 (ballenv_step_many); otherwise the step loop has exactly one trip and folds away.
+template <typename T, int W, bool kFast, bool kRollout>
 __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __grid_constant__ Params p) {
   __shared__ BlockShared<T, W> sh;
   const DevConfig& cfg = p.cfg;
@@ -801,11 +795,12 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
   const int nb = 4 + w * w;
   const int ks = cfg.ks, kd = cfg.kd;
   const bool stepping = kFast || p.mode == kModeStep;
-  const int n_steps = kFast ? p.n_steps : 1;
+  const int n_steps = kRollout ? p.n_steps : 1;
   const size_t obs_step_bytes = (size_t)p.n * (size_t)cfg.obs_row_elems * (cfg.obs_format == BALLENV_OBS_U8 ? 1u : 4u);
   if (p.debug & 1) return;
 
   if (tid < 32) {
+
     // =============================== scalar warp: one thread per environment =====================================
     const bool gym = kFast || cfg.ruleset == BALLENV_RULESET_GYM;
     T* agent_x = reinterpret_cast<T*>(p.agent_x);
@@ -815,218 +810,224 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
     const long long e = e0 + tid;
     const bool mine = tid < cnt_env;
     bool reset_req = false;
-    // ---- state of the environment, in registers for the whole launch
+    // ---- state of the environment, in registers while the hot loop runs
     T ax = (T)0, ay = (T)0, gx = (T)0, gy = (T)0;
     double dist = 0.0, total = 1.0, acc = 0.0;
     int len = 0;
     uint32_t tick = 0, flags = 0;
-    if (mine) {
-      if (!kFast && p.mode == kModeReset) reset_req = p.reset_mask == nullptr || p.reset_mask[e] != 0;
-      if (!reset_req) {
-        ax = agent_x[e];
-        ay = agent_y[e];
-        gx = goal_x[e];
-        gy = goal_y[e];
-      }
-      if (stepping) {
-        dist = p.dist[e];
-        total = p.total[e];
-        acc = p.acc[e];
-        len = p.ep_len[e];
-        tick = p.tick[e];
-      }
-    }
+    if (mine && !kFast && p.mode == kModeReset) reset_req = p.reset_mask == nullptr || p.reset_mask[e] != 0;
     if (tid < 16)
       sh.lut[tid] = make_float4(tid & 1 ? 1.0f : 0.0f, tid & 2 ? 1.0f : 0.0f, tid & 4 ? 1.0f : 0.0f, tid & 8 ? 1.0f : 0.0f);
 
-    for (int t = 0; t < n_steps; ++t) {
-      const bool want_obs = kFast ? (p.obs_all_steps != 0 || t == n_steps - 1) : p.obs != nullptr;
-      uint32_t* words = sh.words[t & 1];
-      const long long et = (long long)t * p.n + e;   // index of this environment in the [T][n] arrays
-      T nx = ax, ny = ay;
-      if (mine && stepping) {
-        // agent move + clamp (ballenv_env.py:247-259 | ballenv_pygame.py:654-664)
-        T adx, ady;
-        if (!kFast && p.action_kind == BALLENV_ACT_XY_F32) {
-          const float2 a = reinterpret_cast<const float2*>(p.actions)[et];
-          adx = (T)a.x;
-          ady = (T)a.y;
-        } else if (!kFast && p.action_kind == BALLENV_ACT_XY_F64) {
-          const double2 a = reinterpret_cast<const double2*>(p.actions)[et];
-          adx = (T)a.x;
-          ady = (T)a.y;
-        } else {
-          long long ai;
-          if (p.action_kind == BALLENV_ACT_INDEX_I64) ai = reinterpret_cast<const long long*>(p.actions)[et];
-          else if (p.action_kind == BALLENV_ACT_INDEX_I32) ai = reinterpret_cast<const int*>(p.actions)[et];
-          else ai = reinterpret_cast<const uint8_t*>(p.actions)[et];
-          if (ai < 0 || ai > 8) {
-            atomicOr(p.errors, (uint32_t)BALLENV_DEVERR_BAD_ACTION);
-            ai = 5;  // (0, 0)
-          }
-          adx = (T)table2(kAgentDx, (uint32_t)ai);
-          ady = (T)table2(kAgentDy, (uint32_t)ai);
-        }
-        if (gym) {
-          nx = r_add(ax, r_mul(CfgV<T>::step_x(cfg), adx));   // speedx_ctrl_person * action[0]
-          ny = r_add(ay, r_mul(CfgV<T>::step_y(cfg), ady));
-        } else {
-          nx = r_add(ax, adx);
-          ny = r_add(ay, ady);
-        }
-        if (nx < (T)0) nx = (T)0;
-        if (ny < (T)0) ny = (T)0;
-        if (nx > CfgV<T>::world_w(cfg)) nx = CfgV<T>::world_w(cfg);
-        if (ny > CfgV<T>::world_h(cfg)) ny = CfgV<T>::world_h(cfg);
-      }
-      sh.ax[tid] = nx;
-      sh.ay[tid] = ny;
-      sh.hit[tid] = kNoHit;
-      sh.reset[tid] = reset_req ? 1 : 0;   // Reset mode: stored obstacles of these environments are ignored
-      if (tid == 0) sh.count = 0;
-      bar_arrive(kBarAgent);
-
-      // distance, progress reward, goal and time-limit flags do not depend on the obstacles: computed while the
-      // obstacle threads move and test (ballenv_env.py:268-286, 200-206 | ballenv_pygame.py:652-706)
-      double d = dist, reward = 0.0;
-      bool goal_flag = false, truncated = false;
-      const int ep_len = len + 1;
-      if (mine && stepping && !(p.debug & 16)) {
-        d = dist64((double)gx, (double)gy, (double)nx, (double)ny);               // :268 | :668
-        truncated = cfg.max_steps > 0 && ep_len >= cfg.max_steps;
-        goal_flag = d < cfg.goal_threshold;                                      // :276 | :690 (pygame: unless hit)
-        if (gym) {
-          reward = (dist - d) / total;                                           // :205-206, old = state[2] (:236)
-        } else {
-          const double od = dist64((double)ax, (double)ay, (double)gx, (double)gy);   // :652
-          reward = (od - d) / total;                                             // :699-706
-        }
-      }
-      bar_sync(kBarNear);
-
-      bool do_reset = false, done_out = false, hit = false, hit_dyn = false, done = false;
+    int t = 0;
+    for (;;) {
+      // (re)load: at launch, and after a reset went through global memory
       if (mine) {
-        if (stepping) {
-          const int hit_first = sh.hit[tid];
-          hit = hit_first != kNoHit;
-          hit_dyn = hit && hit_first >= ks;
-          if (gym) {
-            if (hit) reward -= hit_dyn ? cfg.dynamic_penalty : cfg.static_penalty;  // :222-224
-            acc += reward;                                                          // :280
-            done = goal_flag || hit;                                                // :286
-          } else {
-            if (hit) {                                                              // :683-688 (before the goal test)
-              goal_flag = false;
-              reward = -1.0;
-              done = true;
-            } else if (goal_flag) {                                                 // :690-697
-              reward = 1.0;
-              done = true;
-            }
-            acc += reward;
-          }
-          done_out = done || truncated;
-          do_reset = done_out && cfg.auto_reset;
-        } else if (!kFast && reset_req) {
-          do_reset = true;
-        }
-        if (do_reset) {
-          sh.reset[tid] = 1;
-        } else if (want_obs) {
-          // 4 goal-quadrant bits (examples/ball_cnn_ac3.py:341-350); the obstacle warps are OR-ing cells concurrently
-          const T qdx = r_sub(gx, nx), qdy = r_sub(gy, ny);
-          const int b = tid * nb + goal_quadrant_bit(qdx < (T)0, qdy < (T)0);
-          atomicOr(&words[b >> 5], 1u << (b & 31));
-        }
-      }
-      const bool any_reset = bar_or(kBarDone, do_reset);
-
-      // outputs of the step and statistics: nobody waits for these
-      double st_ret = 0.0, st_len = 0.0;
-      uint32_t st_cnt = 0;  // episode | goal << 1 | hit_static << 2 | hit_dynamic << 3 | timeout << 4
-      if (mine && stepping) {
-        flags = (goal_flag ? BALLENV_FLAG_GOAL : 0) | (hit ? BALLENV_FLAG_HIT : 0) |
-                (truncated ? BALLENV_FLAG_TRUNCATED : 0) | (hit_dyn ? BALLENV_FLAG_HIT_DYNAMIC : 0);
-        if (p.reward != nullptr) {
-          if (sizeof(T) == 4) reinterpret_cast<float*>(p.reward)[et] = (float)reward;
-          else reinterpret_cast<double*>(p.reward)[et] = reward;
-        }
-        if (p.done != nullptr) p.done[et] = done_out ? 1 : 0;
-        if (done_out) {
-          st_ret = acc;
-          st_len = (double)ep_len;
-          st_cnt = 1u | (goal_flag ? 2u : 0u) | ((hit && !hit_dyn) ? 4u : 0u) | (hit_dyn ? 8u : 0u) |
-                   ((truncated && !done) ? 16u : 0u);
-        }
-        ax = nx;
-        ay = ny;
-        dist = d;
-        len = ep_len;
-        tick += 1;
-      }
-      if (stepping) {
-        // episode statistics (the only thing that is ever all-reduced across GPUs): ballot + shuffle in the scalar
-        // warp, one atomic per counter per block, and only in blocks where an episode ended.
-        const uint32_t fin = __ballot_sync(0xffffffffu, st_cnt != 0);
-        if (fin != 0) {
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            st_ret += __shfl_xor_sync(0xffffffffu, st_ret, o);
-            st_len += __shfl_xor_sync(0xffffffffu, st_len, o);
-          }
-          const uint32_t n_goal = __popc(__ballot_sync(0xffffffffu, st_cnt & 2u));
-          const uint32_t n_hs = __popc(__ballot_sync(0xffffffffu, st_cnt & 4u));
-          const uint32_t n_hd = __popc(__ballot_sync(0xffffffffu, st_cnt & 8u));
-          const uint32_t n_to = __popc(__ballot_sync(0xffffffffu, st_cnt & 16u));
-          if (tid == 0) {
-            atomicAdd(&p.stats[BALLENV_STAT_EPISODES], (double)__popc(fin));
-            atomicAdd(&p.stats[BALLENV_STAT_RETURN_SUM], st_ret);
-            atomicAdd(&p.stats[BALLENV_STAT_LENGTH_SUM], st_len);
-            if (n_goal) atomicAdd(&p.stats[BALLENV_STAT_GOALS], (double)n_goal);
-            if (n_hs) atomicAdd(&p.stats[BALLENV_STAT_HITS_STATIC], (double)n_hs);
-            if (n_hd) atomicAdd(&p.stats[BALLENV_STAT_HITS_DYNAMIC], (double)n_hd);
-            if (n_to) atomicAdd(&p.stats[BALLENV_STAT_TIMEOUTS], (double)n_to);
-          }
-        }
-        if (e == 0) atomicAdd(&p.stats[BALLENV_STAT_STEPS], (double)p.n);
-      }
-
-      // (rare) reset through global memory, then take the new episode's scalars into the registers
-      if (any_reset) {
-        reset_stage<T, W>(p, sh, words, e0, cnt_env, want_obs);
-        if (mine && do_reset) {
+        if (!reset_req) {
           ax = agent_x[e];
           ay = agent_y[e];
           gx = goal_x[e];
           gy = goal_y[e];
+        }
+        if (stepping) {
           dist = p.dist[e];
           total = p.total[e];
-          acc = 0.0;
-          len = 0;
+          acc = p.acc[e];
+          len = p.ep_len[e];
+          tick = p.tick[e];
         }
       }
-      if (want_obs && !(p.debug & 8)) {
-        const Params& pp = p;
-        store_obs<W, kFast>(pp, reinterpret_cast<char*>(p.obs) + (kFast && p.obs_all_steps ? (size_t)t * obs_step_bytes : 0),
-                            words, sh.lut, e0, cnt_env);
-      }
-    }
+      bool pending_reset = false;
+      // ------------------------------------------- hot loop: no calls inside -------------------------------------
+      for (; t < n_steps; ++t) {
+        const bool want_obs = kFast ? (p.obs_all_steps != 0 || t == n_steps - 1) : p.obs != nullptr;
+        uint32_t* words = sh.words[t & 1];
+        const long long et = (long long)t * p.n + e;   // index of this environment in the [T][n] arrays
+        T nx = ax, ny = ay;
+        if (mine && stepping) {
+          // agent move + clamp (ballenv_env.py:247-259 | ballenv_pygame.py:654-664)
+          T adx, ady;
+          if (!kFast && p.action_kind == BALLENV_ACT_XY_F32) {
+            const float2 a = reinterpret_cast<const float2*>(p.actions)[et];
+            adx = (T)a.x;
+            ady = (T)a.y;
+          } else if (!kFast && p.action_kind == BALLENV_ACT_XY_F64) {
+            const double2 a = reinterpret_cast<const double2*>(p.actions)[et];
+            adx = (T)a.x;
+            ady = (T)a.y;
+          } else {
+            long long ai;
+            if (p.action_kind == BALLENV_ACT_INDEX_I64) ai = reinterpret_cast<const long long*>(p.actions)[et];
+            else if (p.action_kind == BALLENV_ACT_INDEX_I32) ai = reinterpret_cast<const int*>(p.actions)[et];
+            else ai = reinterpret_cast<const uint8_t*>(p.actions)[et];
+            if (ai < 0 || ai > 8) {
+              atomicOr(p.errors, (uint32_t)BALLENV_DEVERR_BAD_ACTION);
+              ai = 5;  // (0, 0)
+            }
+            adx = (T)table2(kAgentDx, (uint32_t)ai);
+            ady = (T)table2(kAgentDy, (uint32_t)ai);
+          }
+          if (gym) {
+            nx = r_add(ax, r_mul(CfgV<T>::step_x(cfg), adx));   // speedx_ctrl_person * action[0]
+            ny = r_add(ay, r_mul(CfgV<T>::step_y(cfg), ady));
+          } else {
+            nx = r_add(ax, adx);
+            ny = r_add(ay, ady);
+          }
+          if (nx < (T)0) nx = (T)0;
+          if (ny < (T)0) ny = (T)0;
+          if (nx > CfgV<T>::world_w(cfg)) nx = CfgV<T>::world_w(cfg);
+          if (ny > CfgV<T>::world_h(cfg)) ny = CfgV<T>::world_h(cfg);
+        }
+        sh.ax[tid] = nx;
+        sh.ay[tid] = ny;
+        sh.hit[tid] = kNoHit;
+        sh.reset[tid] = reset_req ? 1 : 0;   // Reset mode: stored obstacles of these environments are ignored
+        if (tid == 0) sh.count = 0;
+        bar_arrive(kBarAgent);
 
-    // ---- write the scalar state back
-    if (mine) {
-      if (stepping) {
-        agent_x[e] = ax;
-        agent_y[e] = ay;
-        p.dist[e] = dist;
-        p.acc[e] = acc;
-        p.ep_len[e] = len;
-        p.tick[e] = tick;
-        p.flags[e] = (uint8_t)flags;
-      } else if (reset_req) {
-        p.flags[e] = 0;
+        // distance, progress reward, goal and time-limit flags do not depend on the obstacles: computed while the
+        // obstacle threads move and test (ballenv_env.py:268-286, 200-206 | ballenv_pygame.py:652-706)
+        double d = dist, reward = 0.0;
+        bool goal_flag = false, truncated = false;
+        const int ep_len = len + 1;
+        if (mine && stepping && !(p.debug & 16)) {
+          d = dist64((double)gx, (double)gy, (double)nx, (double)ny);               // :268 | :668
+          truncated = cfg.max_steps > 0 && ep_len >= cfg.max_steps;
+          goal_flag = d < cfg.goal_threshold;                                      // :276 | :690 (pygame: unless hit)
+          if (gym) {
+            reward = (dist - d) / total;                                           // :205-206, old = state[2] (:236)
+          } else {
+            const double od = dist64((double)ax, (double)ay, (double)gx, (double)gy);   // :652
+            reward = (od - d) / total;                                             // :699-706
+          }
+        }
+        bar_sync(kBarNear);
+
+        bool do_reset = false, done_out = false, hit = false, hit_dyn = false, done = false;
+        if (mine) {
+          if (stepping) {
+            const int hit_first = sh.hit[tid];
+            hit = hit_first != kNoHit;
+            hit_dyn = hit && hit_first >= ks;
+            if (gym) {
+              if (hit) reward -= hit_dyn ? cfg.dynamic_penalty : cfg.static_penalty;  // :222-224
+              acc += reward;                                                          // :280
+              done = goal_flag || hit;                                                // :286
+            } else {
+              if (hit) {                                                              // :683-688 (before the goal test)
+                goal_flag = false;
+                reward = -1.0;
+                done = true;
+              } else if (goal_flag) {                                                 // :690-697
+                reward = 1.0;
+                done = true;
+              }
+              acc += reward;
+            }
+            done_out = done || truncated;
+            do_reset = done_out && cfg.auto_reset;
+          } else if (!kFast && reset_req) {
+            do_reset = true;
+          }
+          if (do_reset) {
+            sh.reset[tid] = 1;
+          } else if (want_obs) {
+            // 4 goal-quadrant bits (examples/ball_cnn_ac3.py:341-350); the obstacle warps are OR-ing cells concurrently
+            const T qdx = r_sub(gx, nx), qdy = r_sub(gy, ny);
+            const int b = tid * nb + goal_quadrant_bit(qdx < (T)0, qdy < (T)0);
+            atomicOr(&words[b >> 5], 1u << (b & 31));
+          }
+        }
+        const bool any_reset = bar_or(kBarDone, do_reset);
+
+        // outputs of the step and statistics: nobody waits for these
+        double st_ret = 0.0, st_len = 0.0;
+        uint32_t st_cnt = 0;  // episode | goal << 1 | hit_static << 2 | hit_dynamic << 3 | timeout << 4
+        if (mine && stepping) {
+          flags = (goal_flag ? BALLENV_FLAG_GOAL : 0) | (hit ? BALLENV_FLAG_HIT : 0) |
+                  (truncated ? BALLENV_FLAG_TRUNCATED : 0) | (hit_dyn ? BALLENV_FLAG_HIT_DYNAMIC : 0);
+          if (p.reward != nullptr) {
+            if (sizeof(T) == 4) reinterpret_cast<float*>(p.reward)[et] = (float)reward;
+            else reinterpret_cast<double*>(p.reward)[et] = reward;
+          }
+          if (p.done != nullptr) p.done[et] = done_out ? 1 : 0;
+          if (done_out) {
+            st_ret = acc;
+            st_len = (double)ep_len;
+            st_cnt = 1u | (goal_flag ? 2u : 0u) | ((hit && !hit_dyn) ? 4u : 0u) | (hit_dyn ? 8u : 0u) |
+                     ((truncated && !done) ? 16u : 0u);
+          }
+          ax = nx;
+          ay = ny;
+          dist = d;
+          len = ep_len;
+          tick += 1;
+        }
+        if (stepping) {
+          // episode statistics (the only thing that is ever all-reduced across GPUs): ballot + shuffle in the scalar
+          // warp, one atomic per counter per block, and only in blocks where an episode ended.
+          const uint32_t fin = __ballot_sync(0xffffffffu, st_cnt != 0);
+          if (fin != 0) {
+  #pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              st_ret += __shfl_xor_sync(0xffffffffu, st_ret, o);
+              st_len += __shfl_xor_sync(0xffffffffu, st_len, o);
+            }
+            const uint32_t n_goal = __popc(__ballot_sync(0xffffffffu, st_cnt & 2u));
+            const uint32_t n_hs = __popc(__ballot_sync(0xffffffffu, st_cnt & 4u));
+            const uint32_t n_hd = __popc(__ballot_sync(0xffffffffu, st_cnt & 8u));
+            const uint32_t n_to = __popc(__ballot_sync(0xffffffffu, st_cnt & 16u));
+            if (tid == 0) {
+              atomicAdd(&p.stats[BALLENV_STAT_EPISODES], (double)__popc(fin));
+              atomicAdd(&p.stats[BALLENV_STAT_RETURN_SUM], st_ret);
+              atomicAdd(&p.stats[BALLENV_STAT_LENGTH_SUM], st_len);
+              if (n_goal) atomicAdd(&p.stats[BALLENV_STAT_GOALS], (double)n_goal);
+              if (n_hs) atomicAdd(&p.stats[BALLENV_STAT_HITS_STATIC], (double)n_hs);
+              if (n_hd) atomicAdd(&p.stats[BALLENV_STAT_HITS_DYNAMIC], (double)n_hd);
+              if (n_to) atomicAdd(&p.stats[BALLENV_STAT_TIMEOUTS], (double)n_to);
+            }
+          }
+          if (e == 0) atomicAdd(&p.stats[BALLENV_STAT_STEPS], (double)p.n);
+        }
+        if (any_reset) {   // leave the hot loop: the reset goes through global memory
+          pending_reset = true;
+          break;
+        }
+        if (want_obs && !(p.debug & 8))
+          store_obs<W, kFast>(p, reinterpret_cast<char*>(p.obs) + (kFast && p.obs_all_steps ? (size_t)t * obs_step_bytes : 0),
+                              words, sh.lut, e0, cnt_env);
+      }
+
+      // ---- write the scalar state back (a pending reset then overwrites it for the environments that finished)
+      if (mine) {
+        if (stepping) {
+          agent_x[e] = ax;
+          agent_y[e] = ay;
+          p.dist[e] = dist;
+          p.acc[e] = acc;
+          p.ep_len[e] = len;
+          p.tick[e] = tick;
+          p.flags[e] = (uint8_t)flags;
+        } else if (reset_req) {
+          p.flags[e] = 0;
+        }
+      }
+      if (!pending_reset) break;
+      {
+        // (rare) the step that is being finished is t: reset, then its observation
+        const bool want_obs = kFast ? (p.obs_all_steps != 0 || t == n_steps - 1) : p.obs != nullptr;
+        uint32_t* words = sh.words[t & 1];
+        reset_stage<T, W>(p, sh, words, e0, cnt_env, want_obs);
+        if (want_obs && !(p.debug & 8))
+          store_obs<W, kFast>(p, reinterpret_cast<char*>(p.obs) + (kFast && p.obs_all_steps ? (size_t)t * obs_step_bytes : 0),
+                              words, sh.lut, e0, cnt_env);
+        reset_req = false;
+        if (++t >= n_steps) break;
       }
     }
   } else {
+
     // =============================== obstacle threads: one quad per thread per iteration =========================
     const int lt = tid - 32;
     const int qs = (ks + 3) >> 2, qd = (kd + 3) >> 2;         // static / dynamic quads per environment
@@ -1037,7 +1038,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
     const T* stat_x = reinterpret_cast<const T*>(p.stat_x);
     const T* stat_y = reinterpret_cast<const T*>(p.stat_y);
 
-    // ---- the thread's own quad (slot lt), in registers for the whole launch: issue its loads before anything else
+    // ---- the thread's own quad (slot lt), in registers while the hot loop runs
     T qx[4], qy[4];
     uint32_t qm[4];
     uint32_t tick = 0;
@@ -1053,20 +1054,9 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
       q_have = q_el < cnt_env;
       if (!kFast && q_have && p.mode == kModeReset)
         q_have = p.reset_mask == nullptr ? false : p.reset_mask[e0 + q_el] == 0;
-      if (q_have) {
-        if (!q_dyn) {
-          q_k0 = 4 * qq;
-          q_kend = ks;
-          load4(stat_x + q_off, qx);
-          load4(stat_y + q_off, qy);
-        } else {
-          q_jq = qq;
-          q_k0 = ks + 4 * qq;
-          q_kend = ks + kd;
-          if (stepping) tick = p.tick[e0 + q_el];
-          dynamic_load<T>(p, q_off, stepping, qx, qy, qm);
-        }
-      }
+      q_jq = qq;
+      q_k0 = q_dyn ? ks + 4 * qq : 4 * qq;
+      q_kend = q_dyn ? ks + kd : ks;
     }
     // block setup shared by the obstacle threads: cleared bit-stream; goal and move tables.  Every warp writes the
     // (identical) table entries it is going to read, so a warp-level sync is all the moves below need.
@@ -1081,83 +1071,97 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
       __syncwarp();
     }
 
-    for (int t = 0; t < n_steps; ++t) {
-      const bool want_obs = kFast ? (p.obs_all_steps != 0 || t == n_steps - 1) : p.obs != nullptr;
-      uint32_t* words = sh.words[t & 1];
-      // obstacle motion does not depend on the agent: draw and move while the scalar warp works
-      if (q_have && q_dyn && stepping && !(p.debug & 2)) {
-        if (kFast || (p.step_tape == nullptr && cfg.goals_distinct))
-          dynamic_move<T, W, true>(p, sh, e0 + q_el, q_jq, tick + (uint32_t)t, qx, qy, qm);
-        else
-          dynamic_move<T, W, false>(p, sh, e0 + q_el, q_jq, tick + (uint32_t)t, qx, qy, qm);
-      }
-      bar_sync(kBarAgent);   // agent positions published; everybody is done with the previous step's bit-stream
-      if (t + 1 < n_steps)
-        for (int i = lt; i < nb; i += kLaneThreads) sh.words[(t + 1) & 1][i] = 0;
-
-      // bounding-box test every obstacle against the agent; near ones are hit-tested and queued
-      if (q_have && !(p.debug & 4)) {
-        const T ax = sh.ax[q_el], ay = sh.ay[q_el];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          if (q_k0 + i < q_kend)
-            near_test<T, W>(sh, words, cfg, q_el, ax, ay, margin, qx[i], qy[i], q_k0 + i, stepping, want_obs, nb);
-      }
-      for (int slot = lt + kLaneThreads; slot < n_slot; slot += kLaneThreads) {   // more than 8 quads per environment
-        const bool dyn = slot >= n_stat;
-        const int sl = dyn ? slot - n_stat : slot;
-        const int per = dyn ? qd : qs;
-        const int el = div_slot(sl, dyn ? cfg.rcp_qd : cfg.rcp_qs), qq = sl - el * per;
-        if (el >= cnt_env || sh.reset[el] != 0) continue;
-        T x[4], y[4];
-        if (!dyn) {
-          load4(stat_x + stat0 + 4u * (uint32_t)sl, x);
-          load4(stat_y + stat0 + 4u * (uint32_t)sl, y);
+    int t = 0, t_load = 0;
+    for (;;) {
+      // (re)load the quad: at launch, and after a reset went through global memory
+      t_load = t;
+      if (q_have) {
+        if (!q_dyn) {
+          load4(stat_x + q_off, qx);
+          load4(stat_y + q_off, qy);
         } else {
-          uint32_t m[4];
-          const uint32_t off = dyn0 + 4u * (uint32_t)sl;
-          dynamic_load<T>(p, off, stepping, x, y, m);
-          if (stepping) {
-            dynamic_move<T, W, false>(p, sh, e0 + el, qq, p.tick[e0 + el] + (uint32_t)t, x, y, m);
-            dynamic_store<T>(p, off, x, y, m);
-          }
+          if (stepping) tick = p.tick[e0 + q_el] - (uint32_t)t;   // tick of step 0 of this launch
+          dynamic_load<T>(p, q_off, stepping, qx, qy, qm);
         }
-        const int k0 = dyn ? ks + 4 * qq : 4 * qq, kend = dyn ? ks + kd : ks;
-        const T ax = sh.ax[el], ay = sh.ay[el];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          if (k0 + i < kend)
-            near_test<T, W>(sh, words, cfg, el, ax, ay, margin, x[i], y[i], k0 + i, stepping, want_obs, nb);
       }
-      bar_sync(kBarNear);
+      bool pending_reset = false;
+      // ------------------------------------------- hot loop: no calls inside -------------------------------------
+      for (; t < n_steps; ++t) {
+        const bool want_obs = kFast ? (p.obs_all_steps != 0 || t == n_steps - 1) : p.obs != nullptr;
+        uint32_t* words = sh.words[t & 1];
+        // obstacle motion does not depend on the agent: draw and move while the scalar warp works
+        if (q_have && q_dyn && stepping && !(p.debug & 2)) {
+          if (kFast || (p.step_tape == nullptr && cfg.goals_distinct))
+            dynamic_move<T, W, true>(p, sh, e0 + q_el, q_jq, tick + (uint32_t)t, qx, qy, qm);
+          else
+            dynamic_move<T, W, false>(p, sh, e0 + q_el, q_jq, tick + (uint32_t)t, qx, qy, qm);
+        }
+        bar_sync(kBarAgent);   // agent positions published; everybody is done with the previous step's bit-stream
+        if (t + 1 < n_steps)
+          for (int i = lt; i < nb; i += kLaneThreads) sh.words[(t + 1) & 1][i] = 0;
 
-      // block-cooperative raster of the near list
-      if (want_obs) raster_list<T, W>(sh, words, cfg, lt, nb);
-      const bool any_reset = bar_or(kBarDone, false);
-
-      // (rare) reset through global memory, then take the new episode's quad into the registers
-      if (any_reset) {
-        const bool mine_reset = q_have && sh.reset[q_el] != 0;
-        // the quads of the finished episode may be overwritten; everybody else's registers stay authoritative
-        reset_stage<T, W>(p, sh, words, e0, cnt_env, want_obs);
-        if (mine_reset) {
-          if (!q_dyn) {
-            load4(stat_x + q_off, qx);
-            load4(stat_y + q_off, qy);
+        // bounding-box test every obstacle against the agent; near ones are hit-tested and queued
+        if (q_have && !(p.debug & 4)) {
+          const T ax = sh.ax[q_el], ay = sh.ay[q_el];
+  #pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (q_k0 + i < q_kend)
+              near_test<T, W>(sh, words, cfg, q_el, ax, ay, margin, qx[i], qy[i], q_k0 + i, stepping, want_obs, nb);
+        }
+        for (int slot = lt + kLaneThreads; slot < n_slot; slot += kLaneThreads) {   // more than 8 quads per environment
+          const bool dyn = slot >= n_stat;
+          const int sl = dyn ? slot - n_stat : slot;
+          const int per = dyn ? qd : qs;
+          const int el = div_slot(sl, dyn ? cfg.rcp_qd : cfg.rcp_qs), qq = sl - el * per;
+          if (el >= cnt_env || sh.reset[el] != 0) continue;
+          T x[4], y[4];
+          if (!dyn) {
+            load4(stat_x + stat0 + 4u * (uint32_t)sl, x);
+            load4(stat_y + stat0 + 4u * (uint32_t)sl, y);
           } else {
-            dynamic_load<T>(p, q_off, true, qx, qy, qm);
+            uint32_t m[4];
+            const uint32_t off = dyn0 + 4u * (uint32_t)sl;
+            dynamic_load<T>(p, off, stepping, x, y, m);
+            if (stepping) {
+              // p.tick is written back only when the hot loop is left: tick of this step = stored + steps since (re)load
+              dynamic_move<T, W, false>(p, sh, e0 + el, qq, p.tick[e0 + el] + (uint32_t)(t - t_load), x, y, m);
+              dynamic_store<T>(p, off, x, y, m);
+            }
           }
+          const int k0 = dyn ? ks + 4 * qq : 4 * qq, kend = dyn ? ks + kd : ks;
+          const T ax = sh.ax[el], ay = sh.ay[el];
+  #pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (k0 + i < kend)
+              near_test<T, W>(sh, words, cfg, el, ax, ay, margin, x[i], y[i], k0 + i, stepping, want_obs, nb);
         }
+        bar_sync(kBarNear);
+
+        // block-cooperative raster of the near list
+        if (want_obs) raster_list<T, W>(sh, words, cfg, lt, nb);
+        if (bar_or(kBarDone, false)) {   // leave the hot loop: the reset goes through global memory
+          pending_reset = true;
+          break;
+        }
+        if (want_obs && !(p.debug & 8))
+          store_obs<W, kFast>(p, reinterpret_cast<char*>(p.obs) + (kFast && p.obs_all_steps ? (size_t)t * obs_step_bytes : 0),
+                              words, sh.lut, e0, cnt_env);
       }
-      if (want_obs && !(p.debug & 8)) {
-        const Params& pp = p;
-        store_obs<W, kFast>(pp, reinterpret_cast<char*>(p.obs) + (kFast && p.obs_all_steps ? (size_t)t * obs_step_bytes : 0),
-                            words, sh.lut, e0, cnt_env);
+
+      // ---- write the moved quads back (a pending reset then overwrites those of the environments that finished)
+      if (q_have && q_dyn && stepping) dynamic_store<T>(p, q_off, qx, qy, qm);
+      if (!pending_reset) break;
+      {
+        const bool want_obs = kFast ? (p.obs_all_steps != 0 || t == n_steps - 1) : p.obs != nullptr;
+        uint32_t* words = sh.words[t & 1];
+        reset_stage<T, W>(p, sh, words, e0, cnt_env, want_obs);
+        if (want_obs && !(p.debug & 8))
+          store_obs<W, kFast>(p, reinterpret_cast<char*>(p.obs) + (kFast && p.obs_all_steps ? (size_t)t * obs_step_bytes : 0),
+                              words, sh.lut, e0, cnt_env);
+        if (!kFast && lt < n_slot) q_have = q_el < cnt_env;   // Reset mode: the environment has state now
+        if (++t >= n_steps) break;
       }
     }
-
-    // ---- write the moved quads back
-    if (q_have && q_dyn && stepping) dynamic_store<T>(p, q_off, qx, qy, qm);
   }
 }
 

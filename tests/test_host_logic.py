@@ -1,0 +1,82 @@
+"""CPU tests of the host-side mirror of the reference interface (config schema, sharding arithmetic, bench byte model)."""
+import os
+import sys
+from argparse import Namespace
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _args(**over):
+    # read_arguments() defaults of examples/ball_cnn_ac3.py:37-59
+    d = dict(static_obstacles=13, dynamic_obstacles=5, obstacle_speed=[1, 1, 1, 1, 1],
+             obs_goal_position=['12,122', '123,93', '87,150', '430,440', '230,11'], time_step_for_change=50,
+             rd_th_obs=60, rd_th_agent=80, static_thresholds=[0, 0], dynamic_thresholds=[10, 10],
+             static_penalty=[1, 1], dynamic_penalty=[4000, 8000])
+    d.update(over)
+    return Namespace(**d)
+
+
+def test_env_config_from_reference_namespace():
+    from gym_ballenv_b200 import EnvConfig
+    from gym_ballenv_b200 import _lib as L
+    cfg = EnvConfig.from_args(_args())
+    assert cfg.goals() == [(12, 122), (123, 93), (87, 150), (430, 440), (230, 11)]      # ballenv_env.py:99-103
+    c = cfg.to_c(window=10)
+    assert (c.static_obstacles, c.dynamic_obstacles, c.n_goals, c.window) == (13, 5, 5, 10)
+    assert c.static_penalty == 1.0 and c.dynamic_penalty == 8000.0                      # only index 1 is used (:138,158)
+    assert c.ruleset == L.RULESET_GYM and c.max_episode_steps == 1000
+
+
+@pytest.mark.parametrize("over,msg", [
+    (dict(obstacle_speed=[1, 1]), "obstacle_speed"),
+    (dict(obs_goal_position=['1,2']), "obstacle_goal_position"),
+    (dict(static_penalty=[1]), "static_penalty"),
+    (dict(dynamic_thresholds=[1, 2, 3]), "dynamic_thresholds"),
+])
+def test_assert_arguments_mirror(over, msg):
+    """Same list-length checks as assert_arguments() (examples/ball_cnn_ac3.py:61-68), as ValueError."""
+    from gym_ballenv_b200 import EnvConfig
+    with pytest.raises(ValueError, match=msg):
+        EnvConfig.from_args(_args(**over))
+
+
+def test_cli_string_speeds_are_accepted():
+    """--obstacle_speed has no type= in the reference (examples/ball_cnn_ac3.py:42): CLI values arrive as strings."""
+    from gym_ballenv_b200 import EnvConfig
+    c = EnvConfig.from_args(_args(obstacle_speed=['2', '1', '1', '3', '1'])).to_c(window=5)
+    assert [c.obstacle_speed[i] for i in range(5)] == [2.0, 1.0, 1.0, 3.0, 1.0]
+
+
+def test_dense_moving_is_config_3():
+    from gym_ballenv_b200 import EnvConfig
+    cfg = EnvConfig.dense_moving()
+    assert (cfg.static_obstacles, cfg.dynamic_obstacles, len(cfg.goals())) == (8, 24, 24)
+    assert cfg.goals()[0] == (50, 100) and cfg.goals()[-1] == (450, 400)
+
+
+def test_shard_bounds_cover_and_order():
+    from gym_ballenv_b200.distributed import shard_bounds
+    for total in (0, 1, 7, 65536, 1 << 20, 1000003):
+        for world in (1, 2, 3, 4, 8):
+            pos = 0
+            for r in range(world):
+                off, cnt = shard_bounds(total, r, world)
+                assert off == pos and cnt in (total // world, total // world + 1)
+                pos += cnt
+            assert pos == total
+    assert shard_bounds(1 << 20, 7, 8) == (7 * 131072, 131072)       # BASELINE.json config 4
+    with pytest.raises(ValueError):
+        shard_bounds(10, 2, 2)
+
+
+def test_bench_byte_model_matches_survey():
+    sys.path.insert(0, ROOT)
+    import bench
+    assert bench.alg_bytes_per_env_step(bench.workload_spec("w5")) == 405       # 204 + 201
+    assert bench.alg_bytes_per_env_step(bench.workload_spec("c3")) == 1121      # 392 + 729
+    io = 8 + 4 * 104 + 4 + 1
+    assert bench.moved_bytes_per_env_step(bench.workload_spec("c3"), 200) == pytest.approx(io + (1121 - io) / 200)
+    a = bench.config_dict(bench.workload_spec("c3"), 65536, 8, 200)
+    assert a["total_envs"] == 8 * 65536 and "workload" in a and "l2" in a
