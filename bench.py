@@ -331,7 +331,9 @@ def run_gpu(args, spec):
     moved = moved_bytes_per_env_step(spec, chunk)
     traffic = None
     try:   # per-launch DRAM bytes of the step kernel from the committed ncu capture (profiles/)
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(spec["name"])
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(spec["name"])
+        if tr:   # measured DRAM bytes per env-step (ncu --set full, see profiles/) x env-steps of one launch
+            traffic = tr["dram_bytes_per_env_step"] * n * chunk
     except Exception:
         pass
 
