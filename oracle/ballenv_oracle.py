@@ -15,7 +15,7 @@ behaviour (done once elapsed_steps >= max_episode_steps).
 It is deliberately scalar Python with ``math.sqrt``/``math.pow`` like the
 reference, so that timing it is a fair stand-in for the reference's own CPU
 cost (``cpu_baseline.kind == "port"``).  ``oracle/ballenv_oracle.c`` is the same
-algorithm in C for large parity sweeps.
+algorithm in C (checked against this file by tests/test_oracle_c.py) for parity at full sizes.
 
 Reference citations (relative to /root/reference):
   step            gym_ballenv/envs/ballenv_env.py:232-289

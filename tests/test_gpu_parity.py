@@ -184,7 +184,7 @@ def test_obs_formats_agree(obs_dtype):
 @pytest.mark.parametrize("w,cfgname", [(5, "default"), (10, "dense")])
 def test_oracle_rollout(w, cfgname):
     """Config 2 shape at a size the Python oracle finishes in seconds; the 4096-env x 200-step case runs against
-    the C oracle in test_gpu_parity_c.py."""
+    the C oracle in test_gpu_parity_full.py."""
     from gym_ballenv_b200 import BallVecEnv, EnvConfig
     from oracle import draws as D
     from oracle.ballenv_oracle import OracleVec
