@@ -230,6 +230,57 @@ def rollout(cfg, n_envs, T, seed, mode, max_steps, windows=(5, 10), g0=0, polici
     return out
 
 
+def pygame_action(src, g, t):
+    """Raw (dx, dy) of the pygame-ruleset fixtures: multiples of 0.75 in [-3, 3] (non-integral on purpose)."""
+    w = src.action_word(g, t)
+    return (D.mulhi(w, 9) - 4) * 0.75, (D.mulhi(D.mullo(w, 9), 9) - 4) * 0.75
+
+
+def rollout_pygame(n_static, n_envs, T, seed, g0=0):
+    """createBoard (ballenv_pygame.py:314-706) stepped with raw float actions; a finished episode is followed by
+    reset(), like the vector wrapper's auto-reset.  Recorded state is the one after that reset."""
+    src = D.PhiloxDraws(seed)
+    act_src = D.PhiloxDraws(seed ^ 0x5EED)
+    refs = [R.ReferencePygameEnv(n_static, R.PygameRouter(src, g0 + i)) for i in range(n_envs)]
+    K = n_static
+    rec = dict(actions=np.zeros((T, n_envs, 2)), agent=np.zeros((T, n_envs, 2)), goal=np.zeros((T, n_envs, 2)),
+               dist=np.zeros((T, n_envs)), total_distance=np.zeros((T, n_envs)), acc=np.zeros((T, n_envs)),
+               reward=np.zeros((T, n_envs)), done=np.zeros((T, n_envs), np.uint8),
+               obst=np.zeros((T, n_envs, K, 2)))
+    init = dict(agent=np.zeros((n_envs, 2)), goal=np.zeros((n_envs, 2)), dist=np.zeros(n_envs),
+                total_distance=np.zeros(n_envs), obst=np.zeros((n_envs, K, 2)))
+
+    def snap(dst, idx, ref):
+        st = ref.env.state
+        dst["agent"][idx] = st[0]
+        dst["goal"][idx] = st[1]
+        dst["dist"][idx] = st[2]
+        dst["total_distance"][idx] = ref.env.total_distance
+        for k in range(K):
+            dst["obst"][idx + (k,)] = st[3 + k][:2]
+
+    episodes = 0
+    for i, ref in enumerate(refs):
+        ref.reset()
+        snap(init, (i,), ref)
+    for t in range(T):
+        for i, ref in enumerate(refs):
+            a = pygame_action(act_src, g0 + i, t)
+            rec["actions"][t, i] = a
+            _, reward, done, _ = ref.step(a)
+            rec["reward"][t, i], rec["done"][t, i] = reward, done
+            rec["acc"][t, i] = ref.env.total_reward_accumulated
+            if done:
+                episodes += 1
+                ref.reset()
+            snap(rec, (t, i), ref)
+    out = {"rec_" + k: v for k, v in rec.items()}
+    out.update({"init_" + k: v for k, v in init.items()})
+    out["meta"] = json.dumps(dict(ruleset="pygame", n_static=n_static, n_envs=n_envs, T=T, seed=seed, g0=g0,
+                                  episodes=episodes, agent_radius=10, static_obstacle_radius=10))
+    return out
+
+
 def compress_rollout(out):
     """Shrink dtypes where the values are integral (checked)."""
     for k in list(out):
@@ -404,6 +455,7 @@ def main(argv):
         "rollout_philox_busy": lambda: compress_rollout(rollout(CFG_BUSY, 16, 200, 11, "philox", 40, g0=5)),
         "rollout_philox_dense": lambda: compress_rollout(rollout(CFG_DENSE, 8, 120, 3, "philox", 1000, windows=(10,))),
         "rollout_mt_default": lambda: compress_rollout(rollout(CFG_DEFAULT, 8, 150, 0, "mt", 60)),
+        "rollout_pygame": lambda: rollout_pygame(9, 12, 200, 21, g0=40),
     }
     only = set(argv[1:])
     for name, fn in jobs.items():

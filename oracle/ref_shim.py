@@ -329,3 +329,112 @@ class ReferenceEnv(object):
     def observe(self, state, window):
         """prep_state4 of the reference -> numpy float32 [4 + W*W]."""
         return self.prep_state4(state, window).numpy().reshape(-1)
+
+
+# --------------------------------------------------------------------------- pygame ruleset (ballenv_pygame.py)
+class PygameRouter(object):
+    """Answers ``createBoard``'s draws (ballenv_pygame.py:454-457,468-482,489-498 and Obstacle.__init__ :24-33)
+    from an addressed draw source.  reset: ranf x2 (goal), ranf x2 (agent), ranf x2 per agent redraw, then per
+    static obstacle a randint (x, y) pair per attempt; ``step`` draws nothing."""
+
+    def __init__(self, source, g):
+        self.src = source
+        self.g = g
+        self.env = None
+        self.context = "ctor"
+        self.episode = -1
+        self.trace = []
+
+    def begin_reset(self):
+        self.context = "reset"
+        self.episode += 1
+        self._nf = 0
+        self._pair = None
+        self._last_len = -1
+        self._attempt = 0
+
+    def ranf(self):
+        assert self.context == "reset"
+        k = self._nf
+        self._nf += 1
+        if k < 4:      # goal (block 0: words 0-1, 2-3), first agent draw (block 1)
+            w = self.src.reset_words(self.g, self.episode, D.RK_HEAD, item=k // 2, count=4)
+        else:          # agent redraws, two ranf per attempt
+            w = self.src.reset_words(self.g, self.episode, D.RK_AGENT_REDRAW, attempt=(k - 4) // 2, count=4)
+        v = D.ranf_from_words(w[2 * (k % 2)], w[2 * (k % 2) + 1])
+        self.trace.append((self.context, 0.0, 1.0, v))
+        return v
+
+    def randint(self, low, high):
+        n = high - low
+        assert self.context == "reset"
+        if self._pair is None:
+            cur = len(self.env.obstacle_list)
+            if cur != self._last_len:
+                self._last_len, self._attempt = cur, 0
+            else:
+                self._attempt += 1
+            self._pair = self.src.reset_words(self.g, self.episode, D.RK_STATIC, cur, self._attempt)
+            w = self._pair[0]
+        else:
+            w = self._pair[1]
+            self._pair = None
+        v = low + D.mulhi(w, n)
+        self.trace.append((self.context, low, high, v))
+        return v
+
+
+def _install_pygame_standins():
+    """createBoard(display=False) only touches pygame.init / pygame.time.Clock; its step() calls
+    featureExtractor.featureExtractor, which needs CUDA and does not influence state, reward or done."""
+    import types
+    if "pygame" not in sys.modules:
+        pg = types.ModuleType("pygame")
+        pg.init = lambda *a, **k: (0, 0)
+        pg.quit = lambda *a, **k: None
+        pg.time = types.SimpleNamespace(Clock=lambda: types.SimpleNamespace(tick=lambda *a, **k: None))
+        sys.modules["pygame"] = pg
+    if "featureExtractor" not in sys.modules:
+        fe = types.ModuleType("featureExtractor")
+        fe.featureExtractor = lambda *a, **k: None
+        sys.modules["featureExtractor"] = fe
+
+
+def load_pygame_module():
+    if "pg" not in _loaded:
+        import contextlib
+        import importlib.util
+        import io
+        _install_pygame_standins()
+        spec = importlib.util.spec_from_file_location("ref_ballenv_pygame", os.path.join(REFERENCE_ROOT, "ballenv_pygame.py"))
+        mod = importlib.util.module_from_spec(spec)
+        with contextlib.redirect_stdout(io.StringIO()):
+            spec.loader.exec_module(mod)
+        _loaded["pg"] = mod
+    return _loaded["pg"]
+
+
+class ReferencePygameEnv(object):
+    """One reference ``createBoard`` (ballenv_pygame.py:314-706), unedited, driven through a draw router."""
+
+    def __init__(self, static_obstacles, router, agent_radius=10, static_obstacle_radius=10):
+        import contextlib
+        import io
+        self.pg = load_pygame_module()
+        self.router = router
+        self.pg.np = _NumpyProxy(router)
+        with contextlib.redirect_stdout(io.StringIO()):      # the ctor prints pygame.init() and "here"
+            self.env = self.pg.createBoard(display=False, static_obstacles=static_obstacles, agent_radius=agent_radius,
+                                           static_obstacle_radius=static_obstacle_radius)
+        router.env = self.env
+
+    def reset(self):
+        self.pg.np = _NumpyProxy(self.router)
+        self.env.static_obstacle_list = []
+        self.router.begin_reset()
+        return self.env.reset()
+
+    def step(self, action):
+        self.pg.np = _NumpyProxy(self.router)
+        self.router.context = "step"
+        return self.env.step(action)

@@ -353,3 +353,51 @@ def test_rollout_kernel_matches_per_step_launches(w, cfgname, n, keep, monkeypat
     assert one.error_flags() == 0 and per.error_flags() == 0
     one.close()
     per.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("parity", [True, False])
+def test_pygame_ruleset_against_the_reference_rollout(parity):
+    """createBoard (ballenv_pygame.py:650-706, 460-513) recorded through the shim, raw float actions, auto-reset.
+    fp64 parity mode: positions and done bit-exact; distances / rewards to 1e-12 relative - for non-integral
+    coordinates glibc's pow(x, 2) (what math.pow calls) is not guaranteed correctly rounded, the kernel's x * x is, so
+    a distance may differ in the last bit ("fp64 parity mode").  fp32 production mode: positions are stored
+    in fp32 (the coordinates are non-integral here), so rewards agree to 1e-4 relative / 1e-6 absolute and the
+    comparison stops at the first episode end (a discrete event may flip on a last-bit difference)."""
+    from gym_ballenv_b200 import BallVecEnv, EnvConfig
+    z, meta = load_golden("rollout_pygame")
+    n, T, g0 = meta["n_envs"], meta["T"], meta["g0"]
+    env = BallVecEnv(n, window=5, config=EnvConfig.pygame_default(static_obstacles=meta["n_static"]), ruleset="pygame",
+                     seed=meta["seed"], parity=parity, global_env_offset=g0)
+    env.reset()
+    st = env.get_state()
+    real = np.float64 if parity else np.float32
+    assert np.array_equal(st["agent_x"].cpu().numpy(), z["init_agent"][:, 0].astype(real))
+    assert np.array_equal(st["goal_y"].cpu().numpy(), z["init_goal"][:, 1].astype(real))
+    assert np.array_equal(st["static_x"].cpu().numpy().T, z["init_obst"][:, :, 0].astype(real))
+    if parity:
+        np.testing.assert_allclose(st["dist"].cpu().numpy(), z["init_dist"], rtol=1e-14)
+        np.testing.assert_allclose(st["total_distance"].cpu().numpy(), z["init_total_distance"], rtol=1e-14)
+    alive = np.ones(n, bool)
+    for t in range(T):
+        a = torch.from_numpy(z["rec_actions"][t].astype(real)).cuda()
+        obs, rew, done, info = env.step(a)
+        rew, done = rew.cpu().numpy(), done.cpu().numpy()
+        st = env.get_state()
+        if parity:
+            np.testing.assert_allclose(rew, z["rec_reward"][t], rtol=1e-12, atol=1e-15)
+            assert np.array_equal(done, z["rec_done"][t].astype(bool)), t
+            assert np.array_equal(st["agent_x"].cpu().numpy(), z["rec_agent"][t, :, 0]), t
+            assert np.array_equal(st["agent_y"].cpu().numpy(), z["rec_agent"][t, :, 1]), t
+            np.testing.assert_allclose(st["dist"].cpu().numpy(), z["rec_dist"][t], rtol=1e-14)
+            assert np.array_equal(st["static_y"].cpu().numpy().T, z["rec_obst"][t, :, :, 1]), t
+            nd = ~done
+            np.testing.assert_allclose(st["acc_reward"].cpu().numpy()[nd], z["rec_acc"][t][nd], rtol=1e-11, atol=1e-14)
+        else:
+            np.testing.assert_allclose(rew[alive], z["rec_reward"][t][alive], rtol=1e-4, atol=1e-6)
+            assert np.array_equal(done[alive], z["rec_done"][t].astype(bool)[alive]), t
+            alive &= ~z["rec_done"][t].astype(bool)
+    if parity:
+        assert env.stats()["episodes"] == meta["episodes"]
+    assert env.error_flags() == 0
+    env.close()

@@ -110,3 +110,31 @@ def _check_rollout(name):
 def test_rollout(name):
     meta = _check_rollout(name)
     assert meta["stats"]["episodes"] > 0
+
+
+def test_rollout_pygame_ruleset():
+    """createBoard (ballenv_pygame.py) stepped through the shim with raw float actions: the oracle's pygame
+    ruleset reproduces every position, distance, reward, done and accumulated reward exactly (same fp64 ops)."""
+    from oracle.ballenv_oracle import RULESET_PYGAME, OracleConfig
+    z, meta = load_golden("rollout_pygame")
+    n, T, g0 = meta["n_envs"], meta["T"], meta["g0"]
+    cfg = OracleConfig(ruleset=RULESET_PYGAME, window=5, n_static=meta["n_static"], n_dynamic=0, speeds=(), goals=(),
+                       max_episode_steps=0, auto_reset=True, agent_radius=meta["agent_radius"],
+                       static_obstacle_radius=meta["static_obstacle_radius"])
+    vec = OracleVec(cfg, D.PhiloxDraws(meta["seed"]), n, g0)
+    vec.reset()
+    for i, e in enumerate(vec.envs):
+        assert tuple(e.agent) == tuple(z["init_agent"][i]) and tuple(e.goal) == tuple(z["init_goal"][i])
+        assert e.dist == z["init_dist"][i] and e.total_distance == z["init_total_distance"][i]
+        assert np.array_equal(np.array(e.obst, dtype=np.float64), z["init_obst"][i])
+    for t in range(T):
+        rew, done, _ = vec.step([tuple(a) for a in z["rec_actions"][t]])
+        assert [float(r) for r in rew] == list(z["rec_reward"][t]), t
+        assert [int(d) for d in done] == list(z["rec_done"][t]), t
+        for i, e in enumerate(vec.envs):
+            assert tuple(e.agent) == tuple(z["rec_agent"][t, i]) and tuple(e.goal) == tuple(z["rec_goal"][t, i]), (t, i)
+            assert e.dist == z["rec_dist"][t, i] and e.total_distance == z["rec_total_distance"][t, i]
+            assert np.array_equal(np.array(e.obst, dtype=np.float64), z["rec_obst"][t, i])
+            if not done[i]:
+                assert e.acc == z["rec_acc"][t, i]
+    assert vec.stats["episodes"] == meta["episodes"] > 0
