@@ -1,0 +1,69 @@
+#!/usr/bin/env python
+"""The reference's actor-critic example (examples/ball_cnn_ac3.py) on the B200 vector environment.
+
+Same command-line fields as the reference's read_arguments() (:37-59); instead of one environment stepped from
+Python, --envs environments are stepped by the fused CUDA kernel with the policy in the loop on the GPU.
+
+    python examples/ball_cnn_ac3_b200.py --envs 16384 --window 5 --iterations 50
+"""
+import argparse
+import os
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from gym_ballenv_b200 import BallVecEnv, EnvConfig          # noqa: E402
+from gym_ballenv_b200.a2c import Policy, train               # noqa: E402
+
+
+def read_arguments():
+    p = argparse.ArgumentParser(description='A2C on the B200 ball environment')
+    p.add_argument('--static_obstacles', type=int, default=13)
+    p.add_argument('--dynamic_obstacles', type=int, default=5)
+    p.add_argument('--obstacle_speed', nargs='*', default=[1, 1, 1, 1, 1])
+    p.add_argument('--obs_goal_position', nargs='*', default=['12,122', '123,93', '87,150', '430,440', '230,11'])
+    p.add_argument('--time_step_for_change', type=int, default=50)
+    p.add_argument('--rd_th_obs', type=int, default=60)
+    p.add_argument('--rd_th_agent', type=int, default=80)
+    p.add_argument('--static_thresholds', nargs=2, type=int, default=[0, 0])
+    p.add_argument('--dynamic_thresholds', nargs=2, type=int, default=[10, 10])
+    p.add_argument('--static_penalty', nargs=2, type=int, default=[1, 1])
+    p.add_argument('--dynamic_penalty', nargs=2, type=int, default=[4000, 8000])
+    p.add_argument('--gamma', type=float, default=0.99)
+    p.add_argument('--seed', type=int, default=543)
+    p.add_argument('--resume', type=str, default=None, help='state_dict saved by the reference or by this script')
+    p.add_argument('--window', type=int, default=5)
+    p.add_argument('--envs', type=int, default=16384)
+    p.add_argument('--steps', type=int, default=32, help='steps per update')
+    p.add_argument('--iterations', type=int, default=50)
+    return p.parse_args()
+
+
+def main():
+    args = read_arguments()
+    torch.manual_seed(args.seed)
+    dev = torch.device("cuda")
+    env = BallVecEnv(args.envs, window=args.window, config=EnvConfig.from_args(args), seed=args.seed, device=dev)
+    policy = Policy(args.window).to(dev)
+    if args.resume:
+        policy.load_state_dict(torch.load(args.resume, map_location=dev))
+    t0 = time.time()
+
+    def log(it, loss, batch):
+        if it % 10 == 0:
+            st = env.stats()
+            print("iter %4d  loss %12.3f  mean reward %+.5f  episodes %d  goals %d  hits %d  (%.1f s)" %
+                  (it, float(loss.detach()), float(batch["reward"].mean()), st["episodes"], st["goals"],
+                   st["hits_static"] + st["hits_dynamic"], time.time() - t0))
+
+    train(env, policy, args.iterations, n_steps=args.steps, gamma=args.gamma, log=log)
+    torch.cuda.synchronize()
+    n = args.envs * args.steps * args.iterations
+    print("%d env-steps in %.2f s = %.2f M env-steps/s (policy forward/backward included)" %
+          (n, time.time() - t0, n / (time.time() - t0) / 1e6))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,110 @@
+"""Batched actor-critic rollout driver for the vector environment (BASELINE.json config 5).
+
+The reference's training loop (examples/ball_cnn_ac3.py:528-646) drives ONE environment: per step it builds the
+observation on the CPU (prep_state4, :560), copies it to the device (:412), runs ``Policy(window)`` (:109-146),
+samples a 9-way ``Categorical`` and pulls the action back with ``.item()`` (:210-220, a device->host sync per
+step), then calls ``env.step(move_list[action])`` (:588).  Here the same loop runs for N environments with nothing
+leaving the GPU: the fused step kernel returns the observation tensor the policy consumes in place, the sampled
+int64 indices are the kernel's action input, rewards / dones are accumulated on the device and finished
+environments are reset inside the step launch.
+
+``Policy`` keeps the reference's architecture and parameter names (``fc1``, ``action_head``, ``value_head``), so the
+state_dicts the reference saves (:637-639; e.g. ``fc1`` 128x29 for WINDOW=5, 208x104 for WINDOW=10) load unchanged.
+``a2c_loss`` is the batched form of ``finish_episode`` (:222-246).  This module is plumbing around the hot path
+(plain PyTorch); the hot path itself is the CUDA kernel behind ``BallVecEnv.step``.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .vec_env import BallVecEnv
+
+EPS = float(torch.finfo(torch.float32).eps)      # np.finfo(np.float32).eps.item(), examples/ball_cnn_ac3.py:76
+
+
+class Policy(nn.Module):
+    """examples/ball_cnn_ac3.py:109-146: (4 + W*W) -> hidden (128 for W=5, 208 for W=10) -> {9 action logits, 1 value}."""
+
+    def __init__(self, window: int, hidden: Optional[int] = None):
+        super().__init__()
+        n_in = 4 + window * window
+        if hidden is None:
+            hidden = {5: 128, 10: 208}.get(window, 2 * n_in)      # 2 * inputs is the reference's commented default (:115)
+        self.hidden_layer = hidden
+        self.fc1 = nn.Linear(n_in, hidden)
+        self.action_head = nn.Linear(hidden, 9)
+        self.value_head = nn.Linear(hidden, 1)
+
+    def forward(self, x):
+        x = F.relu(self.fc1(x))
+        return F.softmax(self.action_head(x), dim=-1), self.value_head(x)
+
+
+def rollout(env: BallVecEnv, policy: Policy, n_steps: int, obs: Optional[torch.Tensor] = None, greedy: bool = False,
+            generator: Optional[torch.Generator] = None) -> Dict[str, torch.Tensor]:
+    """n_steps of policy-in-the-loop stepping for all environments; no host synchronisation inside the loop.
+
+    -> dict(obs [N, row] (the observation after the last step), log_prob [T, N], value [T, N], reward [T, N],
+            done [T, N] bool, action [T, N] int64)."""
+    if obs is None:
+        obs = env.observe()
+    log_probs, values, rewards, dones, actions = [], [], [], [], []
+    for _ in range(n_steps):
+        probs, value = policy(obs.float())
+        if greedy:
+            action = probs.argmax(dim=-1)
+        else:
+            action = torch.multinomial(probs, 1, generator=generator).squeeze(-1)      # Categorical(probs).sample()
+        log_probs.append(torch.log(probs.gather(-1, action.unsqueeze(-1)).squeeze(-1)))
+        values.append(value.squeeze(-1))
+        obs, reward, done, _ = env.step(action)      # views of env-owned buffers: copy what is kept
+        rewards.append(reward.clone())
+        dones.append(done.clone())
+        actions.append(action)
+    return dict(obs=obs, log_prob=torch.stack(log_probs), value=torch.stack(values), reward=torch.stack(rewards),
+                done=torch.stack(dones), action=torch.stack(actions))
+
+
+def discounted_returns(reward: torch.Tensor, done: torch.Tensor, gamma: float, bootstrap: Optional[torch.Tensor] = None):
+    """R_t = r_t + gamma * R_{t+1}, restarted where an episode ended (examples/ball_cnn_ac3.py:228-230, per env)."""
+    T = reward.shape[0]
+    out = torch.empty_like(reward)
+    R = torch.zeros_like(reward[0]) if bootstrap is None else bootstrap
+    for t in range(T - 1, -1, -1):
+        R = reward[t] + gamma * R * (~done[t]).to(reward.dtype)
+        out[t] = R
+    return out
+
+
+def a2c_loss(batch: Dict[str, torch.Tensor], gamma: float = 0.99, bootstrap: Optional[torch.Tensor] = None):
+    """Batched finish_episode (examples/ball_cnn_ac3.py:222-246): returns normalised over the batch,
+    policy loss -log_prob * (R - V.detach()), value loss smooth_l1(V, R), summed."""
+    returns = discounted_returns(batch["reward"].float(), batch["done"], gamma, bootstrap)
+    returns = (returns - returns.mean()) / (returns.std() + EPS)
+    advantage = returns - batch["value"].detach()
+    policy_loss = (-batch["log_prob"] * advantage).sum()
+    value_loss = F.smooth_l1_loss(batch["value"], returns, reduction="sum")
+    return policy_loss + value_loss
+
+
+def train(env: BallVecEnv, policy: Policy, iterations: int, n_steps: int = 32, gamma: float = 0.99, lr: float = 1e-3,
+          generator: Optional[torch.Generator] = None, log=None):
+    """Adam(lr=1e-3) as examples/ball_cnn_ac3.py:505; one update per n_steps-step rollout of all environments."""
+    opt = torch.optim.Adam(policy.parameters(), lr=lr)
+    obs = env.reset()
+    for it in range(iterations):
+        batch = rollout(env, policy, n_steps, obs=obs, generator=generator)
+        obs = batch["obs"]
+        with torch.no_grad():
+            _, v_last = policy(obs.float())
+        loss = a2c_loss(batch, gamma, bootstrap=v_last.squeeze(-1))
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        if log is not None:
+            log(it, loss, batch)
+    return policy

@@ -526,30 +526,33 @@ __device__ __forceinline__ uint32_t stream_bits(const uint32_t* words, int bit, 
   return __funnelshift_r(lo, hi, sh);
 }
 
+// blk points at the block's span of the step's output (environment e0, element 0).
 template <int W, bool kFast>
-__device__ __forceinline__ void store_obs(const Params& p, void* obs, const uint32_t* words, const float4* lut,
-                                          long long e0, int cnt) {
+__device__ __forceinline__ void store_obs(const Params& p, void* blk, const uint32_t* words, const float4* lut, int cnt) {
   const int w = Win<W>::w(p.cfg.window);
   const int nb = 4 + w * w;
   const int tid = threadIdx.x;
-  const int total = cnt * nb, nvec = total >> 2;
+  const int total = cnt * nb;
   if (kFast || p.cfg.obs_format == BALLENV_OBS_F32) {
-    float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(obs) + e0 * nb);
+    // 16-byte alignment holds unless a [T][n][row] rollout buffer has n * row not a multiple of 4 elements
+    const int nvec = (reinterpret_cast<uintptr_t>(blk) & 15) == 0 ? total >> 2 : 0;
+    float4* dst = reinterpret_cast<float4*>(blk);
     for (int v = tid; v < nvec; v += kBlock)   // streaming store: the rollout buffer is not re-read by this kernel
       __stcs(dst + v, lut[(words[v >> 3] >> ((v & 7) << 2)) & 15u]);
-    for (int f = (nvec << 2) + tid; f < total; f += kBlock)   // only when the last block ends on an odd boundary
-      reinterpret_cast<float*>(obs)[e0 * nb + f] = (words[f >> 5] >> (f & 31)) & 1u ? 1.0f : 0.0f;
+    for (int f = (nvec << 2) + tid; f < total; f += kBlock)   // odd tail of the last block / unaligned span
+      reinterpret_cast<float*>(blk)[f] = (words[f >> 5] >> (f & 31)) & 1u ? 1.0f : 0.0f;
   } else if (p.cfg.obs_format == BALLENV_OBS_U8) {
-    uint32_t* dst = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(obs) + e0 * nb);
+    const int nvec = (reinterpret_cast<uintptr_t>(blk) & 3) == 0 ? total >> 2 : 0;
+    uint32_t* dst = reinterpret_cast<uint32_t*>(blk);
     for (int v = tid; v < nvec; v += kBlock) {
       const uint32_t nib = (words[v >> 3] >> ((v & 7) << 2)) & 15u;
       dst[v] = (nib & 1u) | (nib & 2u) << 7 | (nib & 4u) << 14 | (nib & 8u) << 21;
     }
     for (int f = (nvec << 2) + tid; f < total; f += kBlock)
-      reinterpret_cast<uint8_t*>(obs)[e0 * nb + f] = (uint8_t)((words[f >> 5] >> (f & 31)) & 1u);
+      reinterpret_cast<uint8_t*>(blk)[f] = (uint8_t)((words[f >> 5] >> (f & 31)) & 1u);
   } else {  // BALLENV_OBS_BITS: [n][ceil(nb / 32)] words, bit b of row e = element b of environment e
     const int nw = (nb + 31) >> 5;
-    uint32_t* base = reinterpret_cast<uint32_t*>(obs) + e0 * nw;
+    uint32_t* base = reinterpret_cast<uint32_t*>(blk);
     for (int i = tid; i < cnt * nw; i += kBlock) {
       const int en = i / nw, k = i - en * nw;
       uint32_t v = stream_bits(words, en * nb + 32 * k, nb);
@@ -737,6 +740,12 @@ __device__ __noinline__ void reset_stage(const Params& p, BlockShared<T, W>& sh,
   __syncthreads();
 }
 
+__device__ __forceinline__ long long load_action_index(const Params& p, long long i) {
+  if (p.action_kind == BALLENV_ACT_INDEX_I64) return reinterpret_cast<const long long*>(p.actions)[i];
+  if (p.action_kind == BALLENV_ACT_INDEX_I32) return reinterpret_cast<const int*>(p.actions)[i];
+  return reinterpret_cast<const uint8_t*>(p.actions)[i];
+}
+
 // ---- named barriers (PTX barrier.*, the forms that tolerate intra-warp divergence): the two thread roles below synchronise as producer / consumer ------------------
 //   kBarAgent : the scalar warp ARRIVES (does not wait) once the agent positions are published; obstacle
 //               threads SYNC on it before their bounding-box tests.  Count = all 288 threads.
@@ -796,7 +805,10 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
   const int ks = cfg.ks, kd = cfg.kd;
   const bool stepping = kFast || p.mode == kModeStep;
   const int n_steps = kRollout ? p.n_steps : 1;
-  const size_t obs_step_bytes = (size_t)p.n * (size_t)cfg.obs_row_elems * (cfg.obs_format == BALLENV_OBS_U8 ? 1u : 4u);
+  // the block's span of the observation output: [e0 .. e0 + 32) x row, advanced by one step's rows per iteration
+  const size_t obs_row_bytes = (size_t)cfg.obs_row_elems * (cfg.obs_format == BALLENV_OBS_U8 ? 1u : 4u);
+  const size_t obs_step_bytes = (kRollout && p.obs_all_steps) ? (size_t)p.n * obs_row_bytes : 0;
+  char* obs_blk = reinterpret_cast<char*>(p.obs) + (size_t)e0 * obs_row_bytes;
   if (p.debug & 1) return;
 
   if (tid < 32) {
@@ -820,6 +832,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
       sh.lut[tid] = make_float4(tid & 1 ? 1.0f : 0.0f, tid & 2 ? 1.0f : 0.0f, tid & 4 ? 1.0f : 0.0f, tid & 8 ? 1.0f : 0.0f);
 
     int t = 0;
+    long long a_next = (kFast && mine) ? load_action_index(p, e) : 0;   // action of step 0
     for (;;) {
       // (re)load: at launch, and after a reset went through global memory
       if (mine) {
@@ -839,7 +852,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
       }
       bool pending_reset = false;
       // ------------------------------------------- hot loop: no calls inside -------------------------------------
-      for (; t < n_steps; ++t) {
+      for (; t < n_steps; ++t, obs_blk += obs_step_bytes) {
         const bool want_obs = kFast ? (p.obs_all_steps != 0 || t == n_steps - 1) : p.obs != nullptr;
         uint32_t* words = sh.words[t & 1];
         const long long et = (long long)t * p.n + e;   // index of this environment in the [T][n] arrays
@@ -857,9 +870,12 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
             ady = (T)a.y;
           } else {
             long long ai;
-            if (p.action_kind == BALLENV_ACT_INDEX_I64) ai = reinterpret_cast<const long long*>(p.actions)[et];
-            else if (p.action_kind == BALLENV_ACT_INDEX_I32) ai = reinterpret_cast<const int*>(p.actions)[et];
-            else ai = reinterpret_cast<const uint8_t*>(p.actions)[et];
+            if (kFast) {   // fetched one step ahead: the load latency is off the step's critical path
+              ai = a_next;
+              if (t + 1 < n_steps) a_next = load_action_index(p, et + p.n);
+            } else {
+              ai = load_action_index(p, et);
+            }
             if (ai < 0 || ai > 8) {
               atomicOr(p.errors, (uint32_t)BALLENV_DEVERR_BAD_ACTION);
               ai = 5;  // (0, 0)
@@ -995,8 +1011,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
           break;
         }
         if (want_obs && !(p.debug & 8))
-          store_obs<W, kFast>(p, reinterpret_cast<char*>(p.obs) + (kFast && p.obs_all_steps ? (size_t)t * obs_step_bytes : 0),
-                              words, sh.lut, e0, cnt_env);
+          store_obs<W, kFast>(p, obs_blk, words, sh.lut, cnt_env);
       }
 
       // ---- write the scalar state back (a pending reset then overwrites it for the environments that finished)
@@ -1020,9 +1035,9 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
         uint32_t* words = sh.words[t & 1];
         reset_stage<T, W>(p, sh, words, e0, cnt_env, want_obs);
         if (want_obs && !(p.debug & 8))
-          store_obs<W, kFast>(p, reinterpret_cast<char*>(p.obs) + (kFast && p.obs_all_steps ? (size_t)t * obs_step_bytes : 0),
-                              words, sh.lut, e0, cnt_env);
+          store_obs<W, kFast>(p, obs_blk, words, sh.lut, cnt_env);
         reset_req = false;
+        obs_blk += obs_step_bytes;
         if (++t >= n_steps) break;
       }
     }
@@ -1086,7 +1101,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
       }
       bool pending_reset = false;
       // ------------------------------------------- hot loop: no calls inside -------------------------------------
-      for (; t < n_steps; ++t) {
+      for (; t < n_steps; ++t, obs_blk += obs_step_bytes) {
         const bool want_obs = kFast ? (p.obs_all_steps != 0 || t == n_steps - 1) : p.obs != nullptr;
         uint32_t* words = sh.words[t & 1];
         // obstacle motion does not depend on the agent: draw and move while the scalar warp works
@@ -1144,8 +1159,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
           break;
         }
         if (want_obs && !(p.debug & 8))
-          store_obs<W, kFast>(p, reinterpret_cast<char*>(p.obs) + (kFast && p.obs_all_steps ? (size_t)t * obs_step_bytes : 0),
-                              words, sh.lut, e0, cnt_env);
+          store_obs<W, kFast>(p, obs_blk, words, sh.lut, cnt_env);
       }
 
       // ---- write the moved quads back (a pending reset then overwrites those of the environments that finished)
@@ -1156,9 +1170,9 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
         uint32_t* words = sh.words[t & 1];
         reset_stage<T, W>(p, sh, words, e0, cnt_env, want_obs);
         if (want_obs && !(p.debug & 8))
-          store_obs<W, kFast>(p, reinterpret_cast<char*>(p.obs) + (kFast && p.obs_all_steps ? (size_t)t * obs_step_bytes : 0),
-                              words, sh.lut, e0, cnt_env);
+          store_obs<W, kFast>(p, obs_blk, words, sh.lut, cnt_env);
         if (!kFast && lt < n_slot) q_have = q_el < cnt_env;   // Reset mode: the environment has state now
+        obs_blk += obs_step_bytes;
         if (++t >= n_steps) break;
       }
     }

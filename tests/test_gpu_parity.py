@@ -401,3 +401,27 @@ def test_pygame_ruleset_against_the_reference_rollout(parity):
         assert env.stats()["episodes"] == meta["episodes"]
     assert env.error_flags() == 0
     env.close()
+
+
+@pytest.mark.gpu
+def test_rollout_buffer_with_unaligned_steps():
+    """[T][n][row] rollout rows of step t start at t * n * row elements: with n = 777 and W = 5 (row = 29) that is
+    not a multiple of 4 elements, so the 128-bit store path must fall back to element stores for those steps."""
+    from gym_ballenv_b200 import BallVecEnv
+    n, T = 777, 9
+    a = torch.randint(0, 9, (T, n), generator=torch.Generator().manual_seed(2)).cuda()
+    envs = [BallVecEnv(n, window=5, seed=4, max_episode_steps=5) for _ in range(2)]
+    for e in envs:
+        e.reset()
+    o1, r1, d1 = envs[0].step_many(a, keep_all_obs=True)
+    ref = []
+    envs[1].close()
+    e2 = BallVecEnv(n, window=5, seed=4, max_episode_steps=5)
+    e2.reset()
+    for t in range(T):
+        o, r, d, _ = e2.step(a[t])
+        ref.append((o.clone(), r.clone(), d.clone()))
+    assert torch.equal(o1, torch.stack([x[0] for x in ref]))
+    assert torch.equal(r1, torch.stack([x[1] for x in ref]))
+    assert torch.equal(d1, torch.stack([x[2] for x in ref]))
+    assert envs[0].error_flags() == 0

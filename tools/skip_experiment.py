@@ -7,8 +7,8 @@ from gym_ballenv_b200 import BallVecEnv
 T = 200
 for wl in ("c3",):
     spec = bench.workload_spec(wl)
-    for n in (32, 65536, 262144):
-        for skip in (0, 1, 2, 4, 8, 16, 2 + 4, 2 + 4 + 8 + 16):
+    for n in (65536,):
+        for skip in (0, 2, 4, 8, 16, 2 + 4, 4 + 8, 2 + 4 + 8, 2 + 4 + 8 + 16):
             os.environ["BALLENV_DEBUG_SKIP"] = str(skip)
             env = BallVecEnv(n, window=spec["window"], config=bench.env_config(spec), seed=0, device="cuda:0",
                              max_episode_steps=0)
