@@ -3,6 +3,7 @@
 Public surface
   BallVecEnv              N environments per launch, CUDA tensors in/out (new; vec_env.py)
   BallEnv, make           the registered gym env's API on the same kernels (env.py)
+  createBoard             the stand-alone pygame env's API (ballenv_pygame.py) incl. sensor_readings (env.py)
   EnvConfig               the reference's argparse fields as a dataclass (config.py)
   make_prep_state         prep_state2 / prep_state4 of examples/ball_cnn_ac3.py, GPU-evaluated
   make_sharded_env, shard_bounds, allreduce_stats   one process per GPU, envs partitioned by global id (distributed.py)
@@ -12,11 +13,11 @@ there is no CPU fallback.
 from ._lib import (LIB, BallenvError, FLAG_GOAL, FLAG_HIT, FLAG_HIT_DYNAMIC, FLAG_TRUNCATED, LIB_PATH,
                    STAT_NAMES)
 from .config import EnvConfig
-from .env import BallEnv, TimeLimit, make, make_prep_state
+from .env import BallEnv, TimeLimit, createBoard, make, make_prep_state
 from .vec_env import MOVE_LIST, BallVecEnv
 from .distributed import allreduce_stats, make_sharded_env, shard_bounds
 
-__all__ = ["BallVecEnv", "BallEnv", "TimeLimit", "make", "make_prep_state", "EnvConfig", "MOVE_LIST",
+__all__ = ["BallVecEnv", "BallEnv", "createBoard", "TimeLimit", "make", "make_prep_state", "EnvConfig", "MOVE_LIST",
            "allreduce_stats", "make_sharded_env", "shard_bounds", "BallenvError", "FLAG_GOAL", "FLAG_HIT", "FLAG_TRUNCATED", "FLAG_HIT_DYNAMIC", "STAT_NAMES", "LIB_PATH"]
 
 

@@ -10,7 +10,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libballenv_b200.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_DYNAMIC = 64
 MAX_GOALS = 64
 MAX_STATIC = 1024
@@ -19,7 +19,7 @@ NUM_STATS = 16
 
 RULESET_GYM, RULESET_PYGAME = 0, 1
 F32, F64 = 0, 1
-OBS_F32, OBS_U8, OBS_BITS, OBS_FEAT20 = 0, 1, 2, 3
+OBS_F32, OBS_U8, OBS_BITS = 0, 1, 2
 ACT_INDEX_I64, ACT_INDEX_I32, ACT_INDEX_U8, ACT_XY_F32, ACT_XY_F64 = 0, 1, 2, 3, 4
 FLAG_GOAL, FLAG_HIT, FLAG_TRUNCATED, FLAG_HIT_DYNAMIC = 1, 2, 4, 8
 DEVERR_BAD_ACTION, DEVERR_TAPE_EXHAUSTED, DEVERR_RESET_STUCK = 1, 2, 4
@@ -54,7 +54,7 @@ class BallenvStatePtrs(C.Structure):
 EXPORTS = (
     "ballenv_abi_version", "ballenv_last_error", "ballenv_config_default", "ballenv_state_bytes",
     "ballenv_create", "ballenv_destroy", "ballenv_state_ptrs", "ballenv_reset", "ballenv_step",
-    "ballenv_step_many", "ballenv_observe", "ballenv_step_host", "ballenv_set_draw_tape", "ballenv_stats",
+    "ballenv_step_many", "ballenv_observe", "ballenv_observe_features", "ballenv_step_host", "ballenv_set_draw_tape", "ballenv_stats",
     "ballenv_stats_reset", "ballenv_error_flags", "ballenv_launch_count",
 )
 
@@ -74,6 +74,7 @@ def _bind(lib):
     lib.ballenv_step.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp]
     lib.ballenv_step_many.argtypes = [vp, vp, C.c_int, i32, vp, i32, vp, vp, vp]
     lib.ballenv_observe.argtypes = [vp, vp, vp]
+    lib.ballenv_observe_features.argtypes = [vp, vp, vp]
     lib.ballenv_step_host.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp]
     lib.ballenv_set_draw_tape.argtypes = [vp, vp, i64, vp, i64, i32]
     lib.ballenv_stats.argtypes = [vp, vp, vp]

@@ -9,6 +9,7 @@
 #include <new>
 
 #include "ballenv_kernels.cuh"
+#include "ballenv_features.cuh"
 
 using namespace ballenv;
 
@@ -62,7 +63,6 @@ int obs_row_elems(const BallenvConfig& c) {
     case BALLENV_OBS_F32:
     case BALLENV_OBS_U8: return nb;
     case BALLENV_OBS_BITS: return (nb + 31) / 32;
-    case BALLENV_OBS_FEAT20: return 20;
   }
   return 0;
 }
@@ -498,6 +498,20 @@ int ballenv_observe(BallenvHandle* h, void* obs_out, ballenv_stream_t stream) {
   p.n_steps = 1;
   p.obs = obs_out;
   return launch(h, p, (cudaStream_t)stream);
+}
+
+int ballenv_observe_features(BallenvHandle* h, float* out, ballenv_stream_t stream) {
+  if (h == nullptr || out == nullptr) return fail(BALLENV_EINVAL, "NULL argument");
+  if (((uintptr_t)out & 15) != 0) return fail(BALLENV_EINVAL, "out must be 16-byte aligned");
+  DeviceGuard guard(h->device);
+  const unsigned grid = (unsigned)((h->n + 127) / 128);
+  if (h->cfg.precision == BALLENV_F64)
+    ballenv_features_kernel<double><<<grid, 128, 0, (cudaStream_t)stream>>>(h->base, out, h->cfg.agent_radius, 0.0, 0.0, 0.0, 0.0);
+  else
+    ballenv_features_kernel<float><<<grid, 128, 0, (cudaStream_t)stream>>>(h->base, out, h->cfg.agent_radius, 0.0, 0.0, 0.0, 0.0);
+  h->launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  return BALLENV_OK;
 }
 
 int ballenv_step(BallenvHandle* h, const void* actions, int action_kind, void* obs_out, void* reward_out,

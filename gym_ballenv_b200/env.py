@@ -254,3 +254,81 @@ def make_prep_state(env):
         return prep_state4(state, base._window)[:, 0:4]
 
     return prep_state2, prep_state4
+
+
+class createBoard(object):
+    """The stand-alone pygame environment of the reference (ballenv_pygame.py:314-706) re-hosted on the GPU:
+    100 x 100 float world, static obstacles, raw (dx, dy) actions, hit => -1 (before the goal test), goal (< 15) => +1,
+    otherwise the progress reward.  Same constructor keywords as the reference (:316); rendering, mouse / keyboard
+    input and the dynamic-obstacle branch (undefined names in the reference, :502-506) are not rebuilt.
+    ``sensor_readings`` is the 20-float feature vector of featureExtractor.py:247-265 as a float32 [1, 20] CUDA tensor."""
+
+    def __init__(self, height=100, display=False, width=100, agent_radius=10, static_obstacles=0, dynamic_obstacles=0,
+                 static_obstacle_radius=10, dynamic_obstacle_radius=0, obstacle_speed_list=(), device="cuda", seed=0,
+                 window=5):
+        if display:
+            raise NotImplementedError("rendering stays off the hot path (pygame display is not rebuilt)")
+        if dynamic_obstacles:
+            raise ValueError("createBoard's dynamic obstacles are broken in the reference (ballenv_pygame.py:502-506)")
+        if (height, width) != (100, 100):
+            raise ValueError("the reference clamps to the module constants 100 x 100 (ballenv_pygame.py:8-9, 656-663)")
+        self.height, self.width, self.display = height, width, display
+        self.agent_radius = agent_radius
+        self.no_static_obstacles, self.no_dynamic_obstacles = static_obstacles, 0
+        self.total_obs = static_obstacles
+        self.rad_static_obstacles, self.rad_dynamic_obstacles = static_obstacle_radius, dynamic_obstacle_radius
+        self.goal_threshold = 15
+        self.agent_x_vel = self.agent_y_vel = 0
+        self.actionArray = [np.asarray([0, -1]), np.asarray([1, 0]), np.asarray([0, 1]), np.asarray([-1, 0])]   # :352
+        self.state = self.sensor_readings = self.reward = None
+        self.total_reward_accumulated = self.total_distance = self.old_dist = None
+        self.agent_x = self.agent_y = self.goal_x = self.goal_y = None
+        cfg = EnvConfig.pygame_default(static_obstacles=static_obstacles, agent_radius=agent_radius,
+                                       static_obstacle_radius=static_obstacle_radius)
+        self._vec = BallVecEnv(1, window=window, config=cfg, ruleset="pygame", device=device, seed=seed, parity=True,
+                               auto_reset=False, max_episode_steps=0)
+
+    def calculate_distance(self, tup1, tup2):
+        return math.sqrt(math.pow(tup1[0] - tup2[0], 2) + math.pow(tup1[1] - tup2[1], 2))
+
+    def check_overlap(self, tup1, tup2, thresh=0):
+        return not (self.calculate_distance(tup1, tup2) - thresh > (self.rad_static_obstacles + self.agent_radius))
+
+    def _pull(self):
+        v = self._vec
+        hv = v._views_of(v._arena.cpu())
+        agent = (hv["agent_x"][0].item(), hv["agent_y"][0].item())
+        goal = (hv["goal_x"][0].item(), hv["goal_y"][0].item())
+        self.agent_x, self.agent_y = agent
+        self.goal_x, self.goal_y = goal
+        self.total_distance = hv["total_distance"][0].item()
+        self.total_reward_accumulated = hv["acc_reward"][0].item()
+        state = [agent, goal, hv["dist"][0].item()]
+        # obstacle tuples carry the Obstacle.rad default 20 (ballenv_pygame.py:33-36, 496)
+        state += [(int(x), int(y), 20) for x, y in zip(hv["static_x"][:, 0].tolist(), hv["static_y"][:, 0].tolist())]
+        self.state = state
+        self.sensor_readings = v.sensor_readings()
+        out = np.empty(len(state), dtype=object)
+        for i, s in enumerate(state):
+            out[i] = s
+        return out
+
+    def reset(self):
+        """ballenv_pygame.py:460-513."""
+        self._vec.reset()
+        out = self._pull()
+        self.old_dist = self.state[2]
+        return out
+
+    def step(self, action):
+        """ballenv_pygame.py:650-675 -> (state, reward, done, {})."""
+        if self.state is None:
+            raise RuntimeError("call reset() before step()")
+        self.old_dist = self.calculate_distance(self.state[0], self.state[1])
+        a = torch.tensor([[float(action[0]), float(action[1])]], dtype=torch.float64, device=self._vec.device)
+        _, reward, done, _ = self._vec.step(a)
+        reward, done = float(reward.item()), bool(done.item())
+        return self._pull(), reward, done, {}
+
+    def close(self):
+        self._vec.close()

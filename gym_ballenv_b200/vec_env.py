@@ -154,6 +154,13 @@ class BallVecEnv:
         check(LIB.ballenv_observe(self._h, C.c_void_p(buf["obs"].data_ptr()), self._stream()))
         return buf["obs"]
 
+    def sensor_readings(self) -> torch.Tensor:
+        """The 20-float social-navigation features of the current state (featureExtractor.py:247-265, what
+        createBoard keeps in ``self.sensor_readings``): float32 [N, 20] on the device."""
+        out = torch.empty((self.num_envs, 20), dtype=torch.float32, device=self.device)
+        check(LIB.ballenv_observe_features(self._h, C.c_void_p(out.data_ptr()), self._stream()))
+        return out
+
     def _next_buf(self):
         self._flip ^= 1
         return self._bufs[self._flip]

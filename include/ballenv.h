@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define BALLENV_ABI_VERSION 2
+#define BALLENV_ABI_VERSION 3
 
 #define BALLENV_MAX_DYNAMIC 64
 #define BALLENV_MAX_GOALS 64
@@ -55,7 +55,7 @@ extern "C" {
 #define BALLENV_OBS_F32 0   /* float32 [n][4 + W*W]  - what prep_state4 returns (examples/ball_cnn_ac3.py:412) */
 #define BALLENV_OBS_U8 1    /* uint8   [n][4 + W*W] */
 #define BALLENV_OBS_BITS 2  /* uint32  [n][ceil((4 + W*W) / 32)], bit b of the row = element b */
-#define BALLENV_OBS_FEAT20 3 /* float32 [n][20] - featureExtractor.py:247-265 (pygame ruleset's sensor_readings) */
+/* (the 20-float feature vector of featureExtractor.py is a separate call: ballenv_observe_features) */
 
 /* action_kind of ballenv_step */
 #define BALLENV_ACT_INDEX_I64 0 /* int64 [n]  index into the agent move table of examples/ball_cnn_ac3.py:530 */
@@ -190,6 +190,15 @@ int ballenv_step_many(BallenvHandle *h, const void *actions, int action_kind, in
 
 /* prep_state4 on the current state without stepping (examples/ball_cnn_ac3.py:384-412). */
 int ballenv_observe(BallenvHandle *h, void *obs_out, ballenv_stream_t stream);
+
+/*
+ * Replaces: featureExtractor.featureExtractor(state, obstacle_list, agent_vel, agent_radius)
+ * (featureExtractor.py:247-265), which createBoard calls after reset() and step() to fill self.sensor_readings
+ * (ballenv_pygame.py:512, 674).  out : device float32 [n][20] (goal-distance bin, goal direction one-hot[4],
+ * density[3], orientation x speed histogram[9], social forces[3]) of the CURRENT state.  Agent and obstacle
+ * velocities are 0 as in the reference's only call sites; agent_radius comes from the config.
+ */
+int ballenv_observe_features(BallenvHandle *h, float *out, ballenv_stream_t stream);
 
 /*
  * Same as ballenv_step but with HOST buffers (pinned or pageable): copies actions host->device, steps,

@@ -383,3 +383,49 @@ class OracleVec:
 
     def observe(self):
         return [e.observe() for e in self.envs]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# 20-float social-navigation features (featureExtractor.py:247-265), restated with math.* on Python floats.
+def _angle_between(v1, v2):
+    """featureExtractor.py:43-56: arccos(clip(dot(unit(v1), unit(v2)), -1, 1)); zero vectors stay zero."""
+    n1, n2 = math.hypot(v1[0], v1[1]), math.hypot(v2[0], v2[1])
+    u1 = (v1[0] / n1, v1[1] / n1) if n1 > 0 else v1
+    u2 = (v2[0] / n2, v2[1] / n2) if n2 > 0 else v2
+    d = u1[0] * u2[0] + u1[1] * u2[1]
+    return math.acos(max(-1.0, min(1.0, d)))
+
+
+def features20(agent, goal, obstacles, agent_rad=10, obstacle_rad=20, agent_vel=(0, 0), obstacle_vel=(0, 0)):
+    """-> list of 20 floats: [goal-distance bin] + goal direction one-hot[4] + density[3] + orientation x speed
+    histogram[9] (row-major, rows = orientation bin) + social forces[3]."""
+    f = [0.0] * 20
+    d = math.floor(math.hypot(agent[0] - goal[0], agent[1] - goal[1]) / 5)            # :132-144
+    f[0] = 5.0 if d > 5 else float(d)
+    xi, yi = goal[0] - agent[0], goal[1] - agent[1]                                    # :146-166
+    ang = _angle_between((0, 1), (xi, yi))
+    if ang < math.pi / 4:
+        f[1] = 1.0
+    elif ang > math.pi / 4 and ang < math.pi * 3 / 4:
+        f[2 if xi > 0 else 4] = 1.0
+    else:
+        f[3] = 1.0
+    rv = (obstacle_vel[0] - agent_vel[0], obstacle_vel[1] - agent_vel[1])
+    relvel = math.hypot(rv[0], rv[1])
+    speed_bin = 0 if relvel < 0.015 else (1 if relvel < 0.025 else 2)                  # :66-72
+    for o in obstacles:
+        v1 = (o[0] - agent[0], o[1] - agent[1])
+        dist = math.hypot(v1[0], v1[1]) - agent_rad - obstacle_rad                     # :36-40
+        if dist < 1000:                                                                # :103-108
+            f[7] += 1
+        if dist < 230:
+            f[6] += 1
+        if dist < 101:
+            f[5] += 1
+        psi = _angle_between(v1, rv)                                                   # :74
+        obin = 0 if psi < math.pi / 4 else (1 if (psi > math.pi / 4 and psi < math.pi * 3 / 4) else 2)   # :76-83
+        f[8 + obin * 3 + speed_bin] += 1                                               # :122-124
+        fsoc = 1 * (1 * math.exp(-dist / 10)) * dist * (2 + 0.5 * (1 - 2) * (1 + math.cos(psi)))   # :186-189
+        if fsoc > 1:                                                                   # :191-192
+            f[17 + obin] += fsoc
+    return f

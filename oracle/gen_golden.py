@@ -281,6 +281,32 @@ def rollout_pygame(n_static, n_envs, T, seed, g0=0):
     return out
 
 
+def features_kats():
+    """States -> the 20 floats of the reference's featureExtractor helpers (numpy part, featureExtractor.py:36-257)."""
+    rng = np.random.RandomState(12)
+    agents, goals, obsts, feats, rads = [], [], [], [], []
+    K = 6
+    for i in range(160):
+        world = 100.0 if i % 2 == 0 else 500.0
+        agent = tuple(rng.uniform(0, world, 2)) if i % 4 else tuple(rng.randint(0, int(world), 2).astype(float))
+        goal = tuple(rng.uniform(0, world, 2))
+        if i == 7:
+            goal = agent                       # zero goal vector: arccos(0) -> the "left" sector
+        if i == 9:
+            goal = (agent[0], agent[1] + 30.0)  # straight up
+        if i == 11:
+            goal = (agent[0] - 10.0, agent[1] - 40.0)
+        ob = [(float(x), float(y)) for x, y in rng.randint(0, int(world), (K, 2))]
+        if i % 5 == 0:
+            ob[0] = (agent[0] + 31.0, agent[1])        # surface distance ~1: social force near its threshold
+            ob[1] = (agent[0], agent[1] - 45.0)
+        rad = 10 if i % 3 else 5
+        agents.append(agent); goals.append(goal); obsts.append(ob); rads.append(rad)
+        feats.append(R.reference_features(agent, goal, ob, agent_rad=rad))
+    return dict(agent=np.array(agents), goal=np.array(goals), obst=np.array(obsts), agent_rad=np.array(rads, np.float64),
+                features=np.array(feats), meta=json.dumps(dict(K=K, n=len(agents), obstacle_rad=20)))
+
+
 def compress_rollout(out):
     """Shrink dtypes where the values are integral (checked)."""
     for k in list(out):
@@ -455,6 +481,7 @@ def main(argv):
         "rollout_philox_busy": lambda: compress_rollout(rollout(CFG_BUSY, 16, 200, 11, "philox", 40, g0=5)),
         "rollout_philox_dense": lambda: compress_rollout(rollout(CFG_DENSE, 8, 120, 3, "philox", 1000, windows=(10,))),
         "rollout_mt_default": lambda: compress_rollout(rollout(CFG_DEFAULT, 8, 150, 0, "mt", 60)),
+        "features_kat": lambda: features_kats(),
         "rollout_pygame": lambda: rollout_pygame(9, 12, 200, 21, g0=40),
     }
     only = set(argv[1:])

@@ -438,3 +438,27 @@ class ReferencePygameEnv(object):
         self.pg.np = _NumpyProxy(self.router)
         self.router.context = "step"
         return self.env.step(action)
+
+
+def reference_features(agent, goal, obstacles, agent_rad=10, obstacle_rad=20, agent_vel=(0, 0), obstacle_vel=(0, 0)):
+    """The reference's own numpy helpers (featureExtractor.py:36-193), concatenated exactly as
+    featureExtractor() does (:249-257) - only its final ``.to(cuda)`` (:262-264) is left out."""
+    if "fe" not in _loaded:
+        import importlib.util
+        if "pygame" not in sys.modules or not hasattr(sys.modules["pygame"], "init"):
+            _install_pygame_standins()
+        real = sys.modules.pop("featureExtractor", None)      # the stand-in used by the createBoard driver
+        spec = importlib.util.spec_from_file_location("ref_featureExtractor", os.path.join(REFERENCE_ROOT, "featureExtractor.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        if real is not None:
+            sys.modules["featureExtractor"] = real
+        _loaded["fe"] = mod
+    fe = _loaded["fe"]
+    obs = [types.SimpleNamespace(x=o[0], y=o[1], rad=obstacle_rad, vel_x=obstacle_vel[0], vel_y=obstacle_vel[1])
+           for o in obstacles]
+    state = [tuple(agent), tuple(goal), 0.0, False] + [tuple(o) for o in obstacles]
+    parts = (fe.calcDistanceFromGoal(state, 5), fe.relativeGoalPos(state), fe.densityFeatures(state, obs, agent_rad, 10),
+             fe.speedOrientationFeatures(state, obs, agent_rad, agent_vel).reshape(9),
+             fe.socialForcesFeatures(state, obs, agent_rad, agent_vel))
+    return _np.concatenate(parts).astype(_np.float64)

@@ -425,3 +425,62 @@ def test_rollout_buffer_with_unaligned_steps():
     assert torch.equal(r1, torch.stack([x[1] for x in ref]))
     assert torch.equal(d1, torch.stack([x[2] for x in ref]))
     assert envs[0].error_flags() == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("parity", [True, False])
+def test_features20_kernel_against_the_reference_vectors(parity):
+    """ballenv_observe_features vs the 20 floats the reference's featureExtractor helpers produce for 160 injected
+    states (tests/golden/features_kat.npz).  Counts and one-hots exact; the social-force sums (exp, cos, acos) to
+    1e-12 relative in fp64 parity mode and 2e-5 in fp32 (transcendental functions, fp32 positions)."""
+    from gym_ballenv_b200 import BallVecEnv, EnvConfig
+    z, meta = load_golden("features_kat")
+    n, K = meta["n"], meta["K"]
+    for rad in (5, 10):
+        sel = np.where(z["agent_rad"] == rad)[0]
+        env = BallVecEnv(len(sel), window=5, config=EnvConfig.pygame_default(static_obstacles=K, agent_radius=rad),
+                         ruleset="pygame", parity=parity, auto_reset=False)
+        env.reset()
+        env.set_state(agent_x=z["agent"][sel, 0], agent_y=z["agent"][sel, 1], goal_x=z["goal"][sel, 0],
+                      goal_y=z["goal"][sel, 1], static_x=z["obst"][sel, :, 0].T, static_y=z["obst"][sel, :, 1].T)
+        got = env.sensor_readings().cpu().numpy().astype(np.float64)
+        want = z["features"][sel]
+        if parity:
+            np.testing.assert_allclose(got, want.astype(np.float32), rtol=1e-6, atol=0)     # output rows are fp32
+            assert np.array_equal(got[:, :17], want[:, :17])
+        else:
+            # fp32 positions: a state exactly on a bin boundary may fall on the other side; none of the fixtures is
+            assert np.array_equal(got[:, :17], want[:, :17])
+            np.testing.assert_allclose(got[:, 17:], want[:, 17:], rtol=2e-5, atol=1e-5)
+        env.close()
+
+
+@pytest.mark.gpu
+def test_createboard_facade_against_the_reference_rollout():
+    """gym_ballenv_b200.createBoard (reset / step / state list / sensor_readings) replays one environment of the
+    reference createBoard rollout (the first one whose episode ends): same draws (seed, global id), same actions."""
+    import gym_ballenv_b200 as gb
+    from oracle.ballenv_oracle import features20
+    z, meta = load_golden("rollout_pygame")
+    i = int(np.argmax(z["rec_done"].any(0)))
+    env = gb.createBoard(display=False, static_obstacles=meta["n_static"], seed=meta["seed"])
+    env._vec.close()
+    env._vec = gb.BallVecEnv(1, window=5, config=gb.EnvConfig.pygame_default(static_obstacles=meta["n_static"]),
+                             ruleset="pygame", seed=meta["seed"], parity=True, auto_reset=False, max_episode_steps=0,
+                             global_env_offset=meta["g0"] + i)
+    state = env.reset()
+    assert state[0] == tuple(z["init_agent"][i]) and state[1] == tuple(z["init_goal"][i])
+    assert [s[:2] for s in state[3:]] == [tuple(int(v) for v in o) for o in z["init_obst"][i]] and state[3][2] == 20
+    assert env.total_distance == pytest.approx(z["init_total_distance"][i], rel=1e-14)
+    for t in range(meta["T"]):
+        state, reward, done, info = env.step(tuple(z["rec_actions"][t, i]))
+        assert reward == pytest.approx(z["rec_reward"][t, i], rel=1e-12, abs=1e-15) and done == bool(z["rec_done"][t, i])
+        sr = env.sensor_readings
+        assert tuple(sr.shape) == (1, 20) and sr.is_cuda
+        want = features20(state[0], state[1], [s[:2] for s in state[3:]], agent_rad=10)
+        np.testing.assert_allclose(sr.cpu().numpy()[0], np.array(want, dtype=np.float32), rtol=1e-6)
+        if done:
+            break
+        assert state[0] == tuple(z["rec_agent"][t, i])
+    assert done and env.actionArray[1].tolist() == [1, 0]
+    env.close()

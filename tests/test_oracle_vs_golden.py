@@ -138,3 +138,15 @@ def test_rollout_pygame_ruleset():
             if not done[i]:
                 assert e.acc == z["rec_acc"][t, i]
     assert vec.stats["episodes"] == meta["episodes"] > 0
+
+
+def test_features20_against_the_reference_helpers():
+    """featureExtractor.py's numpy helpers (run through the shim) vs the oracle's restatement, 160 states."""
+    from oracle.ballenv_oracle import features20
+    z, meta = load_golden("features_kat")
+    assert z["features"].shape == (meta["n"], 20)
+    for i in range(meta["n"]):
+        got = features20(tuple(z["agent"][i]), tuple(z["goal"][i]), [tuple(o) for o in z["obst"][i]],
+                         agent_rad=float(z["agent_rad"][i]), obstacle_rad=meta["obstacle_rad"])
+        np.testing.assert_allclose(got, z["features"][i], rtol=1e-12, atol=1e-12, err_msg=str(i))
+    assert z["features"][:, 17:].max() > 1 and set(np.unique(z["features"][:, 0])) >= {0.0, 5.0}
