@@ -527,33 +527,35 @@ __device__ __forceinline__ uint32_t stream_bits(const uint32_t* words, int bit, 
 }
 
 // blk points at the block's span of the step's output (environment e0, element 0).
+// tid / nthreads: the caller's index among the threads that share the store (the obstacle threads in the step
+// loop - the scalar warp is the critical path of a step and stays out of it; everybody after a reset).
 template <int W, bool kFast>
-__device__ __forceinline__ void store_obs(const Params& p, void* blk, const uint32_t* words, const float4* lut, int cnt) {
+__device__ __forceinline__ void store_obs(const Params& p, void* blk, const uint32_t* words, const float4* lut, int cnt,
+                                          int tid, int nthreads) {
   const int w = Win<W>::w(p.cfg.window);
   const int nb = 4 + w * w;
-  const int tid = threadIdx.x;
   const int total = cnt * nb;
   if (kFast || p.cfg.obs_format == BALLENV_OBS_F32) {
     // 16-byte alignment holds unless a [T][n][row] rollout buffer has n * row not a multiple of 4 elements
     const int nvec = (reinterpret_cast<uintptr_t>(blk) & 15) == 0 ? total >> 2 : 0;
     float4* dst = reinterpret_cast<float4*>(blk);
-    for (int v = tid; v < nvec; v += kBlock)   // streaming store: the rollout buffer is not re-read by this kernel
+    for (int v = tid; v < nvec; v += nthreads)   // streaming store: the rollout buffer is not re-read by this kernel
       __stcs(dst + v, lut[(words[v >> 3] >> ((v & 7) << 2)) & 15u]);
-    for (int f = (nvec << 2) + tid; f < total; f += kBlock)   // odd tail of the last block / unaligned span
+    for (int f = (nvec << 2) + tid; f < total; f += nthreads)   // odd tail of the last block / unaligned span
       reinterpret_cast<float*>(blk)[f] = (words[f >> 5] >> (f & 31)) & 1u ? 1.0f : 0.0f;
   } else if (p.cfg.obs_format == BALLENV_OBS_U8) {
     const int nvec = (reinterpret_cast<uintptr_t>(blk) & 3) == 0 ? total >> 2 : 0;
     uint32_t* dst = reinterpret_cast<uint32_t*>(blk);
-    for (int v = tid; v < nvec; v += kBlock) {
+    for (int v = tid; v < nvec; v += nthreads) {
       const uint32_t nib = (words[v >> 3] >> ((v & 7) << 2)) & 15u;
       dst[v] = (nib & 1u) | (nib & 2u) << 7 | (nib & 4u) << 14 | (nib & 8u) << 21;
     }
-    for (int f = (nvec << 2) + tid; f < total; f += kBlock)
+    for (int f = (nvec << 2) + tid; f < total; f += nthreads)
       reinterpret_cast<uint8_t*>(blk)[f] = (uint8_t)((words[f >> 5] >> (f & 31)) & 1u);
   } else {  // BALLENV_OBS_BITS: [n][ceil(nb / 32)] words, bit b of row e = element b of environment e
     const int nw = (nb + 31) >> 5;
     uint32_t* base = reinterpret_cast<uint32_t*>(blk);
-    for (int i = tid; i < cnt * nw; i += kBlock) {
+    for (int i = tid; i < cnt * nw; i += nthreads) {
       const int en = i / nw, k = i - en * nw;
       uint32_t v = stream_bits(words, en * nb + 32 * k, nb);
       const int left = nb - 32 * k;
@@ -740,6 +742,24 @@ __device__ __noinline__ void reset_stage(const Params& p, BlockShared<T, W>& sh,
   __syncthreads();
 }
 
+// Prefetch form: volatile asm keeps the load where it is written (before the barrier arrive of the step), so its
+// latency overlaps a whole step instead of being sunk next to its first use.
+__device__ __forceinline__ long long prefetch_action_index(const Params& p, long long i) {
+  long long v;
+  if (p.action_kind == BALLENV_ACT_INDEX_I64) {
+    asm volatile("ld.global.nc.s64 %0, [%1];" : "=l"(v) : "l"(reinterpret_cast<const long long*>(p.actions) + i));
+  } else if (p.action_kind == BALLENV_ACT_INDEX_I32) {
+    int t;
+    asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(t) : "l"(reinterpret_cast<const int*>(p.actions) + i));
+    v = t;
+  } else {
+    unsigned t;
+    asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(t) : "l"(reinterpret_cast<const uint8_t*>(p.actions) + i));
+    v = t;
+  }
+  return v;
+}
+
 __device__ __forceinline__ long long load_action_index(const Params& p, long long i) {
   if (p.action_kind == BALLENV_ACT_INDEX_I64) return reinterpret_cast<const long long*>(p.actions)[i];
   if (p.action_kind == BALLENV_ACT_INDEX_I32) return reinterpret_cast<const int*>(p.actions)[i];
@@ -831,6 +851,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
     if (tid < 16)
       sh.lut[tid] = make_float4(tid & 1 ? 1.0f : 0.0f, tid & 2 ? 1.0f : 0.0f, tid & 4 ? 1.0f : 0.0f, tid & 8 ? 1.0f : 0.0f);
 
+    __syncthreads();   // block setup done: the bit-stream of step 0 is cleared before anyone ORs into it
     int t = 0;
     long long a_next = (kFast && mine) ? load_action_index(p, e) : 0;   // action of step 0
     for (;;) {
@@ -851,14 +872,57 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
         }
       }
       bool pending_reset = false;
+      // outputs of a step (reward, done, statistics) are written one step late, after the next agent positions are
+      // published: nobody waits for them, and the scalar warp is the critical path of a step
+      bool out_pending = false;
+      long long out_et = 0;
+      double out_reward = 0.0, out_ret = 0.0, out_len = 0.0;
+      uint32_t out_done = 0, out_cnt = 0;
+      auto flush_outputs = [&]() {
+        if (!stepping) return;
+        if (out_pending && mine) {
+          if (p.reward != nullptr) {
+            if (sizeof(T) == 4) reinterpret_cast<float*>(p.reward)[out_et] = (float)out_reward;
+            else reinterpret_cast<double*>(p.reward)[out_et] = out_reward;
+          }
+          if (p.done != nullptr) p.done[out_et] = (uint8_t)out_done;
+        }
+        // episode statistics (the only thing that is ever all-reduced across GPUs): ballot + shuffle in the scalar
+        // warp, one atomic per counter per block, and only in blocks where an episode ended.
+        const uint32_t cnt = (out_pending && mine) ? out_cnt : 0u;
+        const uint32_t fin = __ballot_sync(0xffffffffu, cnt != 0);
+        if (fin != 0) {
+          double st_ret = cnt ? out_ret : 0.0, st_len = cnt ? out_len : 0.0;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            st_ret += __shfl_xor_sync(0xffffffffu, st_ret, o);
+            st_len += __shfl_xor_sync(0xffffffffu, st_len, o);
+          }
+          const uint32_t n_goal = __popc(__ballot_sync(0xffffffffu, cnt & 2u));
+          const uint32_t n_hs = __popc(__ballot_sync(0xffffffffu, cnt & 4u));
+          const uint32_t n_hd = __popc(__ballot_sync(0xffffffffu, cnt & 8u));
+          const uint32_t n_to = __popc(__ballot_sync(0xffffffffu, cnt & 16u));
+          if (tid == 0) {
+            atomicAdd(&p.stats[BALLENV_STAT_EPISODES], (double)__popc(fin));
+            atomicAdd(&p.stats[BALLENV_STAT_RETURN_SUM], st_ret);
+            atomicAdd(&p.stats[BALLENV_STAT_LENGTH_SUM], st_len);
+            if (n_goal) atomicAdd(&p.stats[BALLENV_STAT_GOALS], (double)n_goal);
+            if (n_hs) atomicAdd(&p.stats[BALLENV_STAT_HITS_STATIC], (double)n_hs);
+            if (n_hd) atomicAdd(&p.stats[BALLENV_STAT_HITS_DYNAMIC], (double)n_hd);
+            if (n_to) atomicAdd(&p.stats[BALLENV_STAT_TIMEOUTS], (double)n_to);
+          }
+        }
+        if (out_pending && e == 0) atomicAdd(&p.stats[BALLENV_STAT_STEPS], (double)p.n);
+        out_pending = false;
+      };
       // ------------------------------------------- hot loop: no calls inside -------------------------------------
       for (; t < n_steps; ++t, obs_blk += obs_step_bytes) {
         const bool want_obs = kFast ? (p.obs_all_steps != 0 || t == n_steps - 1) : p.obs != nullptr;
         uint32_t* words = sh.words[t & 1];
         const long long et = (long long)t * p.n + e;   // index of this environment in the [T][n] arrays
+        // ---- critical: agent move + clamp (ballenv_env.py:247-259 | ballenv_pygame.py:654-664), publish, arrive
         T nx = ax, ny = ay;
         if (mine && stepping) {
-          // agent move + clamp (ballenv_env.py:247-259 | ballenv_pygame.py:654-664)
           T adx, ady;
           if (!kFast && p.action_kind == BALLENV_ACT_XY_F32) {
             const float2 a = reinterpret_cast<const float2*>(p.actions)[et];
@@ -872,7 +936,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
             long long ai;
             if (kFast) {   // fetched one step ahead: the load latency is off the step's critical path
               ai = a_next;
-              if (t + 1 < n_steps) a_next = load_action_index(p, et + p.n);
+              if (t + 1 < n_steps) a_next = prefetch_action_index(p, et + p.n);
             } else {
               ai = load_action_index(p, et);
             }
@@ -900,10 +964,18 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
         sh.hit[tid] = kNoHit;
         sh.reset[tid] = reset_req ? 1 : 0;   // Reset mode: stored obstacles of these environments are ignored
         if (tid == 0) sh.count = 0;
+        if (mine && !reset_req && want_obs) {
+          // 4 goal-quadrant bits (examples/ball_cnn_ac3.py:341-350); a reset of this environment clears and redoes them
+          const T qdx = r_sub(gx, nx), qdy = r_sub(gy, ny);
+          const int b = tid * nb + goal_quadrant_bit(qdx < (T)0, qdy < (T)0);
+          atomicOr(&words[b >> 5], 1u << (b & 31));
+        }
         bar_arrive(kBarAgent);
 
-        // distance, progress reward, goal and time-limit flags do not depend on the obstacles: computed while the
-        // obstacle threads move and test (ballenv_env.py:268-286, 200-206 | ballenv_pygame.py:652-706)
+        // ---- off the critical path (the obstacle threads are moving and testing): outputs of the previous step,
+        //      then distance, progress reward, goal and time-limit flags of this one
+        //      (ballenv_env.py:268-286, 200-206 | ballenv_pygame.py:652-706)
+        flush_outputs();
         double d = dist, reward = 0.0;
         bool goal_flag = false, truncated = false;
         const int ep_len = len + 1;
@@ -920,6 +992,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
         }
         bar_sync(kBarNear);
 
+        // ---- critical: apply the hits, decide the resets
         bool do_reset = false, done_out = false, hit = false, hit_dyn = false, done = false;
         if (mine) {
           if (stepping) {
@@ -928,7 +1001,6 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
             hit_dyn = hit && hit_first >= ks;
             if (gym) {
               if (hit) reward -= hit_dyn ? cfg.dynamic_penalty : cfg.static_penalty;  // :222-224
-              acc += reward;                                                          // :280
               done = goal_flag || hit;                                                // :286
             } else {
               if (hit) {                                                              // :683-688 (before the goal test)
@@ -939,40 +1011,30 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
                 reward = 1.0;
                 done = true;
               }
-              acc += reward;
             }
             done_out = done || truncated;
             do_reset = done_out && cfg.auto_reset;
           } else if (!kFast && reset_req) {
             do_reset = true;
           }
-          if (do_reset) {
-            sh.reset[tid] = 1;
-          } else if (want_obs) {
-            // 4 goal-quadrant bits (examples/ball_cnn_ac3.py:341-350); the obstacle warps are OR-ing cells concurrently
-            const T qdx = r_sub(gx, nx), qdy = r_sub(gy, ny);
-            const int b = tid * nb + goal_quadrant_bit(qdx < (T)0, qdy < (T)0);
-            atomicOr(&words[b >> 5], 1u << (b & 31));
-          }
+          if (do_reset) sh.reset[tid] = 1;
         }
         const bool any_reset = bar_or(kBarDone, do_reset);
 
-        // outputs of the step and statistics: nobody waits for these
-        double st_ret = 0.0, st_len = 0.0;
-        uint32_t st_cnt = 0;  // episode | goal << 1 | hit_static << 2 | hit_dynamic << 3 | timeout << 4
+        // ---- state of the next step; the step's outputs are parked until after the next arrive
         if (mine && stepping) {
+          acc += reward;                                                              // :280
           flags = (goal_flag ? BALLENV_FLAG_GOAL : 0) | (hit ? BALLENV_FLAG_HIT : 0) |
                   (truncated ? BALLENV_FLAG_TRUNCATED : 0) | (hit_dyn ? BALLENV_FLAG_HIT_DYNAMIC : 0);
-          if (p.reward != nullptr) {
-            if (sizeof(T) == 4) reinterpret_cast<float*>(p.reward)[et] = (float)reward;
-            else reinterpret_cast<double*>(p.reward)[et] = reward;
-          }
-          if (p.done != nullptr) p.done[et] = done_out ? 1 : 0;
+          out_et = et;
+          out_reward = reward;
+          out_done = done_out ? 1u : 0u;
+          out_cnt = 0;
           if (done_out) {
-            st_ret = acc;
-            st_len = (double)ep_len;
-            st_cnt = 1u | (goal_flag ? 2u : 0u) | ((hit && !hit_dyn) ? 4u : 0u) | (hit_dyn ? 8u : 0u) |
-                     ((truncated && !done) ? 16u : 0u);
+            out_ret = acc;
+            out_len = (double)ep_len;
+            out_cnt = 1u | (goal_flag ? 2u : 0u) | ((hit && !hit_dyn) ? 4u : 0u) | (hit_dyn ? 8u : 0u) |
+                      ((truncated && !done) ? 16u : 0u);
           }
           ax = nx;
           ay = ny;
@@ -980,39 +1042,14 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
           len = ep_len;
           tick += 1;
         }
-        if (stepping) {
-          // episode statistics (the only thing that is ever all-reduced across GPUs): ballot + shuffle in the scalar
-          // warp, one atomic per counter per block, and only in blocks where an episode ended.
-          const uint32_t fin = __ballot_sync(0xffffffffu, st_cnt != 0);
-          if (fin != 0) {
-  #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-              st_ret += __shfl_xor_sync(0xffffffffu, st_ret, o);
-              st_len += __shfl_xor_sync(0xffffffffu, st_len, o);
-            }
-            const uint32_t n_goal = __popc(__ballot_sync(0xffffffffu, st_cnt & 2u));
-            const uint32_t n_hs = __popc(__ballot_sync(0xffffffffu, st_cnt & 4u));
-            const uint32_t n_hd = __popc(__ballot_sync(0xffffffffu, st_cnt & 8u));
-            const uint32_t n_to = __popc(__ballot_sync(0xffffffffu, st_cnt & 16u));
-            if (tid == 0) {
-              atomicAdd(&p.stats[BALLENV_STAT_EPISODES], (double)__popc(fin));
-              atomicAdd(&p.stats[BALLENV_STAT_RETURN_SUM], st_ret);
-              atomicAdd(&p.stats[BALLENV_STAT_LENGTH_SUM], st_len);
-              if (n_goal) atomicAdd(&p.stats[BALLENV_STAT_GOALS], (double)n_goal);
-              if (n_hs) atomicAdd(&p.stats[BALLENV_STAT_HITS_STATIC], (double)n_hs);
-              if (n_hd) atomicAdd(&p.stats[BALLENV_STAT_HITS_DYNAMIC], (double)n_hd);
-              if (n_to) atomicAdd(&p.stats[BALLENV_STAT_TIMEOUTS], (double)n_to);
-            }
-          }
-          if (e == 0) atomicAdd(&p.stats[BALLENV_STAT_STEPS], (double)p.n);
-        }
+        out_pending = stepping;
         if (any_reset) {   // leave the hot loop: the reset goes through global memory
           pending_reset = true;
           break;
         }
-        if (want_obs && !(p.debug & 8))
-          store_obs<W, kFast>(p, obs_blk, words, sh.lut, cnt_env);
+        // (the observation rows of the step are stored by the obstacle threads)
       }
+      flush_outputs();
 
       // ---- write the scalar state back (a pending reset then overwrites it for the environments that finished)
       if (mine) {
@@ -1035,7 +1072,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
         uint32_t* words = sh.words[t & 1];
         reset_stage<T, W>(p, sh, words, e0, cnt_env, want_obs);
         if (want_obs && !(p.debug & 8))
-          store_obs<W, kFast>(p, obs_blk, words, sh.lut, cnt_env);
+          store_obs<W, kFast>(p, obs_blk, words, sh.lut, cnt_env, tid, kBlock);
         reset_req = false;
         obs_blk += obs_step_bytes;
         if (++t >= n_steps) break;
@@ -1083,8 +1120,8 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
         sh.mv[l32].y = (T)table2(kObstDy, (uint32_t)l32);
       }
       for (int i = l32; i < cfg.n_goals; i += 32) sh.goal[i] = CfgV<T>::goal(cfg, i);
-      __syncwarp();
     }
+    __syncthreads();   // block setup done (pairs with the scalar warp's)
 
     int t = 0, t_load = 0;
     for (;;) {
@@ -1159,7 +1196,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
           break;
         }
         if (want_obs && !(p.debug & 8))
-          store_obs<W, kFast>(p, obs_blk, words, sh.lut, cnt_env);
+          store_obs<W, kFast>(p, obs_blk, words, sh.lut, cnt_env, lt, kLaneThreads);
       }
 
       // ---- write the moved quads back (a pending reset then overwrites those of the environments that finished)
@@ -1170,7 +1207,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
         uint32_t* words = sh.words[t & 1];
         reset_stage<T, W>(p, sh, words, e0, cnt_env, want_obs);
         if (want_obs && !(p.debug & 8))
-          store_obs<W, kFast>(p, obs_blk, words, sh.lut, cnt_env);
+          store_obs<W, kFast>(p, obs_blk, words, sh.lut, cnt_env, tid, kBlock);
         if (!kFast && lt < n_slot) q_have = q_el < cnt_env;   // Reset mode: the environment has state now
         obs_blk += obs_step_bytes;
         if (++t >= n_steps) break;
