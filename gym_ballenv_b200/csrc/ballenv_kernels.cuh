@@ -253,6 +253,7 @@ struct BlockShared {
   typename Vec2<T>::type goal[BALLENV_MAX_GOALS];    // obstacle goals (args.obs_goal_position)
   typename Vec2<T>::type mv[12];                     // obstacle move table (ballenv_env.py:324)
   float4 lut[16];                                    // 4 observation bits -> 4 floats
+  long long act[2][kEnvsPerBlock];                   // int64 action indices fetched one step ahead (cp.async)
   // scalar-warp state parked between its two stages (keeps it out of the obstacle threads' register budget)
   T s_gx[kEnvsPerBlock], s_gy[kEnvsPerBlock], s_oax[kEnvsPerBlock], s_oay[kEnvsPerBlock];
   double s_old[kEnvsPerBlock], s_total[kEnvsPerBlock], s_acc[kEnvsPerBlock];
@@ -742,23 +743,13 @@ __device__ __noinline__ void reset_stage(const Params& p, BlockShared<T, W>& sh,
   __syncthreads();
 }
 
-// Prefetch form: volatile asm keeps the load where it is written (before the barrier arrive of the step), so its
-// latency overlaps a whole step instead of being sunk next to its first use.
-__device__ __forceinline__ long long prefetch_action_index(const Params& p, long long i) {
-  long long v;
-  if (p.action_kind == BALLENV_ACT_INDEX_I64) {
-    asm volatile("ld.global.nc.s64 %0, [%1];" : "=l"(v) : "l"(reinterpret_cast<const long long*>(p.actions) + i));
-  } else if (p.action_kind == BALLENV_ACT_INDEX_I32) {
-    int t;
-    asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(t) : "l"(reinterpret_cast<const int*>(p.actions) + i));
-    v = t;
-  } else {
-    unsigned t;
-    asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(t) : "l"(reinterpret_cast<const uint8_t*>(p.actions) + i));
-    v = t;
-  }
-  return v;
+// One-step-ahead action fetch for int64 indices: cp.async copies the 8 bytes global -> shared without a register,
+// so neither a spill nor an early use can pull the load latency back onto the scalar warp's critical path.
+__device__ __forceinline__ void action_fetch_async(long long* smem_slot, const long long* gmem) {
+  const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem_slot);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(gmem) : "memory");
 }
+__device__ __forceinline__ void action_fetch_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 __device__ __forceinline__ long long load_action_index(const Params& p, long long i) {
   if (p.action_kind == BALLENV_ACT_INDEX_I64) return reinterpret_cast<const long long*>(p.actions)[i];
@@ -852,8 +843,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
       sh.lut[tid] = make_float4(tid & 1 ? 1.0f : 0.0f, tid & 2 ? 1.0f : 0.0f, tid & 4 ? 1.0f : 0.0f, tid & 8 ? 1.0f : 0.0f);
 
     __syncthreads();   // block setup done: the bit-stream of step 0 is cleared before anyone ORs into it
-    int t = 0;
-    long long a_next = (kFast && mine) ? load_action_index(p, e) : 0;   // action of step 0
+    int t = 0, t_fetch = 0;   // t_fetch: the step whose action has to be loaded directly (no fetch in flight)
     for (;;) {
       // (re)load: at launch, and after a reset went through global memory
       if (mine) {
@@ -934,9 +924,16 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
             ady = (T)a.y;
           } else {
             long long ai;
-            if (kFast) {   // fetched one step ahead: the load latency is off the step's critical path
-              ai = a_next;
-              if (t + 1 < n_steps) a_next = prefetch_action_index(p, et + p.n);
+            if (kFast && p.action_kind == BALLENV_ACT_INDEX_I64) {
+              // fetched one step ahead into shared memory: the load latency is off the step's critical path
+              if (t == t_fetch) {   // first step after a (re)load: nothing in flight yet
+                ai = reinterpret_cast<const long long*>(p.actions)[et];
+              } else {
+                action_fetch_wait();
+                ai = sh.act[t & 1][tid];
+              }
+              if (t + 1 < n_steps)
+                action_fetch_async(&sh.act[(t + 1) & 1][tid], reinterpret_cast<const long long*>(p.actions) + et + p.n);
             } else {
               ai = load_action_index(p, et);
             }
