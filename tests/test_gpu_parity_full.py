@@ -120,3 +120,44 @@ def test_round_trip_properties_at_full_size():
     assert st["steps"] == n * T
     assert env.error_flags() == 0
     env.close()
+
+
+@pytest.mark.parametrize("ks,kd,w,n", [(40, 12, 5, 100), (0, 5, 5, 70), (3, 0, 7, 33), (70, 40, 10, 64)])
+def test_unusual_obstacle_counts_against_the_c_oracle(ks, kd, w, n):
+    """More than 8 quads per environment (the slots beyond the 256 register-held ones go through global memory
+    every step, dynamic ones included), no static or no dynamic obstacles: per-step launches and the rollout
+    kernel, with auto-resets, against the C oracle."""
+    from gym_ballenv_b200 import BallVecEnv, EnvConfig
+    from oracle.ballenv_oracle import OracleConfig
+    from oracle.c_oracle import COracleVec
+    goals = [(13 * i % 480 + 7, 29 * i % 440 + 30) for i in range(max(kd, 2))]
+    speeds = [1 + (j % 3) for j in range(kd)]
+    cfg = EnvConfig(static_obstacles=ks, dynamic_obstacles=kd, obstacle_speed=speeds,
+                    obs_goal_position=["%d,%d" % g for g in goals] if kd else (), time_step_for_change=7)
+    ocfg = OracleConfig(window=w, n_static=ks, n_dynamic=kd, speeds=speeds, goals=goals, change_step=7,
+                        max_episode_steps=11)
+    seed, T = 17, 30
+    env = BallVecEnv(n, window=w, config=cfg, seed=seed, max_episode_steps=11)
+    c = COracleVec(ocfg, seed, n)
+    obs = env.reset()
+    c.reset()
+    assert np.array_equal(obs.cpu().numpy(), c.observe())
+    g = torch.Generator().manual_seed(4)
+    for t in range(10):                                   # one launch per step
+        a = torch.randint(0, 9, (n,), generator=g)
+        obs, rew, done, info = env.step(a.cuda())
+        r, d, f = c.step(a.numpy())
+        assert np.array_equal(obs.cpu().numpy(), c.observe()), t
+        assert np.array_equal(done.cpu().numpy(), d) and np.array_equal(info["flags"].cpu().numpy(), f), t
+        np.testing.assert_allclose(rew.cpu().numpy(), r, rtol=1e-5, atol=0)
+    a = torch.randint(0, 9, (T, n), generator=g)          # one launch for T steps
+    obs, rew, done = env.step_many(a.cuda(), keep_all_obs=True)
+    obs, rew, done = obs.cpu().numpy(), rew.cpu().numpy(), done.cpu().numpy()
+    for t in range(T):
+        r, d, f = c.step(a[t].numpy())
+        assert np.array_equal(obs[t], c.observe()), t
+        assert np.array_equal(done[t], d), t
+        np.testing.assert_allclose(rew[t], r, rtol=1e-5, atol=0)
+    _check_state(env, c)
+    assert env.stats()["episodes"] == c.stats["episodes"] > 0 and env.error_flags() == 0
+    env.close()
