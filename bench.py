@@ -260,7 +260,7 @@ def measure_e2e(env, torch, n, steps, chunk, dist, world):
     dev = env.device
     g = torch.Generator().manual_seed(7 + env.global_env_offset)
     act = torch.randint(0, 9, (chunk, n), generator=g, dtype=torch.int64).pin_memory()
-    obs = torch.empty((n, env.obs_row), dtype=torch.float32).pin_memory()
+    obs = torch.empty((n, env.obs_row), dtype=env._bufs[0]["obs"].dtype).pin_memory()
     rew = torch.empty(n, dtype=torch.float32).pin_memory()
     done = torch.empty(n, dtype=torch.uint8).pin_memory()
     for t in range(3):
@@ -282,7 +282,7 @@ def measure_e2e(env, torch, n, steps, chunk, dist, world):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms = float(tt[0])
     h2d = chunk * act[0].numel() * 8
-    d2h = chunk * (obs.numel() * 4 + rew.numel() * 4 + done.numel())
+    d2h = chunk * (obs.numel() * obs.element_size() + rew.numel() * 4 + done.numel())
     return ms, h2d, d2h, env.launch_count - l0
 
 
@@ -358,6 +358,18 @@ def run_gpu(args, spec):
     e2e_value = float(world) * n * chunk * e2e_steps / (ems * 1e-3)
     errs = env.error_flags()
     stats = env.stats()
+    # the same host round trip with the observation rows as uint8 (identical 0/1 values, a quarter of the PCIe bytes;
+    # the reference casts its observation with .float() anyway, examples/ball_cnn_ac3.py:211) - reported beside e2e
+    e2e_u8 = None
+    if args.e2e_u8:
+        from gym_ballenv_b200 import make_sharded_env as _mk
+        env8 = _mk(world * n, rank=rank, world=world, device=dev, window=spec["window"], config=env_config(spec),
+                   seed=0, obs_dtype=torch.uint8)
+        env8.reset()
+        ms8, h8, d8, _ = measure_e2e(env8, torch, n, e2e_steps, chunk, dist, world)
+        e2e_u8 = {"value": float(world) * n * chunk * e2e_steps / (ms8 * 1e-3), "unit": UNIT,
+                  "h2d_bytes_per_step": h8, "d2h_bytes_per_step": d8, "obs": "uint8"}
+        env8.close()
 
     secondary = None
     if args.secondary and spec["name"] == "c3":
@@ -398,6 +410,7 @@ def run_gpu(args, spec):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "api": "ballenv_step_host (C ABI), pinned host buffers, fp32 obs to host "
                                                "every env-step"},
+            "e2e_uint8_obs": e2e_u8,
             "gpu_launches": launches,
             "clocks": clocks,
             "episode_stats": {k: stats[k] for k in ("episodes", "goals", "hits_static", "hits_dynamic", "timeouts")},
@@ -422,6 +435,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=CHUNK)
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--closed-loop-steps", type=int, default=5)
+    ap.add_argument("--e2e-u8", type=int, default=1)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--secondary", type=int, default=1)

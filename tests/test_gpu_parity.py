@@ -484,3 +484,26 @@ def test_createboard_facade_against_the_reference_rollout():
         assert state[0] == tuple(z["rec_agent"][t, i])
     assert done and env.actionArray[1].tolist() == [1, 0]
     env.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("obs_dtype", [torch.float32, torch.uint8])
+def test_step_host_equals_step(obs_dtype):
+    """ballenv_step_host (host buffers, copies inside the call - the path bench.py's e2e goes through) returns what
+    ballenv_step returns, for fp32 and uint8 observation rows."""
+    from gym_ballenv_b200 import BallVecEnv
+    n = 333
+    dev_env = BallVecEnv(n, window=5, seed=8, max_episode_steps=9, obs_dtype=obs_dtype)
+    host_env = BallVecEnv(n, window=5, seed=8, max_episode_steps=9, obs_dtype=obs_dtype)
+    dev_env.reset()
+    host_env.reset()
+    obs = torch.empty((n, 29), dtype=obs_dtype).pin_memory()
+    rew = torch.empty(n, dtype=torch.float32).pin_memory()
+    done = torch.empty(n, dtype=torch.uint8).pin_memory()
+    g = torch.Generator().manual_seed(6)
+    for t in range(25):
+        a = torch.randint(0, 9, (n,), generator=g)
+        o, r, d, _ = dev_env.step(a.cuda())
+        host_env.step_host(a.pin_memory(), obs, rew, done)
+        assert torch.equal(o.cpu(), obs) and torch.equal(r.cpu(), rew) and torch.equal(d.cpu(), done.bool()), t
+    assert host_env.error_flags() == 0
