@@ -1120,6 +1120,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
     }
     __syncthreads();   // block setup done (pairs with the scalar warp's)
 
+    const int n_store = (kRollout && n_stat >= 64 && n_stat < kLaneThreads) ? n_stat : kLaneThreads;
     int t = 0, t_load = 0;
     for (;;) {
       // (re)load the quad: at launch, and after a reset went through global memory
@@ -1192,8 +1193,12 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
           pending_reset = true;
           break;
         }
-        if (want_obs && !(p.debug & 8))
-          store_obs<W, kFast>(p, obs_blk, words, sh.lut, cnt_env, lt, kLaneThreads);
+        // The observation rows are stored by the threads that have the least to do in a step: the static-quad
+        // threads (no draws, no moves) when there are at least two warps of them, otherwise every obstacle thread.
+        if (want_obs && !(p.debug & 8)) {
+          if (n_store == kLaneThreads) store_obs<W, kFast>(p, obs_blk, words, sh.lut, cnt_env, lt, kLaneThreads);
+          else if (lt < n_store) store_obs<W, kFast>(p, obs_blk, words, sh.lut, cnt_env, lt, n_store);
+        }
       }
 
       // ---- write the moved quads back (a pending reset then overwrites those of the environments that finished)
