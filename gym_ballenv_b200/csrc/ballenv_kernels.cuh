@@ -1153,10 +1153,16 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
         // bounding-box test every obstacle against the agent; near ones are hit-tested and queued
         if (q_have && !(p.debug & 4)) {
           const T ax = sh.ax[q_el], ay = sh.ay[q_el];
-  #pragma unroll
+          uint32_t near = 0;   // one branch for the quad: the four tests are almost always all false
+#pragma unroll
           for (int i = 0; i < 4; ++i)
-            if (q_k0 + i < q_kend)
-              near_test<T, W>(sh, words, cfg, q_el, ax, ay, margin, qx[i], qy[i], q_k0 + i, stepping, want_obs, nb);
+            near |= (q_k0 + i < q_kend && r_abs(r_sub(ax, qx[i])) <= margin && r_abs(r_sub(ay, qy[i])) <= margin ? 1u : 0u) << i;
+          if (near != 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              if (near >> i & 1u)
+                near_push<T, W>(sh, words, cfg, q_el, ax, ay, qx[i], qy[i], q_k0 + i, stepping, want_obs, nb);
+          }
         }
         for (int slot = lt + kLaneThreads; slot < n_slot; slot += kLaneThreads) {   // more than 8 quads per environment
           const bool dyn = slot >= n_stat;
@@ -1180,7 +1186,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
           }
           const int k0 = dyn ? ks + 4 * qq : 4 * qq, kend = dyn ? ks + kd : ks;
           const T ax = sh.ax[el], ay = sh.ay[el];
-  #pragma unroll
+#pragma unroll
           for (int i = 0; i < 4; ++i)
             if (k0 + i < kend)
               near_test<T, W>(sh, words, cfg, el, ax, ay, margin, x[i], y[i], k0 + i, stepping, want_obs, nb);
