@@ -583,7 +583,8 @@ __device__ __forceinline__ void dynamic_load(const Params& p, uint32_t off, bool
 // ... then one Philox block and four moves, in registers (ballenv_env.py:262-264, 323-353) ...
 // kFast: Philox draws (no tape) and distinct goals - the production case, with the uniform tests hoisted out of
 // the per-obstacle code.
-template <typename T, int W, bool kFast>
+// kFull (with kFast): all four slots of the quad hold obstacles, no per-slot bound test.
+template <typename T, int W, bool kFast, bool kFull = false>
 __device__ __forceinline__ void dynamic_move(const Params& p, const BlockShared<T, W>& sh, long long e, int jq,
                                              uint32_t tick, T (&x)[4], T (&y)[4], uint32_t (&meta)[4]) {
   const DevConfig& cfg = p.cfg;
@@ -595,7 +596,7 @@ __device__ __forceinline__ void dynamic_move(const Params& p, const BlockShared<
     const int j = 4 * jq + i;
     if (kFast) {
       const uint32_t w1 = pick_word(blk, i);
-      if (j < cfg.kd) move_lean<T, W>(cfg, sh, j, w1, w1 * 100u, x[i], y[i], meta[i]);
+      if (kFull || j < cfg.kd) move_lean<T, W>(cfg, sh, j, w1, w1 * 100u, x[i], y[i], meta[i]);
     } else if (j < cfg.kd) {
       uint32_t w1 = pick_word(blk, i), w2 = w1 * 100u;   // second draw: unused low half of w1 * 100
       if (has_tape) {
@@ -1141,7 +1142,9 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
         uint32_t* words = sh.words[t & 1];
         // obstacle motion does not depend on the agent: draw and move while the scalar warp works
         if (q_have && q_dyn && stepping && !(p.debug & 2)) {
-          if (kFast || (p.step_tape == nullptr && cfg.goals_distinct))
+          if (kFast && (kd & 3) == 0)   // block-uniform: every dynamic quad is full
+            dynamic_move<T, W, true, true>(p, sh, e0 + q_el, q_jq, tick + (uint32_t)t, qx, qy, qm);
+          else if (kFast || (p.step_tape == nullptr && cfg.goals_distinct))
             dynamic_move<T, W, true>(p, sh, e0 + q_el, q_jq, tick + (uint32_t)t, qx, qy, qm);
           else
             dynamic_move<T, W, false>(p, sh, e0 + q_el, q_jq, tick + (uint32_t)t, qx, qy, qm);
