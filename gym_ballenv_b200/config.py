@@ -6,8 +6,8 @@ examples/ball_cnn_ac3.py:40-51.  ``EnvConfig.from_args`` accepts such a Namespac
 """
 from __future__ import annotations
 
-from dataclasses import dataclass, field
-from typing import List, Sequence
+from dataclasses import dataclass
+from typing import Sequence
 
 from . import _lib as L
 

@@ -362,6 +362,14 @@ int ballenv_create(const BallenvConfig* cfg, int64_t n_envs, int64_t global_env_
   if (n_envs <= 0 || n_envs > (1ll << 31) - 256) return fail(BALLENV_EINVAL, "n_envs %lld out of range", (long long)n_envs);
   if (global_env_offset < 0 || global_env_offset + n_envs > (1ll << 32))
     return fail(BALLENV_EINVAL, "global env ids must fit 32 bits");
+  {
+    // the kernels address obstacle quads with 32-bit element offsets: n x (obstacles rounded up to 4) must fit
+    const long long kmax = (long long)align_up((size_t)(cfg->static_obstacles > cfg->dynamic_obstacles
+                                                             ? cfg->static_obstacles : cfg->dynamic_obstacles), 4);
+    if ((long long)align_up((size_t)n_envs, 128) * (kmax > 0 ? kmax : 1) >= (1ll << 31))
+      return fail(BALLENV_EINVAL, "n_envs x obstacles per kind (%lld x %lld) must stay below 2^31 elements",
+                  (long long)n_envs, kmax);
+  }
   int ndev = 0;
   CUDA_TRY(cudaGetDeviceCount(&ndev));
   if (device < 0 || device >= ndev) return fail(BALLENV_EINVAL, "device %d not in [0, %d)", device, ndev);

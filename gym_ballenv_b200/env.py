@@ -15,9 +15,8 @@ from types import SimpleNamespace
 import numpy as np
 import torch
 
-from . import _lib as L
 from .config import EnvConfig
-from .vec_env import BallVecEnv, MOVE_LIST
+from .vec_env import BallVecEnv
 
 _screen_width = 500
 _screen_height = 500
