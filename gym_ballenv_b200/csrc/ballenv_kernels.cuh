@@ -1,6 +1,7 @@
 // Fused step + window-observe kernel of the batched ball environment (sm_100a).
 //
-// One launch advances every environment of a handle by one step:
+// One launch advances every environment of a handle by one step (ballenv_step) or by T steps with the state held
+// on chip (ballenv_step_many, the rollout loop):
 //   agent move + wall clamp            gym_ballenv/envs/ballenv_env.py:236-259 | ballenv_pygame.py:652-665
 //   obstacle motion                    ballenv_env.py:262-264, 323-353
 //   distance, goal / obstacle tests,   ballenv_env.py:268-286, 200-229, 179-191 | ballenv_pygame.py:668-706
@@ -13,23 +14,23 @@
 // Mapping (B200: 148 SMs want several hundred thousand threads in flight; 64 K environments alone are too few):
 //   * a block of 288 threads owns 32 consecutive environments.  Warp 0 is the scalar warp: thread t owns
 //     environment t's scalars (agent, goal, distance, reward, counters), struct-of-arrays, so every load and
-//     store of the warp is one full 128-byte line.  Warps 1..8 are obstacle lanes, 8 consecutive lanes per
-//     environment.
-//   * obstacles live env-major, [n][K padded to 4]: lane l of an environment owns obstacle quads l, l+8, ...
-//     and moves them with one 128-bit load and one 128-bit store per field (x, y, meta).  A warp touches
-//     4 environments x K contiguous elements per field, i.e. whole 128-byte lines.  One Philox4x32-10 block
-//     feeds the four obstacles of a quad.  Loads, draws, moves and write-back do not depend on the agent and
-//     overlap the scalar warp's load -> move -> clamp chain.
-//   * most obstacles are far from the agent.  Each lane bounding-box tests its obstacles; the rare near ones
-//     are appended to a shared-memory list, and the obstacle warps then rasterise the list one
-//     (obstacle, window row) item per thread with exactly the reference's arithmetic (dx*dx + dy*dy against the
-//     radius sum), OR-ing row masks into the per-environment observation bit-stream in shared memory.  The
-//     grid is therefore bit-exact by construction and the work is balanced no matter where obstacles cluster.
-//     Meanwhile the scalar warp computes distance, reward, flags, done and the episode statistics.
-//   * the block's observation span [32 envs][4 + W*W] is contiguous and 128-byte aligned in global memory; all
-//     threads expand bits into 128-bit coalesced streaming stores.
-//   * environments that finish are reset in the same launch by their own 8 lanes (rejection sampling runs
-//     per obstacle, quads in parallel), followed by a second list raster; blocks without a reset skip this.
+//     store of the warp is one full 128-byte line.  Warps 1..8 are obstacle threads.
+//   * obstacles live env-major, [n][K padded to 4].  The block's quads form one linear slot space (static quads
+//     first, then dynamic ones, exactly as they lie in memory); thread s owns slot s and moves it with one 128-bit
+//     load and one 128-bit store per field (x, y, meta), so consecutive threads issue consecutive 128-bit accesses
+//     and a warp is purely static or purely dynamic.  One Philox4x32-10 block feeds the four obstacles of a quad.
+//     Draws and moves do not depend on the agent and overlap the scalar warp's action -> move -> clamp chain.
+//   * most obstacles are far from the agent.  Each thread bounding-box tests its quad (one branch for the four
+//     tests); the rare near obstacles are hit-tested and appended to a shared-memory list, and the obstacle threads
+//     then rasterise the list one (obstacle, window row) item per thread with exactly the reference's arithmetic
+//     (dx*dx + dy*dy against the radius sum), OR-ing row masks into the block's observation bit-stream in shared
+//     memory.  The grid is therefore bit-exact by construction and the work is balanced wherever obstacles cluster.
+//     Meanwhile the scalar warp computes distance, reward, flags, done and the episode statistics in fp64.
+//   * the block's observation span [32 envs][4 + W*W] is contiguous and 128-byte aligned in global memory and its
+//     element f is bit f of the bit-stream: a 16-entry float4 table expands one nibble into one 128-bit streaming
+//     store.  In the rollout loop the static-quad threads (no draws, no moves) do the stores.
+//   * environments that finish are reset in the same launch (reset_stage, out of line: rejection sampling per
+//     obstacle, quads in parallel, second list raster); the hot loop is left for it and re-entered after a reload.
 // Nothing here is a dense contraction: no tensor cores.
 #pragma once
 #include <stdint.h>
