@@ -255,6 +255,8 @@ struct BlockShared {
   typename Vec2<T>::type mv[12];                     // obstacle move table (ballenv_env.py:324)
   float4 lut[16];                                    // 4 observation bits -> 4 floats
   long long act[2][kEnvsPerBlock];                   // int64 action indices fetched one step ahead (cp.async)
+  uint8_t rlist[kEnvsPerBlock];                      // reset stage: compact list of the resetting environments
+  int nreset;
   // scalar-warp state parked between its two stages (keeps it out of the obstacle threads' register budget)
   T s_gx[kEnvsPerBlock], s_gy[kEnvsPerBlock], s_oax[kEnvsPerBlock], s_oay[kEnvsPerBlock];
   double s_old[kEnvsPerBlock], s_total[kEnvsPerBlock], s_acc[kEnvsPerBlock];
@@ -365,7 +367,7 @@ struct ResetHead {
 };
 
 template <typename T>
-__device__ __noinline__ ResetHead<T> reset_head_draw(const Params& p, const DrawCtx& dc, uint32_t episode) {
+__device__ __forceinline__ ResetHead<T> reset_head_draw(const Params& p, const DrawCtx& dc, uint32_t episode) {
   const DevConfig& cfg = p.cfg;
   ResetHead<T> r;
   if (cfg.ruleset == BALLENV_RULESET_GYM) {
@@ -398,7 +400,7 @@ __device__ __noinline__ ResetHead<T> reset_head_draw(const Params& p, const Draw
 
 // Static obstacle i: redraw until it clears the agent and the goal (ballenv_env.py:131-149 | ballenv_pygame.py:489-498).
 template <typename T>
-__device__ __noinline__ void reset_static_draw(const Params& p, const DrawCtx& dc, uint32_t episode, int i,
+__device__ __forceinline__ void reset_static_draw(const Params& p, const DrawCtx& dc, uint32_t episode, int i,
                                                const ResetHead<T>& h, T& x, T& y) {
   const DevConfig& cfg = p.cfg;
   for (int attempt = 0;; ++attempt) {
@@ -627,8 +629,15 @@ __device__ __forceinline__ int div_slot(int slot, uint32_t rcp) {
 
 // ---- stage D of the kernel (rare): (auto-)reset ---------------------------------------------------------------------
 // Kept out of line so that its register needs (Philox blocks, rejection loops, fp64 distances) do not count
-// against the per-step path.  Every obstacle thread takes quads of resetting environments (same slot space as
-// the step); the observation of a finished environment becomes the first observation of its next episode.
+// against the per-step path.  While it runs the rest of the block waits, so it is organised for a short critical
+// path rather than for few instructions:
+//   1. the scalar thread of every resetting environment clears the environment's observation bits, draws the head
+//      (goal, agent, distances), writes the scalar state and publishes the head through shared memory;
+//   2. the obstacle draws of all resetting environments form one item space (environment, obstacle) spread over all
+//      256 obstacle threads - one obstacle per thread per pass, each with its own Philox block(s) and rejection loop,
+//      so the draw order of the reference (ballenv_env.py:131-164) needs no sequential stream;
+//   3. the block rasterises the near list of the new episodes.
+// The observation of a finished environment thereby becomes the first observation of its next episode.
 template <typename T, int W>
 __device__ __noinline__ void reset_stage(const Params& p, BlockShared<T, W>& sh, uint32_t* words, long long e0,
                                          int cnt_env, bool want_obs) {
@@ -638,109 +647,92 @@ __device__ __noinline__ void reset_stage(const Params& p, BlockShared<T, W>& sh,
   const int lt = tid - 32;
   const int w = Win<W>::w(cfg.window);
   const int nb = 4 + w * w;
-  const int ks = cfg.ks, kd = cfg.kd;
-  const int qs = (ks + 3) >> 2, qd = (kd + 3) >> 2;
-  const int n_stat = kEnvsPerBlock * qs, n_slot = kEnvsPerBlock * (qs + qd);
+  const int ks = cfg.ks, kd = cfg.kd, K = ks + kd;
   const T margin = CfgV<T>::margin(cfg);
-  const uint32_t stat0 = (uint32_t)e0 * (uint32_t)p.stat_stride, dyn0 = (uint32_t)e0 * (uint32_t)p.dyn_stride;
-  T* agent_x = reinterpret_cast<T*>(p.agent_x);
-  T* agent_y = reinterpret_cast<T*>(p.agent_y);
-  T* goal_x = reinterpret_cast<T*>(p.goal_x);
-  T* goal_y = reinterpret_cast<T*>(p.goal_y);
 
-  if (is_scalar && tid < cnt_env && sh.reset[tid] != 0) {   // clear this environment's bits of the stream
-    for (int b = tid * nb, end = b + nb; b < end;) {
-      const int sh_ = b & 31, take = min(32 - sh_, end - b);
-      const uint32_t mask = (take == 32 ? 0xffffffffu : ((1u << take) - 1u)) << sh_;
-      atomicAnd(&words[b >> 5], ~mask);
-      b += take;
+  if (is_scalar) {
+    const bool mine = tid < cnt_env && sh.reset[tid] != 0;
+    // compact list of the resetting environments
+    const uint32_t m = __ballot_sync(0xffffffffu, mine);
+    if (mine) sh.rlist[__popc(m & ((1u << tid) - 1u))] = (uint8_t)tid;
+    if (tid == 0) {
+      sh.nreset = __popc(m);
+      sh.count = 0;
     }
-  }
-  if (tid == 0) sh.count = 0;
-  __syncthreads();
-  if (!is_scalar) {
-    T* dyn_x = reinterpret_cast<T*>(p.dyn_x);
-    T* dyn_y = reinterpret_cast<T*>(p.dyn_y);
-    T* wstat_x = reinterpret_cast<T*>(p.stat_x);
-    T* wstat_y = reinterpret_cast<T*>(p.stat_y);
-    for (int slot = lt; slot < n_slot; slot += kLaneThreads) {
-      const bool dyn = slot >= n_stat;
-      const int sl = dyn ? slot - n_stat : slot;
-      const int per = dyn ? qd : qs;
-      const int el = div_slot(sl, dyn ? cfg.rcp_qd : cfg.rcp_qs), qq = sl - el * per;
-      if (el >= cnt_env || sh.reset[el] == 0) continue;
-      const long long e = e0 + el;
+    if (mine) {
+      for (int b = tid * nb, end = b + nb; b < end;) {   // clear this environment's bits of the stream
+        const int sh_ = b & 31, take = min(32 - sh_, end - b);
+        const uint32_t mask = (take == 32 ? 0xffffffffu : ((1u << take) - 1u)) << sh_;
+        atomicAnd(&words[b >> 5], ~mask);
+        b += take;
+      }
+      const long long e = e0 + tid;
       const DrawCtx dc{&p, e, p.g0 + (uint32_t)e};
       const uint32_t episode = p.episode[e] + 1;
       const ResetHead<T> head = reset_head_draw<T>(p, dc, episode);
-      T x[4] = {(T)0, (T)0, (T)0, (T)0}, y[4] = {(T)0, (T)0, (T)0, (T)0};
-      if (!dyn) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {                                              // :131-149
-          const int k = 4 * qq + i;
-          if (k < ks) {
-            reset_static_draw<T>(p, dc, episode, k, head, x[i], y[i]);
-            near_test<T, W>(sh, words, cfg, el, head.ax, head.ay, margin, x[i], y[i], k, false, want_obs, nb);
-          }
-        }
-        store4(wstat_x + stat0 + 4u * (uint32_t)sl, x);
-        store4(wstat_y + stat0 + 4u * (uint32_t)sl, y);
-      } else {
-        uint32_t meta[4] = {0, 0, 0, 0};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {                                              // :153-164
-          const int j = 4 * qq + i;
-          if (j < kd) {
-            const uint2 w2 = dc.reset_dynamic(episode, j);
-            x[i] = (T)__umulhi(w2.x, 500u);
-            y[i] = (T)(20u + __umulhi(w2.y, 460u));
-            meta[i] = (uint32_t)j;   // curr_goal = goal_list[j], curr_counter = 0
-            near_test<T, W>(sh, words, cfg, el, head.ax, head.ay, margin, x[i], y[i], ks + j, false, want_obs, nb);
-          }
-        }
-        const uint32_t off = dyn0 + 4u * (uint32_t)sl;
-        store4(dyn_x + off, x);
-        store4(dyn_y + off, y);
-        store4(p.dyn_meta + off, meta);
+      sh.s_gx[tid] = head.gx;
+      sh.s_gy[tid] = head.gy;
+      sh.s_tick[tid] = episode;
+      sh.ax[tid] = head.ax;
+      sh.ay[tid] = head.ay;
+      p.episode[e] = episode;
+      reinterpret_cast<T*>(p.agent_x)[e] = head.ax;
+      reinterpret_cast<T*>(p.agent_y)[e] = head.ay;
+      reinterpret_cast<T*>(p.goal_x)[e] = head.gx;
+      reinterpret_cast<T*>(p.goal_y)[e] = head.gy;
+      p.dist[e] = head.dist;
+      p.total[e] = head.total;
+      p.acc[e] = 0.0;
+      p.ep_len[e] = 0;
+      if (want_obs) {
+        const T qdx = r_sub(head.gx, head.ax), qdy = r_sub(head.gy, head.ay);
+        const int b = tid * nb + goal_quadrant_bit(qdx < (T)0, qdy < (T)0);
+        atomicOr(&words[b >> 5], 1u << (b & 31));
       }
-    }
-  } else if (tid < cnt_env && sh.reset[tid] != 0) {
-    // the scalar thread of a resetting environment draws the same head and owns the scalar state
-    const long long e = e0 + tid;
-    const DrawCtx dc{&p, e, p.g0 + (uint32_t)e};
-    const uint32_t episode = p.episode[e] + 1;
-    const ResetHead<T> head = reset_head_draw<T>(p, dc, episode);
-    sh.s_gx[tid] = head.gx;   // written back below, after every obstacle thread has read p.episode
-    sh.s_gy[tid] = head.gy;
-    sh.s_oax[tid] = head.ax;
-    sh.s_oay[tid] = head.ay;
-    sh.s_old[tid] = head.dist;
-    sh.s_total[tid] = head.total;
-    sh.s_tick[tid] = episode;
-    if (want_obs) {
-      const T qdx = r_sub(head.gx, head.ax), qdy = r_sub(head.gy, head.ay);
-      const int b = tid * nb + goal_quadrant_bit(qdx < (T)0, qdy < (T)0);
-      atomicOr(&words[b >> 5], 1u << (b & 31));
     }
   }
   __syncthreads();
-  if (is_scalar) {
-    if (tid < cnt_env && sh.reset[tid] != 0) {
-      const long long e = e0 + tid;
-      sh.ax[tid] = sh.s_oax[tid];
-      sh.ay[tid] = sh.s_oay[tid];
-      p.episode[e] = sh.s_tick[tid];
-      agent_x[e] = sh.s_oax[tid];
-      agent_y[e] = sh.s_oay[tid];
-      goal_x[e] = sh.s_gx[tid];
-      goal_y[e] = sh.s_gy[tid];
-      p.dist[e] = sh.s_old[tid];
-      p.total[e] = sh.s_total[tid];
-      p.acc[e] = 0.0;
-      p.ep_len[e] = 0;
+
+  if (!is_scalar && K > 0) {
+    T* stat_x = reinterpret_cast<T*>(p.stat_x);
+    T* stat_y = reinterpret_cast<T*>(p.stat_y);
+    T* dyn_x = reinterpret_cast<T*>(p.dyn_x);
+    T* dyn_y = reinterpret_cast<T*>(p.dyn_y);
+    // item = (resetting environment r, obstacle k): k fastest, padded to a power of two so that no division is needed
+    int kbits = 0;
+    while ((1 << kbits) < K) ++kbits;
+    const int items = sh.nreset << kbits;
+    for (int it = lt; it < items; it += kLaneThreads) {
+      const int k = it & ((1 << kbits) - 1);
+      if (k >= K) continue;
+      const int el = sh.rlist[it >> kbits];
+      const long long e = e0 + el;
+      const DrawCtx dc{&p, e, p.g0 + (uint32_t)e};
+      const uint32_t episode = sh.s_tick[el];
+      ResetHead<T> head;
+      head.gx = sh.s_gx[el];
+      head.gy = sh.s_gy[el];
+      head.ax = sh.ax[el];
+      head.ay = sh.ay[el];
+      head.dist = head.total = 0.0;
+      T x, y;
+      if (k < ks) {                                                                // :131-149
+        reset_static_draw<T>(p, dc, episode, k, head, x, y);
+        stat_x[e * p.stat_stride + k] = x;
+        stat_y[e * p.stat_stride + k] = y;
+      } else {                                                                     // :153-164
+        const int j = k - ks;
+        const uint2 w2 = dc.reset_dynamic(episode, j);
+        x = (T)__umulhi(w2.x, 500u);
+        y = (T)(20u + __umulhi(w2.y, 460u));
+        dyn_x[e * p.dyn_stride + j] = x;
+        dyn_y[e * p.dyn_stride + j] = y;
+        p.dyn_meta[e * p.dyn_stride + j] = (uint32_t)j;   // curr_goal = goal_list[j], curr_counter = 0
+      }
+      near_test<T, W>(sh, words, cfg, el, head.ax, head.ay, margin, x, y, k, false, want_obs, nb);
     }
   }
-  __syncthreads();   // sh.ax / sh.ay of the new episodes are published
+  __syncthreads();
   if (!is_scalar && want_obs) raster_list<T, W>(sh, words, cfg, lt, nb);
   __syncthreads();
 }
