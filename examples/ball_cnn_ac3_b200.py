@@ -50,8 +50,12 @@ def main():
     if args.resume:
         policy.load_state_dict(torch.load(args.resume, map_location=dev))
     t0 = time.time()
+    marks = {}
 
     def log(it, loss, batch):
+        if it == 4:          # steady state from here (the first iterations pay CUDA context / allocator warm-up)
+            torch.cuda.synchronize()
+            marks["t"] = time.time()
         if it % 10 == 0:
             st = env.stats()
             print("iter %4d  loss %12.3f  mean reward %+.5f  episodes %d  goals %d  hits %d  (%.1f s)" %
@@ -60,9 +64,11 @@ def main():
 
     train(env, policy, args.iterations, n_steps=args.steps, gamma=args.gamma, log=log)
     torch.cuda.synchronize()
-    n = args.envs * args.steps * args.iterations
-    print("%d env-steps in %.2f s = %.2f M env-steps/s (policy forward/backward included)" %
-          (n, time.time() - t0, n / (time.time() - t0) / 1e6))
+    if "t" in marks and args.iterations > 5:
+        n = args.envs * args.steps * (args.iterations - 5)
+        dt = time.time() - marks["t"]
+        print("steady state: %d env-steps in %.3f s = %.1f M env-steps/s (policy forward / backward / Adam included)" %
+              (n, dt, n / dt / 1e6))
 
 
 if __name__ == "__main__":

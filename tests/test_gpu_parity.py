@@ -507,3 +507,25 @@ def test_step_host_equals_step(obs_dtype):
         host_env.step_host(a.pin_memory(), obs, rew, done)
         assert torch.equal(o.cpu(), obs) and torch.equal(r.cpu(), rew) and torch.equal(d.cpu(), done.bool()), t
     assert host_env.error_flags() == 0
+
+
+@pytest.mark.gpu
+def test_state_snapshot_resumes_identically():
+    """Checkpoint / resume of the environment state: get_state() of a running env loaded into a
+    fresh env of the same seed with set_state() continues bit-identically, resets included."""
+    from gym_ballenv_b200 import BallVecEnv
+    n = 500
+    a = torch.randint(0, 9, (45, n), generator=torch.Generator().manual_seed(3)).cuda()
+    env = BallVecEnv(n, window=5, seed=12, max_episode_steps=13)
+    env.reset()
+    env.step_many(a[:15])
+    snap = env.get_state()
+    o1, r1, d1 = env.step_many(a[15:], keep_all_obs=True)
+    env2 = BallVecEnv(n, window=5, seed=12, max_episode_steps=13)
+    env2.reset()
+    env2.set_state(**snap)
+    o2, r2, d2 = env2.step_many(a[15:], keep_all_obs=True)
+    assert torch.equal(o1, o2) and torch.equal(r1, r2) and torch.equal(d1, d2)
+    s1, s2 = env.get_state(), env2.get_state()
+    for k in s1:
+        assert torch.equal(s1[k], s2[k]), k
