@@ -529,3 +529,34 @@ def test_state_snapshot_resumes_identically():
     s1, s2 = env.get_state(), env2.get_state()
     for k in s1:
         assert torch.equal(s1[k], s2[k]), k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("w", [1, 2, 3, 16, 31, 32])
+def test_extreme_window_sizes_against_the_oracle(w):
+    """WINDOW is a free parameter in the reference (5, 10, 21, 50 appear in its scripts); the kernel supports 1..32.
+    Small rollouts with auto-reset against the Python oracle, per-step launches and the rollout kernel."""
+    from gym_ballenv_b200 import BallVecEnv
+    from oracle import draws as D
+    from oracle.ballenv_oracle import OracleConfig, OracleVec
+    n, T, seed = 40, 12, 5
+    env = BallVecEnv(n, window=w, seed=seed, max_episode_steps=7)
+    vec = OracleVec(OracleConfig(window=w, max_episode_steps=7), D.PhiloxDraws(seed), n)
+    obs = env.reset()
+    vec.reset()
+    assert np.array_equal(obs.cpu().numpy(), np.array(vec.observe(), dtype=np.float32))
+    g = torch.Generator().manual_seed(w)
+    a = torch.randint(0, 9, (2 * T, n), generator=g)
+    for t in range(T):
+        obs, rew, done, _ = env.step(a[t].cuda())
+        r, d, f = vec.step(a[t].tolist())
+        assert np.array_equal(obs.cpu().numpy(), np.array(vec.observe(), dtype=np.float32)), t
+        assert np.array_equal(done.cpu().numpy(), np.array(d)), t
+    obs, rew, done = env.step_many(a[T:].cuda(), keep_all_obs=True)
+    for t in range(T):
+        r, d, f = vec.step(a[T + t].tolist())
+        assert np.array_equal(obs[t].cpu().numpy(), np.array(vec.observe(), dtype=np.float32)), t
+        assert np.array_equal(done[t].cpu().numpy(), np.array(d)), t
+    assert env.error_flags() == 0
+    with pytest.raises(Exception):
+        BallVecEnv(4, window=33)
