@@ -182,8 +182,13 @@ int ballenv_step(BallenvHandle *h, const void *actions, int action_kind, void *o
                  uint8_t *done_out, ballenv_stream_t stream);
 
 /*
- * T consecutive steps in one call (synthetic rollouts).  actions [T][n], reward_out [T][n], done_out [T][n];
+ * T consecutive steps in one call (open-loop rollouts: the actions of all T steps are known up front, i.e. the loop
+ * of examples/ball_cnn_ac3.py:553-613 with pre-sampled actions).  actions [T][n], reward_out [T][n], done_out [T][n];
  * obs_out [T][n][row] if obs_all_steps != 0, else [n][row] holding the last step's observation.
+ * With the production configuration (BALLENV_F32, gym ruleset, Philox draws, index actions, BALLENV_OBS_F32 rows)
+ * this is ONE launch: every block keeps its environments on chip for all T steps, so only actions, observations,
+ * rewards and dones touch device memory inside the loop.  Otherwise it is T launches of ballenv_step.  Results are
+ * identical either way (tests/test_gpu_parity.py::test_rollout_kernel_matches_per_step_launches).
  */
 int ballenv_step_many(BallenvHandle *h, const void *actions, int action_kind, int32_t n_steps, void *obs_out,
                       int32_t obs_all_steps, void *reward_out, uint8_t *done_out, ballenv_stream_t stream);
