@@ -15,7 +15,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from gym_ballenv_b200 import BallVecEnv, EnvConfig          # noqa: E402
-from gym_ballenv_b200.a2c import Policy, train               # noqa: E402
+from gym_ballenv_b200.a2c import Policy, train, train_graphed   # noqa: E402
 
 
 def read_arguments():
@@ -38,6 +38,7 @@ def read_arguments():
     p.add_argument('--envs', type=int, default=16384)
     p.add_argument('--steps', type=int, default=32, help='steps per update')
     p.add_argument('--iterations', type=int, default=50)
+    p.add_argument('--graph', type=int, default=1, help='replay the rollout as one CUDA graph')
     return p.parse_args()
 
 
@@ -62,7 +63,10 @@ def main():
                   (it, float(loss.detach()), float(batch["reward"].mean()), st["episodes"], st["goals"],
                    st["hits_static"] + st["hits_dynamic"], time.time() - t0))
 
-    train(env, policy, args.iterations, n_steps=args.steps, gamma=args.gamma, log=log)
+    if args.graph:
+        train_graphed(env, policy, args.iterations, n_steps=args.steps, gamma=args.gamma, log=log)
+    else:
+        train(env, policy, args.iterations, n_steps=args.steps, gamma=args.gamma, log=log)
     torch.cuda.synchronize()
     if "t" in marks and args.iterations > 5:
         n = args.envs * args.steps * (args.iterations - 5)

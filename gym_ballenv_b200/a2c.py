@@ -69,6 +69,86 @@ def rollout(env: BallVecEnv, policy: Policy, n_steps: int, obs: Optional[torch.T
                 done=torch.stack(dones), action=torch.stack(actions))
 
 
+class GraphedRollout:
+    """The whole T-step policy-in-the-loop rollout as ONE CUDA graph.
+
+    The per-step work of the reference loop (examples/ball_cnn_ac3.py:553-613) is a dozen tiny kernels (the MLP,
+    softmax, sampling, the fused environment step); launched one by one they are launch-bound.  Here the T steps -
+    policy forward, ``multinomial`` sampling and ``ballenv_step`` writing into fixed buffers - are captured once and
+    replayed, so the GPU runs them back to back.  The rollout is recorded without autograd; ``evaluate`` recomputes
+    log-probabilities and values of the stored (observation, action) pairs in one batched forward pass for the
+    update (same numbers as the step-by-step values, since the weights do not change inside a rollout).
+    """
+
+    def __init__(self, env: BallVecEnv, policy: Policy, n_steps: int, greedy: bool = False):
+        self.env, self.policy, self.n_steps, self.greedy = env, policy, n_steps, greedy
+        n, row, dev = env.num_envs, env.obs_row, env.device
+        self.obs = torch.zeros((n_steps + 1, n, row), dtype=torch.float32, device=dev)   # obs[t] is what step t sees
+        self.action = torch.zeros((n_steps, n), dtype=torch.int64, device=dev)
+        self.reward = torch.zeros((n_steps, n), dtype=torch.float32, device=dev)
+        self.done = torch.zeros((n_steps, n), dtype=torch.uint8, device=dev)
+        self.graph = None
+
+    def _body(self):
+        for t in range(self.n_steps):
+            probs, _ = self.policy(self.obs[t])
+            a = probs.argmax(dim=-1) if self.greedy else torch.multinomial(probs, 1).squeeze(-1)
+            self.action[t].copy_(a)
+            self.env.step_into(self.action[t], self.obs[t + 1], self.reward[t], self.done[t])
+
+    @torch.no_grad()
+    def run(self, first_obs: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        """One rollout.  ``first_obs`` defaults to the last observation of the previous rollout (or the current
+        observation of the environment on the first call)."""
+        if first_obs is None:
+            first_obs = self.obs[self.n_steps].clone() if self.graph is not None else self.env.observe()
+        self.obs[0].copy_(first_obs)
+        if self.graph is None:
+            side = torch.cuda.Stream(device=self.env.device)
+            side.wait_stream(torch.cuda.current_stream(self.env.device))
+            with torch.cuda.stream(side):          # warm-up on a side stream, as graph capture requires
+                self._body()
+            torch.cuda.current_stream(self.env.device).wait_stream(side)
+            self.obs[0].copy_(first_obs)           # the warm-up advanced the environments for real: keep that rollout
+            out_first = dict(obs=self.obs.clone(), action=self.action.clone(), reward=self.reward.clone(),
+                             done=self.done.clone().bool())
+            self.graph = torch.cuda.CUDAGraph()
+            self.obs[0].copy_(self.obs[self.n_steps])
+            with torch.cuda.graph(self.graph):
+                self._body()
+            # the capture itself does not execute anything; hand back the warm-up rollout this time
+            return out_first
+        self.graph.replay()
+        return dict(obs=self.obs, action=self.action, reward=self.reward, done=self.done.bool())
+
+    def evaluate(self, batch: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        """log-probabilities and values of the stored pairs, with autograd, in one batched forward pass."""
+        T, n = batch["action"].shape
+        probs, value = self.policy(batch["obs"][:T].reshape(T * n, -1))
+        logp = torch.log(probs.gather(-1, batch["action"].reshape(-1, 1)).squeeze(-1)).view(T, n)
+        return dict(log_prob=logp, value=value.view(T, n), reward=batch["reward"], done=batch["done"])
+
+
+def train_graphed(env: BallVecEnv, policy: Policy, iterations: int, n_steps: int = 32, gamma: float = 0.99,
+                  lr: float = 1e-3, log=None):
+    """train() with the rollout replayed as a CUDA graph and the update computed from one batched forward pass."""
+    opt = torch.optim.Adam(policy.parameters(), lr=lr)
+    env.reset()
+    roll = GraphedRollout(env, policy, n_steps)
+    for it in range(iterations):
+        raw = roll.run()
+        batch = roll.evaluate(raw)
+        with torch.no_grad():
+            _, v_last = policy(raw["obs"][n_steps])
+        loss = a2c_loss(batch, gamma, bootstrap=v_last.squeeze(-1))
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        if log is not None:
+            log(it, loss, batch)
+    return policy
+
+
 def discounted_returns(reward: torch.Tensor, done: torch.Tensor, gamma: float, bootstrap: Optional[torch.Tensor] = None):
     """R_t = r_t + gamma * R_{t+1}, restarted where an episode ended (examples/ball_cnn_ac3.py:228-230, per env)."""
     T = reward.shape[0]

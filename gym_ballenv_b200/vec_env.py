@@ -191,6 +191,18 @@ class BallVecEnv:
         info = {"flags": self.state_views["flags"], "state": self.state_views}
         return buf["obs"], buf["reward"], buf["done"].view(torch.bool), info
 
+    def step_into(self, actions: torch.Tensor, obs_out: torch.Tensor, reward_out: torch.Tensor, done_out: torch.Tensor):
+        """step() writing into caller-owned device tensors (obs [N, row], reward [N], done [N] uint8): fixed
+        addresses, which is what CUDA-graph capture of a policy-in-the-loop rollout needs."""
+        kind = self._action_kind(actions, self.num_envs)
+        if (actions.device != self.device or not actions.is_contiguous() or tuple(obs_out.shape) != (self.num_envs, self.obs_row)
+                or obs_out.dtype != self._bufs[0]["obs"].dtype or reward_out.dtype != self._real
+                or done_out.dtype != torch.uint8 or reward_out.numel() != self.num_envs or done_out.numel() != self.num_envs
+                or not (obs_out.is_contiguous() and reward_out.is_contiguous() and done_out.is_contiguous())):
+            raise ValueError("step_into needs contiguous device tensors of the shapes / dtypes step() returns")
+        check(LIB.ballenv_step(self._h, C.c_void_p(actions.data_ptr()), kind, C.c_void_p(obs_out.data_ptr()),
+                               C.c_void_p(reward_out.data_ptr()), C.c_void_p(done_out.data_ptr()), self._stream()))
+
     def alloc_rollout(self, T: int, keep_all_obs: bool = False):
         """Rollout buffers for step_many(out=...): (obs [T, N, row] or [N, row], reward [T, N], done [T, N] uint8)."""
         n = self.num_envs

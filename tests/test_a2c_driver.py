@@ -67,3 +67,44 @@ def test_train_loop_runs_and_updates_the_policy():
     assert len(losses) == 3 and all(np.isfinite(losses))
     assert not torch.equal(before, policy.fc1.weight.detach())
     assert env.stats()["steps"] == 16384 * 16 * 3 and env.error_flags() == 0
+
+
+@pytest.mark.gpu
+def test_graphed_rollout_equals_the_eager_loop():
+    """The T-step rollout replayed as one CUDA graph (greedy actions, so both sides are deterministic) visits the same
+    observations, actions, rewards and dones as the step-by-step loop, over several replays with resets."""
+    from gym_ballenv_b200 import BallVecEnv
+    from gym_ballenv_b200.a2c import GraphedRollout, Policy, rollout
+    torch.manual_seed(3)
+    policy = Policy(5).cuda()
+    n, T = 4096, 16
+    e1 = BallVecEnv(n, window=5, seed=9, max_episode_steps=11)
+    e2 = BallVecEnv(n, window=5, seed=9, max_episode_steps=11)
+    e1.reset()
+    obs2 = e2.reset().clone()
+    g = GraphedRollout(e1, policy, T, greedy=True)
+    with torch.no_grad():
+        for it in range(4):
+            raw = g.run()
+            ref = rollout(e2, policy, T, obs=obs2, greedy=True)
+            obs2 = ref["obs"].clone()
+            assert torch.equal(raw["action"], ref["action"]), it
+            assert torch.equal(raw["reward"], ref["reward"]) and torch.equal(raw["done"], ref["done"]), it
+            assert torch.equal(raw["obs"][T], ref["obs"]), it
+    ev = g.evaluate(raw)
+    assert ev["log_prob"].requires_grad and ev["value"].shape == (T, n)
+    assert e1.stats() == e2.stats() or abs(e1.stats()["return_sum"] - e2.stats()["return_sum"]) < 1e-6 * abs(e2.stats()["return_sum"])
+
+
+@pytest.mark.gpu
+def test_graphed_training_runs():
+    from gym_ballenv_b200 import BallVecEnv
+    from gym_ballenv_b200.a2c import Policy, train_graphed
+    torch.manual_seed(1)
+    env = BallVecEnv(8192, window=5, seed=3)
+    policy = Policy(5).cuda()
+    before = policy.fc1.weight.detach().clone()
+    losses = []
+    train_graphed(env, policy, iterations=4, n_steps=8, log=lambda it, loss, batch: losses.append(float(loss.detach())))
+    assert len(losses) == 4 and all(np.isfinite(losses)) and not torch.equal(before, policy.fc1.weight.detach())
+    assert env.stats()["steps"] == 8192 * 8 * 4 and env.error_flags() == 0
