@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libballenv_b200.so")
+LIB_PATH = os.environ.get("BALLENV_LIB_PATH") or os.path.join(HERE, "libballenv_b200.so")   # override: A/B experiments
 
 ABI_VERSION = 3
 MAX_DYNAMIC = 64

@@ -15,11 +15,13 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(CSRC, "_obj")
-LIB = os.path.join(HERE, "libballenv_b200.so")
+OBJ = os.path.join(CSRC, "_obj" + os.environ.get("BALLENV_OBJ_SUFFIX", ""))
+LIB = os.path.join(HERE, os.environ.get("BALLENV_LIB_NAME", "libballenv_b200.so"))   # A/B experiments: other name
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+if os.environ.get("BALLENV_EXTRA_DEFS"):   # A/B experiments: e.g. "-DBALLENV_EXP_FOO=1"
+    FLAGS.extend(os.environ["BALLENV_EXTRA_DEFS"].split())
 if os.environ.get("BALLENV_MINBLOCKS"):   # tuning experiments: resident blocks per SM the kernels are compiled for
     FLAGS.append("-DBALLENV_MINBLOCKS=" + os.environ["BALLENV_MINBLOCKS"])
 

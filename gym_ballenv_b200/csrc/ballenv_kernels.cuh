@@ -493,7 +493,7 @@ __device__ __forceinline__ void move_obstacle(const DevConfig& cfg, const typena
 
 // Hot-path form of move_obstacle for distinct goals: select instead of branch; x + m * s as one FMA, which
 // rounds like r_add(x, r_mul(m, s)) because m is -1, 0 or 1 and the product is therefore exact.
-template <typename T, int W>
+template <typename T, int W, bool kSelects = false>
 __device__ __forceinline__ void move_lean(const DevConfig& cfg, const BlockShared<T, W>& sh, int j, uint32_t w1,
                                           uint32_t w2, T& x, T& y, uint32_t& meta) {
   const uint32_t gi = meta & 0xffu;
@@ -508,7 +508,15 @@ __device__ __forceinline__ void move_lean(const DevConfig& cfg, const BlockShare
     mx = tx > (T)0 ? (T)1 : (T)-1;
     my = ty > (T)0 ? (T)1 : (T)-1;
   }
-  if ((int)(meta >> 8) < cfg.change_step) {                            // :327
+  if constexpr (kSelects) {
+    // selects only: measured faster when the quad is partly filled (the per-slot bound tests already branch)
+    const bool moving = (int)(meta >> 8) < cfg.change_step;            // :327
+    const T s = moving ? CfgV<T>::speed(cfg, j) : (T)0;                // x + m * 0 == x exactly (m is -1, 0 or 1)
+    x = fma(mx, s, x);
+    y = fma(my, s, y);
+    const uint32_t m = __umulhi(w1, (uint32_t)(cfg.n_goals - 1));      // :349-353 pick another goal, do not move
+    meta = moving ? meta + 256u : m + (m >= gi ? 1u : 0u);             // :348 / :352-353
+  } else if ((int)(meta >> 8) < cfg.change_step) {                     // :327
     const T s = CfgV<T>::speed(cfg, j);
     x = fma(mx, s, x);
     y = fma(my, s, y);
@@ -599,7 +607,8 @@ __device__ __forceinline__ void dynamic_move(const Params& p, const BlockShared<
     const int j = 4 * jq + i;
     if (kFast) {
       const uint32_t w1 = pick_word(blk, i);
-      if (kFull || j < cfg.kd) move_lean<T, W>(cfg, sh, j, w1, w1 * 100u, x[i], y[i], meta[i]);
+      if (kFull) move_lean<T, W, false>(cfg, sh, j, w1, w1 * 100u, x[i], y[i], meta[i]);
+      else if (j < cfg.kd) move_lean<T, W, true>(cfg, sh, j, w1, w1 * 100u, x[i], y[i], meta[i]);
     } else if (j < cfg.kd) {
       uint32_t w1 = pick_word(blk, i), w2 = w1 * 100u;   // second draw: unused low half of w1 * 100
       if (has_tape) {
