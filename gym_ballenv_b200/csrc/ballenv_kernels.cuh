@@ -102,7 +102,10 @@ struct Params {
   int mode, action_kind;
   int n_steps;        // steps advanced by this launch (rollout loop; > 1 only with the fast specialisation)
   int obs_all_steps;  // rollout: observation rows of every step ([T][n][row]) or only of the last one ([n][row])
-  int debug;   // BALLENV_DEBUG_SKIP (profiling experiments only): 1 exit, 2 no moves, 4 no near tests, 8 no store, 16 no fp64
+  // BALLENV_DEBUG_SKIP (profiling experiments, tools/skip_experiment.py): 1 exit, 2 no moves, 4 no near tests,
+  // 8 no store, 16 no fp64.  Compiling the tests of this word out was measured SLOWER (tools/ab.sh: 10.7 -> 11.4 us
+  // per step for C3 - a different ptxas schedule), so they stay in; the word is 0 unless the variable is set.
+  int debug;
   void *agent_x, *agent_y, *goal_x, *goal_y;
   double *dist, *total, *acc;
   int *ep_len;
