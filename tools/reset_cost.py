@@ -6,7 +6,7 @@ import bench
 from gym_ballenv_b200 import BallVecEnv
 T, n = 200, 65536
 spec = bench.workload_spec("c3")
-for limit in (0, 1000, 50):
+for limit in (0, 1000, 200, 50, 10):
     os.environ["BALLENV_DEBUG_SKIP"] = os.environ.get("SKIP", "0")
     env = BallVecEnv(n, window=10, config=bench.env_config(spec), seed=0, device="cuda:0", max_episode_steps=limit)
     env.reset()
