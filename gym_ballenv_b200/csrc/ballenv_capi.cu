@@ -200,7 +200,12 @@ bool fast_eligible(const BallenvHandle* h, const Params& p) {
          !h->force_generic;
 }
 
-int launch(BallenvHandle* h, const Params& p, cudaStream_t s) {
+int launch(BallenvHandle* h, const Params& p_in, cudaStream_t s) {
+  Params p = p_in;   // + the constants the kernels would otherwise derive per step
+  p.obs_row_bytes = (long long)p.cfg.obs_row_elems * (p.cfg.obs_format == BALLENV_OBS_U8 ? 1 : 4);
+  p.obs_step_bytes = (p.n_steps > 1 && p.obs_all_steps) ? p.n * p.obs_row_bytes : 0;
+  p.n_stat = kEnvsPerBlock * ((p.cfg.ks + 3) / 4);
+  p.n_slot = p.n_stat + kEnvsPerBlock * ((p.cfg.kd + 3) / 4);
   const unsigned grid = (unsigned)((p.n + kEnvsPerBlock - 1) / kEnvsPerBlock);
   const bool f64 = h->cfg.precision == BALLENV_F64;
   const bool fast = fast_eligible(h, p);

@@ -106,6 +106,10 @@ struct Params {
   // 8 no store, 16 no fp64.  Compiling the tests of this word out was measured SLOWER (tools/ab.sh: 10.7 -> 11.4 us
   // per step for C3 - a different ptxas schedule), so they stay in; the word is 0 unless the variable is set.
   int debug;
+  // derived per launch by the host (ballenv_capi.cu: launch) so that the step loop re-reads one constant instead of
+  // recomputing it when registers are short
+  long long obs_row_bytes, obs_step_bytes;   // bytes of one observation row; of one step's rows ([T][n][row]) or 0
+  int n_stat, n_slot;                        // static / all quad slots of a block (32 environments)
   void *agent_x, *agent_y, *goal_x, *goal_y;
   double *dist, *total, *acc;
   int *ep_len;
@@ -541,10 +545,49 @@ __device__ __forceinline__ uint32_t stream_bits(const uint32_t* words, int bit, 
   return __funnelshift_r(lo, hi, sh);
 }
 
+// kThreads storing threads, a multiple of 8: thread tid always expands nibble (tid & 7) of the words tid / 8 +
+// k * kThreads / 8, so the shift is loop-invariant: rotate the nibble to bits 4..7 (= its byte offset in the
+// table), mask, load the float4, store.  A full block (32 environments) of a compile-time window unrolls completely.
+template <int W, int kThreads>
+__device__ __forceinline__ void store_rows_f32(float4* dst, const uint32_t* words, const float4* lut, int nvec,
+                                               int tid) {
+  static_assert(kThreads % 8 == 0, "the nibble a thread expands must not depend on the iteration");
+  const uint32_t rot = (((uint32_t)tid & 7u) * 4u + 28u) & 31u;
+  const uint32_t* wp = words + (tid >> 3);
+  const char* lutb = reinterpret_cast<const char*>(lut);
+  float4* d = dst + tid;
+  constexpr int kFullVec = W > 0 ? 8 * (4 + W * W) : 0;
+  if (W > 0 && nvec == kFullVec) {
+    constexpr int kIter = kFullVec / kThreads, kTail = kFullVec % kThreads;
+#pragma unroll
+    for (int k = 0; k < kIter; ++k) {
+      const uint32_t wd = wp[k * (kThreads / 8)];
+      __stcs(d + k * kThreads, *reinterpret_cast<const float4*>(lutb + (__funnelshift_r(wd, wd, rot) & 0xf0u)));
+    }
+    if (kTail != 0 && tid < kTail) {
+      const uint32_t wd = wp[kIter * (kThreads / 8)];
+      __stcs(d + kIter * kThreads, *reinterpret_cast<const float4*>(lutb + (__funnelshift_r(wd, wd, rot) & 0xf0u)));
+    }
+  } else {
+    for (int v = tid; v < nvec; v += kThreads, wp += kThreads / 8, d += kThreads) {
+      const uint32_t wd = *wp;
+      __stcs(d, *reinterpret_cast<const float4*>(lutb + (__funnelshift_r(wd, wd, rot) & 0xf0u)));
+    }
+  }
+}
+
+// Measured (tools/ab3.sh): the specialised store gains 4 % for WINDOW = 10 rows (13 stores per thread with 64
+// threads) and loses 3 % for WINDOW = 5 (2 per thread) - used from three stores per thread on.
+template <int W, int kThreads>
+__device__ __forceinline__ constexpr bool row_store_pays() {
+  return W == 0 || 8 * (4 + W * W) >= 3 * kThreads;
+}
+
 // blk points at the block's span of the step's output (environment e0, element 0).
 // tid / nthreads: the caller's index among the threads that share the store (the obstacle threads in the step
 // loop - the scalar warp is the critical path of a step and stays out of it; everybody after a reset).
-template <int W, bool kFast>
+// kHot: the call of the step loop (the specialised row store pays there); the stores after a reset stay generic.
+template <int W, bool kFast, bool kHot = false>
 __device__ __forceinline__ void store_obs(const Params& p, void* blk, const uint32_t* words, const float4* lut, int cnt,
                                           int tid, int nthreads) {
   const int w = Win<W>::w(p.cfg.window);
@@ -554,6 +597,11 @@ __device__ __forceinline__ void store_obs(const Params& p, void* blk, const uint
     // 16-byte alignment holds unless a [T][n][row] rollout buffer has n * row not a multiple of 4 elements
     const int nvec = (reinterpret_cast<uintptr_t>(blk) & 15) == 0 ? total >> 2 : 0;
     float4* dst = reinterpret_cast<float4*>(blk);
+    if (kHot && nthreads == 64 && row_store_pays<W, 64>()) store_rows_f32<W, 64>(dst, words, lut, nvec, tid);
+    else if (kHot && nthreads == 128 && row_store_pays<W, 128>()) store_rows_f32<W, 128>(dst, words, lut, nvec, tid);
+    else if (kHot && nthreads == kLaneThreads && row_store_pays<W, kLaneThreads>())
+      store_rows_f32<W, kLaneThreads>(dst, words, lut, nvec, tid);
+    else
     for (int v = tid; v < nvec; v += nthreads)   // streaming store: the rollout buffer is not re-read by this kernel
       __stcs(dst + v, lut[(words[v >> 3] >> ((v & 7) << 2)) & 15u]);
     for (int f = (nvec << 2) + tid; f < total; f += nthreads)   // odd tail of the last block / unaligned span
@@ -605,6 +653,30 @@ __device__ __forceinline__ void dynamic_move(const Params& p, const BlockShared<
   const bool has_tape = !kFast && p.step_tape != nullptr;
   uint4 blk = make_uint4(0, 0, 0, 0);
   if (!has_tape) blk = philox4x32_10(p.g0 + (uint32_t)e, tick, (uint32_t)jq, kStreamStep, p.k0, p.k1);
+  if (kFast && kFull) {
+    // The step counters of an environment's obstacles run in lockstep (all start at 0 with the episode, all pick a
+    // new goal on the same step), so the quad almost always moves as a whole: one branch for it instead of four,
+    // and four independent chains inside.  meta = goal | count << 8, so count < change_step <=> meta < change_step << 8.
+    const uint32_t lim = (uint32_t)cfg.change_step << 8;
+    const uint32_t top = max(max(meta[0], meta[1]), max(meta[2], meta[3]));
+    if (top < lim) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t w1 = pick_word(blk, i);
+        const typename Vec2<T>::type gl = sh.goal[meta[i] & 0xffu];
+        const T tx = r_sub(gl.x, x[i]), ty = r_sub(gl.y, y[i]);
+        const bool diag = tx != (T)0 && ty != (T)0;
+        const bool seek = diag && (int)__umulhi(w1, 100u) < cfg.rd_th;
+        const typename Vec2<T>::type mv = sh.mv[__umulhi(diag ? w1 * 100u : w1, 9u)];
+        const T mx = seek ? (tx > (T)0 ? (T)1 : (T)-1) : mv.x, my = seek ? (ty > (T)0 ? (T)1 : (T)-1) : mv.y;
+        const T s = CfgV<T>::speed(cfg, 4 * jq + i);
+        x[i] = fma(mx, s, x[i]);
+        y[i] = fma(my, s, y[i]);
+        meta[i] += 256u;
+      }
+      return;
+    }
+  }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int j = 4 * jq + i;
@@ -810,6 +882,14 @@ __device__ __forceinline__ bool bar_or(int id, bool pred) {
 // index actions, fp32 observation rows requested.  Every uniform test of the generic kernel folds away; the host
 // (ballenv_capi.cu) selects it when all of that holds.
 // kRollout: p.n_steps may exceed 1 (ballenv_step_many); otherwise the step loop has exactly one trip and folds away.
+// Address of the block's observation rows of step t: (rows of step t) + (rows of the environments before e0).
+// Computed where a store needs it, so the step loop carries no pointer.
+template <bool kRollout>
+__device__ __forceinline__ char* obs_block(const Params& p, long long e0, int t) {
+  return reinterpret_cast<char*>(p.obs) +
+         ((size_t)(kRollout ? t : 0) * (size_t)p.obs_step_bytes + (size_t)e0 * (size_t)p.obs_row_bytes);
+}
+
 template <typename T, int W, bool kFast, bool kRollout>
 __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __grid_constant__ Params p) {
   __shared__ BlockShared<T, W> sh;
@@ -822,10 +902,6 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
   const int ks = cfg.ks, kd = cfg.kd;
   const bool stepping = kFast || p.mode == kModeStep;
   const int n_steps = kRollout ? p.n_steps : 1;
-  // the block's span of the observation output: [e0 .. e0 + 32) x row, advanced by one step's rows per iteration
-  const size_t obs_row_bytes = (size_t)cfg.obs_row_elems * (cfg.obs_format == BALLENV_OBS_U8 ? 1u : 4u);
-  const size_t obs_step_bytes = (kRollout && p.obs_all_steps) ? (size_t)p.n * obs_row_bytes : 0;
-  char* obs_blk = reinterpret_cast<char*>(p.obs) + (size_t)e0 * obs_row_bytes;
   if (p.debug & 1) return;
 
   if (tid < 32) {
@@ -912,7 +988,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
         out_pending = false;
       };
       // ------------------------------------------- hot loop: no calls inside -------------------------------------
-      for (; t < n_steps; ++t, obs_blk += obs_step_bytes) {
+      for (; t < n_steps; ++t) {
         const bool want_obs = kFast ? (p.obs_all_steps != 0 || t == n_steps - 1) : p.obs != nullptr;
         uint32_t* words = sh.words[t & 1];
         const long long et = (long long)t * p.n + e;   // index of this environment in the [T][n] arrays
@@ -1075,9 +1151,8 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
         uint32_t* words = sh.words[t & 1];
         reset_stage<T, W>(p, sh, words, e0, cnt_env, want_obs);
         if (want_obs && !(p.debug & 8))
-          store_obs<W, kFast>(p, obs_blk, words, sh.lut, cnt_env, tid, kBlock);
+          store_obs<W, kFast>(p, obs_block<kRollout>(p, e0, t), words, sh.lut, cnt_env, tid, kBlock);
         reset_req = false;
-        obs_blk += obs_step_bytes;
         if (++t >= n_steps) break;
       }
     }
@@ -1086,7 +1161,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
     // =============================== obstacle threads: one quad per thread per iteration =========================
     const int lt = tid - 32;
     const int qs = (ks + 3) >> 2, qd = (kd + 3) >> 2;         // static / dynamic quads per environment
-    const int n_stat = kEnvsPerBlock * qs, n_slot = kEnvsPerBlock * (qs + qd);
+    const int n_stat = p.n_stat, n_slot = p.n_slot;   // kEnvsPerBlock * qs, kEnvsPerBlock * (qs + qd)
     const T margin = CfgV<T>::margin(cfg);
     // element offsets of the block's obstacle slices (n * K fits 31 bits, checked at create time)
     const uint32_t stat0 = (uint32_t)e0 * (uint32_t)p.stat_stride, dyn0 = (uint32_t)e0 * (uint32_t)p.dyn_stride;
@@ -1142,7 +1217,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
       }
       bool pending_reset = false;
       // ------------------------------------------- hot loop: no calls inside -------------------------------------
-      for (; t < n_steps; ++t, obs_blk += obs_step_bytes) {
+      for (; t < n_steps; ++t) {
         const bool want_obs = kFast ? (p.obs_all_steps != 0 || t == n_steps - 1) : p.obs != nullptr;
         uint32_t* words = sh.words[t & 1];
         // obstacle motion does not depend on the agent: draw and move while the scalar warp works
@@ -1210,8 +1285,10 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
         // The observation rows are stored by the threads that have the least to do in a step: the static-quad
         // threads (no draws, no moves) when there are at least two warps of them, otherwise every obstacle thread.
         if (want_obs && !(p.debug & 8)) {
-          if (n_store == kLaneThreads) store_obs<W, kFast>(p, obs_blk, words, sh.lut, cnt_env, lt, kLaneThreads);
-          else if (lt < n_store) store_obs<W, kFast>(p, obs_blk, words, sh.lut, cnt_env, lt, n_store);
+          if (n_store == kLaneThreads)
+            store_obs<W, kFast, true>(p, obs_block<kRollout>(p, e0, t), words, sh.lut, cnt_env, lt, kLaneThreads);
+          else if (lt < n_store)
+            store_obs<W, kFast, true>(p, obs_block<kRollout>(p, e0, t), words, sh.lut, cnt_env, lt, n_store);
         }
       }
 
@@ -1223,9 +1300,8 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
         uint32_t* words = sh.words[t & 1];
         reset_stage<T, W>(p, sh, words, e0, cnt_env, want_obs);
         if (want_obs && !(p.debug & 8))
-          store_obs<W, kFast>(p, obs_blk, words, sh.lut, cnt_env, tid, kBlock);
+          store_obs<W, kFast>(p, obs_block<kRollout>(p, e0, t), words, sh.lut, cnt_env, tid, kBlock);
         if (!kFast && lt < n_slot) q_have = q_el < cnt_env;   // Reset mode: the environment has state now
-        obs_blk += obs_step_bytes;
         if (++t >= n_steps) break;
       }
     }

@@ -5,9 +5,10 @@ import torch
 import bench
 from gym_ballenv_b200 import BallVecEnv
 T = int(os.environ.get("T", "200"))
+NS = [int(x) for x in os.environ.get("NS", "65536,262144").split(",")]
 for wl in ("c3", "w5"):
     spec = bench.workload_spec(wl)
-    for n in (65536, 262144):
+    for n in NS:
         for mode in ("rollout", "per-step"):
             os.environ["BALLENV_NO_ROLLOUT"] = "1" if mode == "per-step" else "0"
             env = BallVecEnv(n, window=spec["window"], config=bench.env_config(spec), seed=0, device="cuda:0")
