@@ -141,6 +141,15 @@ __device__ __forceinline__ double r_sub(double a, double b) { return __dsub_rn(a
 __device__ __forceinline__ float r_abs(float a) { return fabsf(a); }
 __device__ __forceinline__ double r_abs(double a) { return fabs(a); }
 
+// num / den, bit for bit.  A zero numerator is common (the agent did not change its distance to the goal: action
+// (0, 0), or pinned at a wall) and sends the lane - and with it the scalar warp, the longest dependency chain of a
+// step - through the slow path of the fp64 division; (+-0) / den is +-0 for den > 0, so those lanes divide 1 instead.
+__device__ __forceinline__ double div64(double num, double den) {
+  const bool zero = num == 0.0 && den > 0.0;
+  const double q = (zero ? 1.0 : num) / den;
+  return zero ? num : q;
+}
+
 __device__ __forceinline__ double dist64(double ax, double ay, double bx, double by) {
   const double dx = __dsub_rn(ax, bx), dy = __dsub_rn(ay, by);
   return sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
@@ -252,7 +261,10 @@ struct BlockShared {
   // observation bits of the block as ONE stream: environment el owns bits [el * nb, (el + 1) * nb), nb = 4 + W*W
   // (4 goal-quadrant bits, then the W*W cells), so output element f of the block's span is bit f.
   uint32_t words[2][Win<W>::kBlockWords];           // double-buffered by step parity (see the rollout loop)
-  T ax[kEnvsPerBlock], ay[kEnvsPerBlock];            // agent position the window is centred on
+  // agent position the window is centred on, double-buffered by step parity: the scalar warp runs ahead and
+  // publishes the positions of step t + 1 while obstacle threads may still raster step t
+  T ax[2][kEnvsPerBlock], ay[2][kEnvsPerBlock];
+  int any_reset;                                     // scalar warp -> obstacle threads: an environment of the block resets
   int hit[kEnvsPerBlock];                            // list index of the first obstacle hit, or kNoHit
   int reset[kEnvsPerBlock];
   T near_x[kListCap], near_y[kListCap];              // near-obstacle list
@@ -303,7 +315,7 @@ __device__ __forceinline__ void near_test(BlockShared<T, W>& sh, uint32_t* words
 // Obstacle threads (lt = 0 .. kLaneThreads-1): rasterise the queued (obstacle, row) items.
 template <typename T, int W>
 __device__ __forceinline__ void raster_list(BlockShared<T, W>& sh, uint32_t* words, const DevConfig& cfg, int lt,
-                                            int nb) {
+                                            int nb, int par) {
   const int cnt = sh.count < kListCap ? sh.count : kListCap;
   if (cnt == 0) return;
   const Overlap<T> ov(cfg.radius_sum);
@@ -314,7 +326,7 @@ __device__ __forceinline__ void raster_list(BlockShared<T, W>& sh, uint32_t* wor
   for (int it = lt; it < items; it += kLaneThreads) {
     const int en = it / nyi, yi = it - en * nyi;
     const int el = sh.near_env[en];
-    raster_item<T, W>(words, el * nb, sh.near_x[en], sh.near_y[en], sh.ax[el], sh.ay[el], step_x, step_y, yi, w, ov);
+    raster_item<T, W>(words, el * nb, sh.near_x[en], sh.near_y[en], sh.ax[par][el], sh.ay[par][el], step_x, step_y, yi, w, ov);
   }
 }
 
@@ -724,7 +736,7 @@ __device__ __forceinline__ int div_slot(int slot, uint32_t rcp) {
 // The observation of a finished environment thereby becomes the first observation of its next episode.
 template <typename T, int W>
 __device__ __noinline__ void reset_stage(const Params& p, BlockShared<T, W>& sh, uint32_t* words, long long e0,
-                                         int cnt_env, bool want_obs) {
+                                         int cnt_env, bool want_obs, int par) {
   const DevConfig& cfg = p.cfg;
   const int tid = threadIdx.x;
   const bool is_scalar = tid < 32;
@@ -757,8 +769,8 @@ __device__ __noinline__ void reset_stage(const Params& p, BlockShared<T, W>& sh,
       sh.s_gx[tid] = head.gx;
       sh.s_gy[tid] = head.gy;
       sh.s_tick[tid] = episode;
-      sh.ax[tid] = head.ax;
-      sh.ay[tid] = head.ay;
+      sh.ax[par][tid] = head.ax;
+      sh.ay[par][tid] = head.ay;
       p.episode[e] = episode;
       reinterpret_cast<T*>(p.agent_x)[e] = head.ax;
       reinterpret_cast<T*>(p.agent_y)[e] = head.ay;
@@ -796,8 +808,8 @@ __device__ __noinline__ void reset_stage(const Params& p, BlockShared<T, W>& sh,
       ResetHead<T> head;
       head.gx = sh.s_gx[el];
       head.gy = sh.s_gy[el];
-      head.ax = sh.ax[el];
-      head.ay = sh.ay[el];
+      head.ax = sh.ax[par][el];
+      head.ay = sh.ay[par][el];
       head.dist = head.total = 0.0;
       T x, y;
       if (k < ks) {                                                                // :131-149
@@ -817,8 +829,9 @@ __device__ __noinline__ void reset_stage(const Params& p, BlockShared<T, W>& sh,
     }
   }
   __syncthreads();
-  if (!is_scalar && want_obs) raster_list<T, W>(sh, words, cfg, lt, nb);
+  if (!is_scalar && want_obs) raster_list<T, W>(sh, words, cfg, lt, nb, par);
   __syncthreads();
+  if (tid == 0) sh.count = 0;   // the list is consumed; the step loop's next pushes come after its kBarAgent
 }
 
 // One-step-ahead action fetch for int64 indices: cp.async copies the 8 bytes global -> shared without a register,
@@ -839,7 +852,9 @@ __device__ __forceinline__ long long load_action_index(const Params& p, long lon
 //   kBarAgent : the scalar warp ARRIVES (does not wait) once the agent positions are published; obstacle
 //               threads SYNC on it before their bounding-box tests.  Count = all 288 threads.
 //   kBarNear  : everybody syncs: hits and the near list are complete.
-//   kBarDone  : everybody syncs with an OR-reduction of "some environment of the block resets".
+//   kBarDone  : the scalar warp publishes "some environment of the block resets" (sh.any_reset) and ARRIVES; it
+//               knows the answer from its own vote and runs ahead into the next step (state update, next agent
+//               move, outputs) while the obstacle threads, which SYNC here, finish the raster of this one.
 constexpr int kBarAgent = 1, kBarNear = 2, kBarDone = 3;
 __device__ __forceinline__ void bar_sync(int id) {
   asm volatile("barrier.sync %0, %1;" ::"r"(id), "n"(kBlock) : "memory");
@@ -882,6 +897,16 @@ __device__ __forceinline__ bool bar_or(int id, bool pred) {
 // index actions, fp32 observation rows requested.  Every uniform test of the generic kernel folds away; the host
 // (ballenv_capi.cu) selects it when all of that holds.
 // kRollout: p.n_steps may exceed 1 (ballenv_step_many); otherwise the step loop has exactly one trip and folds away.
+// BALLENV_TRACE (tools/phase_trace.py): block 0 writes clock64() stamps of its phases over the reward rows of
+// environments 32.. of every step; block 1 keeps its rewards out of the way.  Profiling builds only.
+#ifdef BALLENV_TRACE
+#define BALLENV_STAMP(cond, slot)                                                                          \
+  if (kFast && kRollout && blockIdx.x == 0 && (cond))                                                                         \
+    reinterpret_cast<float*>(p.reward)[(long long)t * p.n + 32 + (slot)] = (float)(clock64() & 0xffffff)
+#else
+#define BALLENV_STAMP(cond, slot)
+#endif
+
 // Address of the block's observation rows of step t: (rows of step t) + (rows of the environments before e0).
 // Computed where a store needs it, so the step loop carries no pointer.
 template <bool kRollout>
@@ -953,7 +978,11 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
       auto flush_outputs = [&]() {
         if (!stepping) return;
         if (out_pending && mine) {
+#ifdef BALLENV_TRACE
+          if (p.reward != nullptr && blockIdx.x != 1) {
+#else
           if (p.reward != nullptr) {
+#endif
             if (sizeof(T) == 4) reinterpret_cast<float*>(p.reward)[out_et] = (float)out_reward;
             else reinterpret_cast<double*>(p.reward)[out_et] = out_reward;
           }
@@ -989,6 +1018,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
       };
       // ------------------------------------------- hot loop: no calls inside -------------------------------------
       for (; t < n_steps; ++t) {
+        BALLENV_STAMP(tid == 0, 0);
         const bool want_obs = kFast ? (p.obs_all_steps != 0 || t == n_steps - 1) : p.obs != nullptr;
         uint32_t* words = sh.words[t & 1];
         const long long et = (long long)t * p.n + e;   // index of this environment in the [T][n] arrays
@@ -1038,17 +1068,17 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
           if (nx > CfgV<T>::world_w(cfg)) nx = CfgV<T>::world_w(cfg);
           if (ny > CfgV<T>::world_h(cfg)) ny = CfgV<T>::world_h(cfg);
         }
-        sh.ax[tid] = nx;
-        sh.ay[tid] = ny;
+        sh.ax[t & 1][tid] = nx;
+        sh.ay[t & 1][tid] = ny;
         sh.hit[tid] = kNoHit;
         sh.reset[tid] = reset_req ? 1 : 0;   // Reset mode: stored obstacles of these environments are ignored
-        if (tid == 0) sh.count = 0;
         if (mine && !reset_req && want_obs) {
           // 4 goal-quadrant bits (examples/ball_cnn_ac3.py:341-350); a reset of this environment clears and redoes them
           const T qdx = r_sub(gx, nx), qdy = r_sub(gy, ny);
           const int b = tid * nb + goal_quadrant_bit(qdx < (T)0, qdy < (T)0);
           atomicOr(&words[b >> 5], 1u << (b & 31));
         }
+        BALLENV_STAMP(tid == 0, 1);
         bar_arrive(kBarAgent);
 
         // ---- off the critical path (the obstacle threads are moving and testing): outputs of the previous step,
@@ -1063,13 +1093,15 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
           truncated = cfg.max_steps > 0 && ep_len >= cfg.max_steps;
           goal_flag = d < cfg.goal_threshold;                                      // :276 | :690 (pygame: unless hit)
           if (gym) {
-            reward = (dist - d) / total;                                           // :205-206, old = state[2] (:236)
+            reward = div64(dist - d, total);                                           // :205-206, old = state[2] (:236)
           } else {
             const double od = dist64((double)ax, (double)ay, (double)gx, (double)gy);   // :652
-            reward = (od - d) / total;                                             // :699-706
+            reward = div64(od - d, total);                                             // :699-706
           }
         }
+        BALLENV_STAMP(tid == 0, 2);
         bar_sync(kBarNear);
+        BALLENV_STAMP(tid == 0, 3);
 
         // ---- critical: apply the hits, decide the resets
         bool do_reset = false, done_out = false, hit = false, hit_dyn = false, done = false;
@@ -1098,7 +1130,14 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
           }
           if (do_reset) sh.reset[tid] = 1;
         }
-        const bool any_reset = bar_or(kBarDone, do_reset);
+        // The vote is complete inside this warp (it owns all 32 environments): publish it and arrive without
+        // waiting.  The scalar warp is the longest dependency chain of a step; everything below, up to the next
+        // agent positions, overlaps with the obstacle threads' raster of this step.
+        const bool any_reset = __any_sync(0xffffffffu, do_reset);
+        if (tid == 0) sh.any_reset = any_reset ? 1 : 0;
+        BALLENV_STAMP(tid == 0, 4);
+        if (any_reset) bar_sync(kBarDone);   // the reset stage rewrites what the raster of this step still reads
+        else bar_arrive(kBarDone);
 
         // ---- state of the next step; the step's outputs are parked until after the next arrive
         if (mine && stepping) {
@@ -1149,7 +1188,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
         // (rare) the step that is being finished is t: reset, then its observation
         const bool want_obs = kFast ? (p.obs_all_steps != 0 || t == n_steps - 1) : p.obs != nullptr;
         uint32_t* words = sh.words[t & 1];
-        reset_stage<T, W>(p, sh, words, e0, cnt_env, want_obs);
+        reset_stage<T, W>(p, sh, words, e0, cnt_env, want_obs, t & 1);
         if (want_obs && !(p.debug & 8))
           store_obs<W, kFast>(p, obs_block<kRollout>(p, e0, t), words, sh.lut, cnt_env, tid, kBlock);
         reset_req = false;
@@ -1191,6 +1230,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
     // block setup shared by the obstacle threads: cleared bit-stream; goal and move tables.  Every warp writes the
     // (identical) table entries it is going to read, so a warp-level sync is all the moves below need.
     for (int i = lt; i < nb; i += kLaneThreads) sh.words[0][i] = 0;
+    if (lt == 0) sh.count = 0;
     {
       const int l32 = tid & 31;
       if (l32 < 9) {
@@ -1217,7 +1257,11 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
       }
       bool pending_reset = false;
       // ------------------------------------------- hot loop: no calls inside -------------------------------------
+#ifdef BALLENV_TRACE
+      const int tr = lt == 0 ? 8 : (lt == n_stat ? 16 : -1);
+#endif
       for (; t < n_steps; ++t) {
+        BALLENV_STAMP(tr >= 0, tr + 0);
         const bool want_obs = kFast ? (p.obs_all_steps != 0 || t == n_steps - 1) : p.obs != nullptr;
         uint32_t* words = sh.words[t & 1];
         // obstacle motion does not depend on the agent: draw and move while the scalar warp works
@@ -1229,13 +1273,15 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
           else
             dynamic_move<T, W, false>(p, sh, e0 + q_el, q_jq, tick + (uint32_t)t, qx, qy, qm);
         }
+        BALLENV_STAMP(tr >= 0, tr + 1);
         bar_sync(kBarAgent);   // agent positions published; everybody is done with the previous step's bit-stream
+        BALLENV_STAMP(tr >= 0, tr + 2);
         if (t + 1 < n_steps)
           for (int i = lt; i < nb; i += kLaneThreads) sh.words[(t + 1) & 1][i] = 0;
 
         // bounding-box test every obstacle against the agent; near ones are hit-tested and queued
         if (q_have && !(p.debug & 4)) {
-          const T ax = sh.ax[q_el], ay = sh.ay[q_el];
+          const T ax = sh.ax[t & 1][q_el], ay = sh.ay[t & 1][q_el];
           uint32_t near = 0;   // one branch for the quad: the four tests are almost always all false
 #pragma unroll
           for (int i = 0; i < 4; ++i)
@@ -1268,17 +1314,23 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
             }
           }
           const int k0 = dyn ? ks + 4 * qq : 4 * qq, kend = dyn ? ks + kd : ks;
-          const T ax = sh.ax[el], ay = sh.ay[el];
+          const T ax = sh.ax[t & 1][el], ay = sh.ay[t & 1][el];
 #pragma unroll
           for (int i = 0; i < 4; ++i)
             if (k0 + i < kend)
               near_test<T, W>(sh, words, cfg, el, ax, ay, margin, x[i], y[i], k0 + i, stepping, want_obs, nb);
         }
+        BALLENV_STAMP(tr >= 0, tr + 3);
         bar_sync(kBarNear);
+        BALLENV_STAMP(tr >= 0, tr + 4);
 
         // block-cooperative raster of the near list
-        if (want_obs) raster_list<T, W>(sh, words, cfg, lt, nb);
-        if (bar_or(kBarDone, false)) {   // leave the hot loop: the reset goes through global memory
+        if (want_obs) raster_list<T, W>(sh, words, cfg, lt, nb, t & 1);
+        BALLENV_STAMP(tr >= 0, tr + 5);
+        bar_sync(kBarDone);
+        BALLENV_STAMP(tr >= 0, tr + 6);
+        if (lt == 0) sh.count = 0;   // the near list of the step is consumed (the next pushes come after kBarAgent)
+        if (sh.any_reset != 0) {   // leave the hot loop: the reset goes through global memory
           pending_reset = true;
           break;
         }
@@ -1298,7 +1350,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
       {
         const bool want_obs = kFast ? (p.obs_all_steps != 0 || t == n_steps - 1) : p.obs != nullptr;
         uint32_t* words = sh.words[t & 1];
-        reset_stage<T, W>(p, sh, words, e0, cnt_env, want_obs);
+        reset_stage<T, W>(p, sh, words, e0, cnt_env, want_obs, t & 1);
         if (want_obs && !(p.debug & 8))
           store_obs<W, kFast>(p, obs_block<kRollout>(p, e0, t), words, sh.lut, cnt_env, tid, kBlock);
         if (!kFast && lt < n_slot) q_have = q_el < cnt_env;   // Reset mode: the environment has state now

@@ -7,7 +7,8 @@ import bench
 from gym_ballenv_b200 import BallVecEnv
 T = 200
 spec = bench.workload_spec("c3")
-for n in (18944, 37888, 56832, 65536, 75776, 131072):
+NS = [int(x) for x in os.environ.get("NS", "18944,37888,56832,65536,75776,131072").split(",")]
+for n in NS:
     env = BallVecEnv(n, window=10, config=bench.env_config(spec), seed=0, device="cuda:0")
     env.reset()
     a = torch.randint(0, 9, (T, n), device="cuda:0")

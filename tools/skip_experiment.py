@@ -7,7 +7,7 @@ from gym_ballenv_b200 import BallVecEnv
 T = 200
 for wl in ("c3",):
     spec = bench.workload_spec(wl)
-    for n in (65536,):
+    for n in [int(x) for x in os.environ.get("NS", "65536").split(",")]:
         for skip in (0, 2, 4, 8, 16, 2 + 4, 4 + 8, 2 + 4 + 8, 2 + 4 + 8 + 16):
             os.environ["BALLENV_DEBUG_SKIP"] = str(skip)
             env = BallVecEnv(n, window=spec["window"], config=bench.env_config(spec), seed=0, device="cuda:0",
