@@ -55,7 +55,7 @@ EXPORTS = (
     "ballenv_abi_version", "ballenv_last_error", "ballenv_config_default", "ballenv_state_bytes",
     "ballenv_create", "ballenv_destroy", "ballenv_state_ptrs", "ballenv_reset", "ballenv_step",
     "ballenv_step_many", "ballenv_observe", "ballenv_observe_features", "ballenv_step_host", "ballenv_set_draw_tape", "ballenv_stats",
-    "ballenv_stats_reset", "ballenv_error_flags", "ballenv_launch_count",
+    "ballenv_stats_reset", "ballenv_error_flags", "ballenv_launch_count", "ballenv_selftest",
 )
 
 
@@ -82,6 +82,8 @@ def _bind(lib):
     lib.ballenv_error_flags.argtypes = [vp, vp, vp]
     lib.ballenv_launch_count.argtypes = [vp]
     lib.ballenv_launch_count.restype = i64
+    lib.ballenv_selftest.argtypes = [C.c_int, i64, C.c_int, C.POINTER(i64)]
+    lib.ballenv_selftest.restype = C.c_int
     for name in EXPORTS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int and name not in ("ballenv_abi_version",):

@@ -25,6 +25,13 @@ void launch_f32_w10_fast(const Params&, unsigned, cudaStream_t);
 void launch_f32_wany_fast(const Params&, unsigned, cudaStream_t);
 }  // namespace ballenv
 
+__global__ void selftest_sqrt_kernel(long long n, unsigned long long* bad) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float s = (float)i;
+  if (__double_as_longlong(ballenv::sqrt_int22(s)) != __double_as_longlong(sqrt((double)s))) atomicAdd(bad, 1ull);
+}
+
 namespace {
 
 thread_local char g_err[512] = "";
@@ -677,5 +684,22 @@ int ballenv_error_flags(BallenvHandle* h, uint32_t* out, ballenv_stream_t stream
 }
 
 int64_t ballenv_launch_count(BallenvHandle* h) { return h ? h->launches : 0; }
+
+int ballenv_selftest(int which, int64_t arg, int device, int64_t* mismatches) {
+  if (mismatches == nullptr) return fail(BALLENV_EINVAL, "mismatches is null");
+  if (which != 0) return fail(BALLENV_EINVAL, "unknown self-test %d", which);
+  if (arg < 0 || arg > (1ll << 22)) return fail(BALLENV_EINVAL, "sqrt_int22 is defined for 0 <= s < 2^22");
+  DeviceGuard guard(device);
+  unsigned long long* d_bad = nullptr;
+  CUDA_TRY(cudaMalloc(&d_bad, sizeof(*d_bad)));
+  cudaMemset(d_bad, 0, sizeof(*d_bad));
+  selftest_sqrt_kernel<<<(unsigned)((arg + 255) / 256), 256>>>(arg, d_bad);
+  unsigned long long bad = 0;
+  cudaError_t e = cudaMemcpy(&bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost);
+  cudaFree(d_bad);
+  if (e != cudaSuccess) return fail(BALLENV_ECUDA, "self-test failed: %s", cudaGetErrorString(e));
+  *mismatches = (int64_t)bad;
+  return BALLENV_OK;
+}
 
 }  // extern "C"

@@ -155,6 +155,26 @@ __device__ __forceinline__ double dist64(double ax, double ay, double bx, double
   return sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
 }
 
+// sqrt((double)s) for an integer-valued float 0 <= s < 2^22, bit for bit (ballenv_selftest(0, ...) compares every
+// s of that range with sqrt()): fp32 reciprocal-square-root seed, one coupled Newton step in fp64 for g ~ sqrt(s)
+// and h ~ 1 / (2 sqrt(s)), then g + (s - g*g) * h with the residual as a single fused operation - the value before
+// the final rounding is within 2^-80 of sqrt(s), far inside the distance of any such root from a rounding
+// boundary.  Four dependent fp64 operations instead of the library routine's dozen - and the distance to the
+// goal sits on the scalar warp's chain, the longest of a step.
+__device__ __forceinline__ double sqrt_int22(float s) {
+  float rs;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(s));
+  const double sd = (double)s, h0 = 0.5 * (double)rs, g0 = sd * (double)rs;   // exact products: one shared seed error
+  const double r0 = fma(-g0, h0, 0.5);
+  const double g1 = fma(g0, r0, g0), h1 = fma(h0, r0, h0);
+  const double g2 = fma(fma(-g1, g1, sd), h1, g1);
+  return s == 0.0f ? 0.0 : g2;
+}
+// true if v is an integer of magnitude <= 1024: differences of two such values are exact in fp32 and the sum of
+// two squared differences stays below 2^22 + 1
+__device__ __forceinline__ bool small_int(float v) { return v == truncf(v) && fabsf(v) <= 1024.0f; }
+__device__ __forceinline__ bool small_int(double) { return false; }
+
 // check_overlap (ballenv_env.py:185-191): NOT (sqrt(dx^2 + dy^2) > r).  In fp32 the squares of the integral
 // coordinates the env produces are exact (< 2^24), so "<= r^2" is the same predicate without the sqrt.
 template <typename T>
@@ -315,7 +335,7 @@ __device__ __forceinline__ void near_test(BlockShared<T, W>& sh, uint32_t* words
 // Obstacle threads (lt = 0 .. kLaneThreads-1): rasterise the queued (obstacle, row) items.
 template <typename T, int W>
 __device__ __forceinline__ void raster_list(BlockShared<T, W>& sh, uint32_t* words, const DevConfig& cfg, int lt,
-                                            int nb, int par) {
+                                            int nb, int par, int nthreads = kLaneThreads) {
   const int cnt = sh.count < kListCap ? sh.count : kListCap;
   if (cnt == 0) return;
   const Overlap<T> ov(cfg.radius_sum);
@@ -323,7 +343,7 @@ __device__ __forceinline__ void raster_list(BlockShared<T, W>& sh, uint32_t* wor
   const int nyi = w > 1 ? w - 1 : 1;
   const int items = cnt * nyi;
   const T step_x = CfgV<T>::step_x(cfg), step_y = CfgV<T>::step_y(cfg);
-  for (int it = lt; it < items; it += kLaneThreads) {
+  for (int it = lt; it < items; it += nthreads) {
     const int en = it / nyi, yi = it - en * nyi;
     const int el = sh.near_env[en];
     raster_item<T, W>(words, el * nb, sh.near_x[en], sh.near_y[en], sh.ax[par][el], sh.ay[par][el], step_x, step_y, yi, w, ov);
@@ -571,10 +591,21 @@ __device__ __forceinline__ void store_rows_f32(float4* dst, const uint32_t* word
   constexpr int kFullVec = W > 0 ? 8 * (4 + W * W) : 0;
   if (W > 0 && nvec == kFullVec) {
     constexpr int kIter = kFullVec / kThreads, kTail = kFullVec % kThreads;
+    // batches of four: the word loads, then the table loads, then the stores - four independent chains in flight
+    // instead of one (the storing threads are on the step's critical path)
 #pragma unroll
-    for (int k = 0; k < kIter; ++k) {
-      const uint32_t wd = wp[k * (kThreads / 8)];
-      __stcs(d + k * kThreads, *reinterpret_cast<const float4*>(lutb + (__funnelshift_r(wd, wd, rot) & 0xf0u)));
+    for (int k0 = 0; k0 < kIter; k0 += 4) {
+      uint32_t wd[4];
+      float4 v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (k0 + j < kIter) wd[j] = wp[(k0 + j) * (kThreads / 8)];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (k0 + j < kIter) v[j] = *reinterpret_cast<const float4*>(lutb + (__funnelshift_r(wd[j], wd[j], rot) & 0xf0u));
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (k0 + j < kIter) __stcs(d + (k0 + j) * kThreads, v[j]);
     }
     if (kTail != 0 && tid < kTail) {
       const uint32_t wd = wp[kIter * (kThreads / 8)];
@@ -855,12 +886,22 @@ __device__ __forceinline__ long long load_action_index(const Params& p, long lon
 //   kBarDone  : the scalar warp publishes "some environment of the block resets" (sh.any_reset) and ARRIVES; it
 //               knows the answer from its own vote and runs ahead into the next step (state update, next agent
 //               move, outputs) while the obstacle threads, which SYNC here, finish the raster of this one.
-constexpr int kBarAgent = 1, kBarNear = 2, kBarDone = 3;
+//   kBarRaster: split form of kBarDone, used when whole warps hold static quads only (they have no draws and no
+//               moves to do): those threads rasterise the near list, then SYNC here with each other and with the
+//               scalar warp's decision, and store the rows; the dynamic-quad threads SYNC on kBarDone for the decision
+//               alone and go straight to their next moves.  Counts: 32 + static threads / 32 + the other threads.
+constexpr int kBarAgent = 1, kBarNear = 2, kBarDone = 3, kBarRaster = 4;
 __device__ __forceinline__ void bar_sync(int id) {
   asm volatile("barrier.sync %0, %1;" ::"r"(id), "n"(kBlock) : "memory");
 }
 __device__ __forceinline__ void bar_arrive(int id) {
   asm volatile("barrier.arrive %0, %1;" ::"r"(id), "n"(kBlock) : "memory");
+}
+__device__ __forceinline__ void bar_sync_n(int id, int count) {
+  asm volatile("barrier.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bar_arrive_n(int id, int count) {
+  asm volatile("barrier.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 __device__ __forceinline__ bool bar_or(int id, bool pred) {
   int r;
@@ -927,6 +968,10 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
   const int ks = cfg.ks, kd = cfg.kd;
   const bool stepping = kFast || p.mode == kModeStep;
   const int n_steps = kRollout ? p.n_steps : 1;
+  // threads that store the observation rows: the static-quad threads (no draws, no moves) when they are at least
+  // two and not all of the warps, otherwise every obstacle thread; see kBarRaster
+  const int n_store = (kRollout && p.n_stat >= 64 && p.n_stat < kLaneThreads) ? p.n_stat : kLaneThreads;
+  const bool split = n_store != kLaneThreads;
   if (p.debug & 1) return;
 
   if (tid < 32) {
@@ -968,53 +1013,37 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
           tick = p.tick[e];
         }
       }
+      // Integral coordinates (what the gym ruleset produces: integer draws, unit steps) stay integral while the
+      // loop runs, and the squared distance to the goal is then an exact small integer: sqrt_int22 applies.
+      const bool exact32 =
+          kFast && __all_sync(0xffffffffu, !mine || (small_int(ax) && small_int(ay) && small_int(gx) && small_int(gy))) &&
+          small_int(CfgV<T>::step_x(cfg)) && small_int(CfgV<T>::step_y(cfg)) && small_int(CfgV<T>::world_w(cfg)) &&
+          small_int(CfgV<T>::world_h(cfg));
       bool pending_reset = false;
-      // outputs of a step (reward, done, statistics) are written one step late, after the next agent positions are
-      // published: nobody waits for them, and the scalar warp is the critical path of a step
-      bool out_pending = false;
-      long long out_et = 0;
-      double out_reward = 0.0, out_ret = 0.0, out_len = 0.0;
-      uint32_t out_done = 0, out_cnt = 0;
-      auto flush_outputs = [&]() {
-        if (!stepping) return;
-        if (out_pending && mine) {
-#ifdef BALLENV_TRACE
-          if (p.reward != nullptr && blockIdx.x != 1) {
-#else
-          if (p.reward != nullptr) {
-#endif
-            if (sizeof(T) == 4) reinterpret_cast<float*>(p.reward)[out_et] = (float)out_reward;
-            else reinterpret_cast<double*>(p.reward)[out_et] = out_reward;
-          }
-          if (p.done != nullptr) p.done[out_et] = (uint8_t)out_done;
-        }
-        // episode statistics (the only thing that is ever all-reduced across GPUs): ballot + shuffle in the scalar
-        // warp, one atomic per counter per block, and only in blocks where an episode ended.
-        const uint32_t cnt = (out_pending && mine) ? out_cnt : 0u;
+      // Episode statistics (the only thing that is ever all-reduced across GPUs): ballot + shuffle in the scalar
+      // warp, one atomic per counter per block, and only in blocks where an episode ended.  cnt: 0, or 1 | 2 goal |
+      // 4 static hit | 8 dynamic hit | 16 time-out.
+      auto episode_stats = [&](uint32_t cnt, double ret, double ep_len) {
         const uint32_t fin = __ballot_sync(0xffffffffu, cnt != 0);
-        if (fin != 0) {
-          double st_ret = cnt ? out_ret : 0.0, st_len = cnt ? out_len : 0.0;
+        double st_ret = cnt ? ret : 0.0, st_len = cnt ? ep_len : 0.0;
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            st_ret += __shfl_xor_sync(0xffffffffu, st_ret, o);
-            st_len += __shfl_xor_sync(0xffffffffu, st_len, o);
-          }
-          const uint32_t n_goal = __popc(__ballot_sync(0xffffffffu, cnt & 2u));
-          const uint32_t n_hs = __popc(__ballot_sync(0xffffffffu, cnt & 4u));
-          const uint32_t n_hd = __popc(__ballot_sync(0xffffffffu, cnt & 8u));
-          const uint32_t n_to = __popc(__ballot_sync(0xffffffffu, cnt & 16u));
-          if (tid == 0) {
-            atomicAdd(&p.stats[BALLENV_STAT_EPISODES], (double)__popc(fin));
-            atomicAdd(&p.stats[BALLENV_STAT_RETURN_SUM], st_ret);
-            atomicAdd(&p.stats[BALLENV_STAT_LENGTH_SUM], st_len);
-            if (n_goal) atomicAdd(&p.stats[BALLENV_STAT_GOALS], (double)n_goal);
-            if (n_hs) atomicAdd(&p.stats[BALLENV_STAT_HITS_STATIC], (double)n_hs);
-            if (n_hd) atomicAdd(&p.stats[BALLENV_STAT_HITS_DYNAMIC], (double)n_hd);
-            if (n_to) atomicAdd(&p.stats[BALLENV_STAT_TIMEOUTS], (double)n_to);
-          }
+        for (int o = 16; o > 0; o >>= 1) {
+          st_ret += __shfl_xor_sync(0xffffffffu, st_ret, o);
+          st_len += __shfl_xor_sync(0xffffffffu, st_len, o);
         }
-        if (out_pending && e == 0) atomicAdd(&p.stats[BALLENV_STAT_STEPS], (double)p.n);
-        out_pending = false;
+        const uint32_t n_goal = __popc(__ballot_sync(0xffffffffu, cnt & 2u));
+        const uint32_t n_hs = __popc(__ballot_sync(0xffffffffu, cnt & 4u));
+        const uint32_t n_hd = __popc(__ballot_sync(0xffffffffu, cnt & 8u));
+        const uint32_t n_to = __popc(__ballot_sync(0xffffffffu, cnt & 16u));
+        if (tid == 0) {
+          atomicAdd(&p.stats[BALLENV_STAT_EPISODES], (double)__popc(fin));
+          atomicAdd(&p.stats[BALLENV_STAT_RETURN_SUM], st_ret);
+          atomicAdd(&p.stats[BALLENV_STAT_LENGTH_SUM], st_len);
+          if (n_goal) atomicAdd(&p.stats[BALLENV_STAT_GOALS], (double)n_goal);
+          if (n_hs) atomicAdd(&p.stats[BALLENV_STAT_HITS_STATIC], (double)n_hs);
+          if (n_hd) atomicAdd(&p.stats[BALLENV_STAT_HITS_DYNAMIC], (double)n_hd);
+          if (n_to) atomicAdd(&p.stats[BALLENV_STAT_TIMEOUTS], (double)n_to);
+        }
       };
       // ------------------------------------------- hot loop: no calls inside -------------------------------------
       for (; t < n_steps; ++t) {
@@ -1081,15 +1110,18 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
         BALLENV_STAMP(tid == 0, 1);
         bar_arrive(kBarAgent);
 
-        // ---- off the critical path (the obstacle threads are moving and testing): outputs of the previous step,
-        //      then distance, progress reward, goal and time-limit flags of this one
-        //      (ballenv_env.py:268-286, 200-206 | ballenv_pygame.py:652-706)
-        flush_outputs();
+        // ---- while the obstacle threads move and test: distance, progress reward, goal and time-limit flags of
+        //      this step (ballenv_env.py:268-286, 200-206 | ballenv_pygame.py:652-706)
         double d = dist, reward = 0.0;
         bool goal_flag = false, truncated = false;
         const int ep_len = len + 1;
         if (mine && stepping && !(p.debug & 16)) {
-          d = dist64((double)gx, (double)gy, (double)nx, (double)ny);               // :268 | :668
+          if (exact32) {
+            const float dx = (float)gx - (float)nx, dy = (float)gy - (float)ny;     // exact, as are the squares
+            d = sqrt_int22(__fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+          } else {
+            d = dist64((double)gx, (double)gy, (double)nx, (double)ny);             // :268 | :668
+          }
           truncated = cfg.max_steps > 0 && ep_len >= cfg.max_steps;
           goal_flag = d < cfg.goal_threshold;                                      // :276 | :690 (pygame: unless hit)
           if (gym) {
@@ -1136,38 +1168,48 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
         const bool any_reset = __any_sync(0xffffffffu, do_reset);
         if (tid == 0) sh.any_reset = any_reset ? 1 : 0;
         BALLENV_STAMP(tid == 0, 4);
-        if (any_reset) bar_sync(kBarDone);   // the reset stage rewrites what the raster of this step still reads
-        else bar_arrive(kBarDone);
+        if (!split) {
+          if (any_reset) bar_sync(kBarDone);   // the reset stage rewrites what the raster of this step still reads
+          else bar_arrive(kBarDone);
+        } else {
+          bar_arrive_n(kBarDone, 32 + kLaneThreads - n_store);
+          if (any_reset) bar_sync_n(kBarRaster, 32 + n_store);
+          else bar_arrive_n(kBarRaster, 32 + n_store);
+        }
 
-        // ---- state of the next step; the step's outputs are parked until after the next arrive
+        // ---- outputs of the step (the scalar warp is past the barrier: nobody waits for these), next state
         if (mine && stepping) {
           acc += reward;                                                              // :280
           flags = (goal_flag ? BALLENV_FLAG_GOAL : 0) | (hit ? BALLENV_FLAG_HIT : 0) |
                   (truncated ? BALLENV_FLAG_TRUNCATED : 0) | (hit_dyn ? BALLENV_FLAG_HIT_DYNAMIC : 0);
-          out_et = et;
-          out_reward = reward;
-          out_done = done_out ? 1u : 0u;
-          out_cnt = 0;
-          if (done_out) {
-            out_ret = acc;
-            out_len = (double)ep_len;
-            out_cnt = 1u | (goal_flag ? 2u : 0u) | ((hit && !hit_dyn) ? 4u : 0u) | (hit_dyn ? 8u : 0u) |
-                      ((truncated && !done) ? 16u : 0u);
+#ifdef BALLENV_TRACE
+          if (p.reward != nullptr && blockIdx.x != 1) {
+#else
+          if (p.reward != nullptr) {
+#endif
+            if (sizeof(T) == 4) reinterpret_cast<float*>(p.reward)[et] = (float)reward;
+            else reinterpret_cast<double*>(p.reward)[et] = reward;
           }
+          if (p.done != nullptr) p.done[et] = done_out ? 1 : 0;
+          if (e == 0) atomicAdd(&p.stats[BALLENV_STAT_STEPS], (double)p.n);
           ax = nx;
           ay = ny;
           dist = d;
           len = ep_len;
           tick += 1;
         }
-        out_pending = stepping;
+        if (stepping && __any_sync(0xffffffffu, done_out)) {   // an episode of the block ended (rare)
+          const uint32_t cnt = done_out ? (1u | (goal_flag ? 2u : 0u) | ((hit && !hit_dyn) ? 4u : 0u) |
+                                           (hit_dyn ? 8u : 0u) | ((truncated && !done) ? 16u : 0u))
+                                        : 0u;
+          episode_stats(cnt, acc, (double)ep_len);
+        }
         if (any_reset) {   // leave the hot loop: the reset goes through global memory
           pending_reset = true;
           break;
         }
         // (the observation rows of the step are stored by the obstacle threads)
       }
-      flush_outputs();
 
       // ---- write the scalar state back (a pending reset then overwrites it for the environments that finished)
       if (mine) {
@@ -1241,7 +1283,6 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
     }
     __syncthreads();   // block setup done (pairs with the scalar warp's)
 
-    const int n_store = (kRollout && n_stat >= 64 && n_stat < kLaneThreads) ? n_stat : kLaneThreads;
     int t = 0, t_load = 0;
     for (;;) {
       // (re)load the quad: at launch, and after a reset went through global memory
@@ -1324,10 +1365,19 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
         bar_sync(kBarNear);
         BALLENV_STAMP(tr >= 0, tr + 4);
 
-        // block-cooperative raster of the near list
-        if (want_obs) raster_list<T, W>(sh, words, cfg, lt, nb, t & 1);
-        BALLENV_STAMP(tr >= 0, tr + 5);
-        bar_sync(kBarDone);
+        // cooperative raster of the near list, then the reset decision (see kBarRaster)
+        if (!split) {
+          if (want_obs) raster_list<T, W>(sh, words, cfg, lt, nb, t & 1);
+          BALLENV_STAMP(tr >= 0, tr + 5);
+          bar_sync(kBarDone);
+        } else if (lt < n_store) {
+          if (want_obs) raster_list<T, W>(sh, words, cfg, lt, nb, t & 1, n_store);
+          BALLENV_STAMP(tr >= 0, tr + 5);
+          bar_sync_n(kBarRaster, 32 + n_store);
+        } else {
+          BALLENV_STAMP(tr >= 0, tr + 5);
+          bar_sync_n(kBarDone, 32 + kLaneThreads - n_store);
+        }
         BALLENV_STAMP(tr >= 0, tr + 6);
         if (lt == 0) sh.count = 0;   // the near list of the step is consumed (the next pushes come after kBarAgent)
         if (sh.any_reset != 0) {   // leave the hot loop: the reset goes through global memory

@@ -230,6 +230,11 @@ int ballenv_stats_reset(BallenvHandle *h, ballenv_stream_t stream);
 int ballenv_error_flags(BallenvHandle *h, uint32_t *out /* host */, ballenv_stream_t stream);
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
 int64_t ballenv_launch_count(BallenvHandle *h);
+/* Device self-tests of the arithmetic shortcuts the step kernel takes (no reference counterpart; run by the GPU
+ * tests).  which = 0: the integer square root used for the distance to the goal when all coordinates are integral
+ * (sqrt_int22) against sqrt() for every integer 0 <= s < arg; *mismatches receives the number of differing
+ * results (synchronises the device). */
+int ballenv_selftest(int which, int64_t arg, int device, int64_t *mismatches /* host */);
 
 #ifdef __cplusplus
 }

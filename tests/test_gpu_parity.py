@@ -560,3 +560,15 @@ def test_extreme_window_sizes_against_the_oracle(w):
     assert env.error_flags() == 0
     with pytest.raises(Exception):
         BallVecEnv(4, window=33)
+
+
+@pytest.mark.gpu
+def test_integer_sqrt_shortcut_is_exact():
+    """The step kernel takes sqrt_int22 for the distance to the goal when every coordinate is integral: it must
+    return the bits of sqrt() for every argument it can see (squared distances of a world of at most 1024 x 1024)."""
+    import ctypes as C
+    from gym_ballenv_b200 import _lib as L
+    bad = C.c_int64(-1)
+    rc = L.LIB.ballenv_selftest(0, 1 << 22, 0, C.byref(bad))
+    assert rc == 0, L.LIB.ballenv_last_error()
+    assert bad.value == 0, "%d of 2^22 arguments differ from sqrt()" % bad.value

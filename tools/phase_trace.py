@@ -11,7 +11,9 @@ from gym_ballenv_b200 import BallVecEnv
 T = 60
 spec = bench.workload_spec(os.environ.get("WL", "c3"))
 for n in [int(x) for x in os.environ.get("NS", "4736,65536").split(",")]:
+    os.environ["BALLENV_DEBUG_SKIP"] = os.environ.get("SKIP", "0")   # read when the handle is created
     env = BallVecEnv(n, window=spec["window"], config=bench.env_config(spec), seed=0, device="cuda:0", max_episode_steps=0)
+    os.environ["BALLENV_DEBUG_SKIP"] = "0"
     env.reset()
     a = torch.randint(0, 9, (T, n), device="cuda:0")
     out = env.alloc_rollout(T, keep_all_obs=True)
