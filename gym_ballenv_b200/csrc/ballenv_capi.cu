@@ -582,7 +582,22 @@ int ballenv_step_many(BallenvHandle* h, const void* actions, int action_kind, in
     p.done = done_out;
     p.reset_tape = h->reset_tape;
     p.step_tape = h->step_tape;
-    if (!h->no_rollout && fast_eligible(h, p)) return launch(h, p, (cudaStream_t)stream);
+    if (!h->no_rollout && fast_eligible(h, p)) {
+      // the kernel indexes the [T][n] arrays with 32 bits: at most (2^31 - 1) / n steps per launch
+      const int64_t max_t = n > 0 ? (int64_t)0x7fffffff / (int64_t)n : n_steps;
+      if (max_t < 1) return fail(BALLENV_EINVAL, "too many environments for one launch");
+      for (int64_t t0 = 0; t0 < n_steps; t0 += max_t) {
+        const int64_t tn = n_steps - t0 < max_t ? n_steps - t0 : max_t;
+        p.n_steps = (int)tn;
+        p.actions = (const char*)actions + (size_t)t0 * n * ab;
+        p.obs = obs_all_steps ? (char*)obs_out + (size_t)t0 * n * obs_row : obs_out;
+        p.reward = reward_out ? (char*)reward_out + (size_t)t0 * n * rew_b : nullptr;
+        p.done = done_out ? done_out + (size_t)t0 * n : nullptr;
+        int rc = launch(h, p, (cudaStream_t)stream);
+        if (rc != BALLENV_OK) return rc;
+      }
+      return BALLENV_OK;
+    }
   }
   for (int t = 0; t < n_steps; ++t) {
     void* obs_t = nullptr;

@@ -146,7 +146,9 @@ __device__ __forceinline__ double r_abs(double a) { return fabs(a); }
 // step - through the slow path of the fp64 division; (+-0) / den is +-0 for den > 0, so those lanes divide 1 instead.
 __device__ __forceinline__ double div64(double num, double den) {
   const bool zero = num == 0.0 && den > 0.0;
-  const double q = (zero ? 1.0 : num) / den;
+  double safe = zero ? 1.0 : num;
+  asm("" : "+d"(safe));   // opaque: otherwise the compiler divides num itself again (its quotient is unused when zero)
+  const double q = safe / den;
   return zero ? num : q;
 }
 
@@ -673,7 +675,8 @@ __device__ __forceinline__ void store_obs(const Params& p, void* blk, const uint
 
 __device__ __forceinline__ int goal_quadrant_bit(bool dx_neg, bool dy_neg) {
   // prep_state2 (examples/ball_cnn_ac3.py:341-350): idx1 dx>=0,dy>=0 ; idx0 dx<0,dy>=0 ; idx3 dx<0,dy<0 ; idx2 else
-  return (!dx_neg && !dy_neg) ? 1 : ((dx_neg && !dy_neg) ? 0 : ((dx_neg && dy_neg) ? 3 : 2));
+  // as a packed table over (dx_neg | dy_neg << 1): 1, 0, 2, 3
+  return (int)((0xe1u >> (2u * ((dx_neg ? 1u : 0u) | (dy_neg ? 2u : 0u)))) & 3u);
 }
 
 // Dynamic quad at element offset off: 128-bit loads of x, y (and meta when stepping) ...
@@ -1050,7 +1053,8 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
         BALLENV_STAMP(tid == 0, 0);
         const bool want_obs = kFast ? (p.obs_all_steps != 0 || t == n_steps - 1) : p.obs != nullptr;
         uint32_t* words = sh.words[t & 1];
-        const long long et = (long long)t * p.n + e;   // index of this environment in the [T][n] arrays
+        // index of this environment in the [T][n] arrays (n_steps * n < 2^31 per launch: ballenv_step_many splits)
+        const long long et = (long long)((uint32_t)t * (uint32_t)p.n + (uint32_t)e);
         // ---- critical: agent move + clamp (ballenv_env.py:247-259 | ballenv_pygame.py:654-664), publish, arrive
         T nx = ax, ny = ay;
         if (mine && stepping) {
