@@ -1257,7 +1257,8 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
     T qx[4], qy[4];
     uint32_t qm[4];
     uint32_t tick = 0;
-    int q_el = 0, q_k0 = 0, q_kend = 0, q_jq = 0;   // environment (of the block), first list index, end index, dynamic quad
+    int q_el = 0, q_jq = 0;    // environment (of the block), quad of its kind within the environment
+    uint32_t q_valid = 0;      // which of the quad's four slots hold obstacles (the last quad of a kind may be padded)
     bool q_have = false;
     const bool q_dyn = lt >= n_stat;
     const uint32_t q_off = q_dyn ? dyn0 + 4u * (uint32_t)(lt - n_stat) : stat0 + 4u * (uint32_t)lt;
@@ -1270,8 +1271,8 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
       if (!kFast && q_have && p.mode == kModeReset)
         q_have = p.reset_mask == nullptr ? false : p.reset_mask[e0 + q_el] == 0;
       q_jq = qq;
-      q_k0 = q_dyn ? ks + 4 * qq : 4 * qq;
-      q_kend = q_dyn ? ks + kd : ks;
+      const int left = (q_dyn ? kd : ks) - 4 * qq;
+      q_valid = left >= 4 ? 15u : (1u << left) - 1u;
     }
     // block setup shared by the obstacle threads: cleared bit-stream; goal and move tables.  Every warp writes the
     // (identical) table entries it is going to read, so a warp-level sync is all the moves below need.
@@ -1330,12 +1331,14 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
           uint32_t near = 0;   // one branch for the quad: the four tests are almost always all false
 #pragma unroll
           for (int i = 0; i < 4; ++i)
-            near |= (q_k0 + i < q_kend && r_abs(r_sub(ax, qx[i])) <= margin && r_abs(r_sub(ay, qy[i])) <= margin ? 1u : 0u) << i;
+            near |= (r_abs(r_sub(ax, qx[i])) <= margin && r_abs(r_sub(ay, qy[i])) <= margin ? 1u : 0u) << i;
+          near &= q_valid;
           if (near != 0) {
 #pragma unroll
             for (int i = 0; i < 4; ++i)
               if (near >> i & 1u)
-                near_push<T, W>(sh, words, cfg, q_el, ax, ay, qx[i], qy[i], q_k0 + i, stepping, want_obs, nb);
+                near_push<T, W>(sh, words, cfg, q_el, ax, ay, qx[i], qy[i], (q_dyn ? ks : 0) + 4 * q_jq + i, stepping,
+                                want_obs, nb);
           }
         }
         for (int slot = lt + kLaneThreads; slot < n_slot; slot += kLaneThreads) {   // more than 8 quads per environment
