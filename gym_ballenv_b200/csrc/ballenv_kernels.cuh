@@ -890,9 +890,10 @@ __device__ __forceinline__ long long load_action_index(const Params& p, long lon
 //               knows the answer from its own vote and runs ahead into the next step (state update, next agent
 //               move, outputs) while the obstacle threads, which SYNC here, finish the raster of this one.
 //   kBarRaster: split form of kBarDone, used when whole warps hold static quads only (they have no draws and no
-//               moves to do): those threads rasterise the near list, then SYNC here with each other and with the
-//               scalar warp's decision, and store the rows; the dynamic-quad threads SYNC on kBarDone for the decision
-//               alone and go straight to their next moves.  Counts: 32 + static threads / 32 + the other threads.
+//               moves to do).  Every obstacle thread rasterises its share of the near list; the static-quad threads
+//               then SYNC here (all rasters done, decision published: count = all 288) and store the rows, while the
+//               dynamic-quad threads only ARRIVE here, SYNC on kBarDone (count = 32 + their number) for the decision
+//               alone and go straight to their next moves.
 constexpr int kBarAgent = 1, kBarNear = 2, kBarDone = 3, kBarRaster = 4;
 __device__ __forceinline__ void bar_sync(int id) {
   asm volatile("barrier.sync %0, %1;" ::"r"(id), "n"(kBlock) : "memory");
@@ -1177,8 +1178,8 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
           else bar_arrive(kBarDone);
         } else {
           bar_arrive_n(kBarDone, 32 + kLaneThreads - n_store);
-          if (any_reset) bar_sync_n(kBarRaster, 32 + n_store);
-          else bar_arrive_n(kBarRaster, 32 + n_store);
+          if (any_reset) bar_sync(kBarRaster);
+          else bar_arrive(kBarRaster);
         }
 
         // ---- outputs of the step (the scalar warp is past the barrier: nobody waits for these), next state
@@ -1377,13 +1378,15 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
           if (want_obs) raster_list<T, W>(sh, words, cfg, lt, nb, t & 1);
           BALLENV_STAMP(tr >= 0, tr + 5);
           bar_sync(kBarDone);
-        } else if (lt < n_store) {
-          if (want_obs) raster_list<T, W>(sh, words, cfg, lt, nb, t & 1, n_store);
-          BALLENV_STAMP(tr >= 0, tr + 5);
-          bar_sync_n(kBarRaster, 32 + n_store);
         } else {
+          if (want_obs) raster_list<T, W>(sh, words, cfg, lt, nb, t & 1);   // everybody takes a share of the list
           BALLENV_STAMP(tr >= 0, tr + 5);
-          bar_sync_n(kBarDone, 32 + kLaneThreads - n_store);
+          if (lt < n_store) {
+            bar_sync(kBarRaster);    // storing threads: the whole raster and the decision
+          } else {
+            bar_arrive(kBarRaster);  // the others: their share is done; they wait for the decision alone
+            bar_sync_n(kBarDone, 32 + kLaneThreads - n_store);
+          }
         }
         BALLENV_STAMP(tr >= 0, tr + 6);
         if (lt == 0) sh.count = 0;   // the near list of the step is consumed (the next pushes come after kBarAgent)
