@@ -582,7 +582,13 @@ __device__ __forceinline__ uint32_t stream_bits(const uint32_t* words, int bit, 
 // kThreads storing threads, a multiple of 8: thread tid always expands nibble (tid & 7) of the words tid / 8 +
 // k * kThreads / 8, so the shift is loop-invariant: rotate the nibble to bits 4..7 (= its byte offset in the
 // table), mask, load the float4, store.  A full block (32 environments) of a compile-time window unrolls completely.
-template <int W, int kThreads>
+template <bool kStream>
+__device__ __forceinline__ void put_row4(float4* d, const float4& v) {
+  if (kStream) __stcs(d, v);   // global rollout buffer: not re-read by this kernel
+  else *d = v;                 // shared-memory staging
+}
+
+template <int W, int kThreads, bool kStream = true>
 __device__ __forceinline__ void store_rows_f32(float4* dst, const uint32_t* words, const float4* lut, int nvec,
                                                int tid) {
   static_assert(kThreads % 8 == 0, "the nibble a thread expands must not depend on the iteration");
@@ -607,16 +613,17 @@ __device__ __forceinline__ void store_rows_f32(float4* dst, const uint32_t* word
         if (k0 + j < kIter) v[j] = *reinterpret_cast<const float4*>(lutb + (__funnelshift_r(wd[j], wd[j], rot) & 0xf0u));
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        if (k0 + j < kIter) __stcs(d + (k0 + j) * kThreads, v[j]);
+        if (k0 + j < kIter) put_row4<kStream>(d + (k0 + j) * kThreads, v[j]);
     }
     if (kTail != 0 && tid < kTail) {
       const uint32_t wd = wp[kIter * (kThreads / 8)];
-      __stcs(d + kIter * kThreads, *reinterpret_cast<const float4*>(lutb + (__funnelshift_r(wd, wd, rot) & 0xf0u)));
+      put_row4<kStream>(d + kIter * kThreads,
+                        *reinterpret_cast<const float4*>(lutb + (__funnelshift_r(wd, wd, rot) & 0xf0u)));
     }
   } else {
     for (int v = tid; v < nvec; v += kThreads, wp += kThreads / 8, d += kThreads) {
       const uint32_t wd = *wp;
-      __stcs(d, *reinterpret_cast<const float4*>(lutb + (__funnelshift_r(wd, wd, rot) & 0xf0u)));
+      put_row4<kStream>(d, *reinterpret_cast<const float4*>(lutb + (__funnelshift_r(wd, wd, rot) & 0xf0u)));
     }
   }
 }
@@ -894,7 +901,8 @@ __device__ __forceinline__ long long load_action_index(const Params& p, long lon
 //               then SYNC here (all rasters done, decision published: count = all 288) and store the rows, while the
 //               dynamic-quad threads only ARRIVE here, SYNC on kBarDone (count = 32 + their number) for the decision
 //               alone and go straight to their next moves.
-constexpr int kBarAgent = 1, kBarNear = 2, kBarDone = 3, kBarRaster = 4;
+//   kBarStore : the storing threads among themselves: the staged rows of the step are complete (bulk store below).
+constexpr int kBarAgent = 1, kBarNear = 2, kBarDone = 3, kBarRaster = 4, kBarStore = 5;
 __device__ __forceinline__ void bar_sync(int id) {
   asm volatile("barrier.sync %0, %1;" ::"r"(id), "n"(kBlock) : "memory");
 }
@@ -915,6 +923,23 @@ __device__ __forceinline__ bool bar_or(int id, bool pred) {
       : "r"(id), "r"(pred ? 1 : 0), "n"(kBlock)
       : "memory");
   return r != 0;
+}
+
+// ---- bulk store of a block's rows (TMA, cp.async.bulk shared -> global) -----------------------------------------------
+// The rows a block produces in one step are one contiguous, 16-byte aligned span of the rollout buffer.  Instead of
+// 13 (WINDOW = 10) dependent 128-bit global stores per storing thread, those threads expand the bits into a
+// shared-memory staging buffer and one of them hands the whole span to the copy engine; that thread makes sure
+// the engine has read the buffer (wait_group.read) before it arrives at the next step's agent barrier, behind which
+// the buffer is written again.
+__device__ __forceinline__ void bulk_store_rows(void* gmem, const void* smem, uint32_t bytes) {
+  const uint32_t src = (uint32_t)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem), "r"(src), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_fence_smem_writes() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+template <int kPending>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kPending) : "memory");
 }
 
 // ---- the kernel -----------------------------------------------------------------------------------------------------
@@ -960,9 +985,15 @@ __device__ __forceinline__ char* obs_block(const Params& p, long long e0, int t)
          ((size_t)(kRollout ? t : 0) * (size_t)p.obs_step_bytes + (size_t)e0 * (size_t)p.obs_row_bytes);
 }
 
+__device__ __forceinline__ long long e0_ll(unsigned block) { return (long long)block * kEnvsPerBlock; }
+
 template <typename T, int W, bool kFast, bool kRollout>
 __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __grid_constant__ Params p) {
   __shared__ BlockShared<T, W> sh;
+  // staged rows of a step: rollout kernels with a compile-time window only (13 KB for WINDOW = 10).  One buffer:
+  // every kilobyte of shared memory is a kilobyte less L1, and the spilled loop state lives there.
+  constexpr int kStageVec = (kFast && kRollout && W > 0 && W <= 10) ? 8 * (4 + W * W) : 0;
+  __shared__ __align__(128) float4 stage[kStageVec > 0 ? kStageVec : 1];
   const DevConfig& cfg = p.cfg;
   const int tid = threadIdx.x;
   const long long e0 = (long long)blockIdx.x * kEnvsPerBlock;
@@ -976,6 +1007,10 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
   // two and not all of the warps, otherwise every obstacle thread; see kBarRaster
   const int n_store = (kRollout && p.n_stat >= 64 && p.n_stat < kLaneThreads) ? p.n_stat : kLaneThreads;
   const bool split = n_store != kLaneThreads;
+  // bulk store of the rows: full blocks whose span of every step is 16-byte aligned (n_store is 64 or 128 then)
+  const bool bulk = kStageVec > 0 && split && (n_store == 64 || n_store == 128) && p.n - e0_ll(blockIdx.x) >= kEnvsPerBlock &&
+                    ((reinterpret_cast<uintptr_t>(p.obs) + (size_t)e0_ll(blockIdx.x) * (size_t)p.obs_row_bytes) & 15) == 0 &&
+                    (p.obs_step_bytes & 15) == 0;
   if (p.debug & 1) return;
 
   if (tid < 32) {
@@ -1320,6 +1355,8 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
           else
             dynamic_move<T, W, false>(p, sh, e0 + q_el, q_jq, tick + (uint32_t)t, qx, qy, qm);
         }
+        // (the copy engine has had a move phase to read the staged rows of the previous step: free for the next)
+        if (kStageVec > 0 && bulk && lt == 0) bulk_wait_read<0>();
         BALLENV_STAMP(tr >= 0, tr + 1);
         bar_sync(kBarAgent);   // agent positions published; everybody is done with the previous step's bit-stream
         BALLENV_STAMP(tr >= 0, tr + 2);
@@ -1397,12 +1434,25 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
         // The observation rows are stored by the threads that have the least to do in a step: the static-quad
         // threads (no draws, no moves) when there are at least two warps of them, otherwise every obstacle thread.
         if (want_obs && !(p.debug & 8)) {
-          if (n_store == kLaneThreads)
+          if (kStageVec > 0 && bulk) {
+            if (lt < n_store) {
+              float4* st = stage;
+              if (n_store == 64) store_rows_f32<W, 64, false>(st, words, sh.lut, kStageVec, lt);
+              else store_rows_f32<W, 128, false>(st, words, sh.lut, kStageVec, lt);
+              bulk_fence_smem_writes();
+              bar_sync_n(kBarStore, n_store);
+              if (lt == 0) {
+                bulk_store_rows(obs_block<kRollout>(p, e0, t), st, (uint32_t)(kStageVec * sizeof(float4)));
+              }
+            }
+          } else if (n_store == kLaneThreads) {
             store_obs<W, kFast, true>(p, obs_block<kRollout>(p, e0, t), words, sh.lut, cnt_env, lt, kLaneThreads);
-          else if (lt < n_store)
+          } else if (lt < n_store) {
             store_obs<W, kFast, true>(p, obs_block<kRollout>(p, e0, t), words, sh.lut, cnt_env, lt, n_store);
+          }
         }
       }
+      if (kStageVec > 0 && bulk && lt == 0) bulk_wait_read<0>();   // nothing of this block's staging is still being read
 
       // ---- write the moved quads back (a pending reset then overwrites those of the environments that finished)
       if (q_have && q_dyn && stepping) dynamic_store<T>(p, q_off, qx, qy, qm);
