@@ -49,7 +49,9 @@ constexpr int kBlock = 32 + kLaneThreads;          // + warp 0, the scalar warp:
 #endif
 template <typename T>
 constexpr int kMinBlocks = sizeof(T) == 4 ? BALLENV_MINBLOCKS : 2; // resident blocks per SM the register budget is held to
-constexpr int kListCap = 768;                      // near-obstacle list entries per block (overflow: in-lane raster)
+// near-obstacle list entries per block (typically one or two are in use; a longer list only takes L1 away from the
+// spilled loop state: 768 -> 192 measured 1 % faster for C3); overflow is rasterised in-lane
+constexpr int kListCap = 192;
 constexpr int kMaxResetAttempts = 4096;            // the reference would loop forever on an unsatisfiable layout
 constexpr int kNoHit = 0x7fffffff;
 

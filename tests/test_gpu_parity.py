@@ -572,3 +572,27 @@ def test_integer_sqrt_shortcut_is_exact():
     rc = L.LIB.ballenv_selftest(0, 1 << 22, 0, C.byref(bad))
     assert rc == 0, L.LIB.ballenv_last_error()
     assert bad.value == 0, "%d of 2^22 arguments differ from sqrt()" % bad.value
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("parity", [False, True])
+def test_near_list_overflow(parity):
+    """Every obstacle of every environment inside the agent's window: 32 x 32 = 1024 near obstacles per block, more
+    than the shared-memory near list holds, so the in-thread raster of the overflow path produces part of the rows."""
+    from gym_ballenv_b200 import BallVecEnv, EnvConfig
+    from oracle.ballenv_oracle import window_obs
+    n, k, w = 64, 32, 10
+    rng = np.random.RandomState(3)
+    agent = rng.randint(60, 440, size=(n, 2)).astype(np.float64)
+    goal = rng.randint(0, 500, size=(n, 2)).astype(np.float64)
+    obst = agent[:, None, :] + rng.randint(-30, 31, size=(n, k, 2))
+    cfg = EnvConfig(static_obstacles=k, dynamic_obstacles=0, obstacle_speed=(), obs_goal_position=())
+    env = BallVecEnv(n, window=w, config=cfg, parity=parity, auto_reset=False, max_episode_steps=0)
+    env.set_state(agent_x=agent[:, 0], agent_y=agent[:, 1], goal_x=goal[:, 0], goal_y=goal[:, 1],
+                  static_x=obst[:, :, 0].T, static_y=obst[:, :, 1].T)
+    obs = env.observe().cpu().numpy()
+    for e in range(n):
+        exp = window_obs(tuple(agent[e]), tuple(goal[e]), [tuple(o) for o in obst[e]], w)
+        assert np.array_equal(obs[e], np.asarray(exp, dtype=obs.dtype)), e
+    assert env.error_flags() == 0
+    env.close()
