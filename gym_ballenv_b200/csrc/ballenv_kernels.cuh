@@ -47,8 +47,10 @@ constexpr int kBlock = 32 + kLaneThreads;          // + warp 0, the scalar warp:
 #ifndef BALLENV_MINBLOCKS
 #define BALLENV_MINBLOCKS 4
 #endif
-template <typename T>
-constexpr int kMinBlocks = sizeof(T) == 4 ? BALLENV_MINBLOCKS : 2; // resident blocks per SM the register budget is held to
+// resident blocks per SM the register budget is held to; kLW = obstacle warps of the block (8, or 6 for
+// configurations of at most six quads per environment: 224 threads, five blocks at the same 56 registers)
+template <typename T, int kLW = kLanes>
+constexpr int kMinBlocks = sizeof(T) == 4 ? (kLW == 6 ? 5 : BALLENV_MINBLOCKS) : 2;
 // near-obstacle list entries per block (typically one or two are in use; a longer list only takes L1 away from the
 // spilled loop state: 768 -> 192 measured 1 % faster for C3); overflow is rasterised in-lane
 constexpr int kListCap = 192;
@@ -779,7 +781,7 @@ __device__ __forceinline__ int div_slot(int slot, uint32_t rcp) {
 // The observation of a finished environment thereby becomes the first observation of its next episode.
 template <typename T, int W>
 __device__ __noinline__ void reset_stage(const Params& p, BlockShared<T, W>& sh, uint32_t* words, long long e0,
-                                         int cnt_env, bool want_obs, int par) {
+                                         int cnt_env, bool want_obs, int par, int nlt) {
   const DevConfig& cfg = p.cfg;
   const int tid = threadIdx.x;
   const bool is_scalar = tid < 32;
@@ -841,7 +843,7 @@ __device__ __noinline__ void reset_stage(const Params& p, BlockShared<T, W>& sh,
     int kbits = 0;
     while ((1 << kbits) < K) ++kbits;
     const int items = sh.nreset << kbits;
-    for (int it = lt; it < items; it += kLaneThreads) {
+    for (int it = lt; it < items; it += nlt) {
       const int k = it & ((1 << kbits) - 1);
       if (k >= K) continue;
       const int el = sh.rlist[it >> kbits];
@@ -872,7 +874,7 @@ __device__ __noinline__ void reset_stage(const Params& p, BlockShared<T, W>& sh,
     }
   }
   __syncthreads();
-  if (!is_scalar && want_obs) raster_list<T, W>(sh, words, cfg, lt, nb, par);
+  if (!is_scalar && want_obs) raster_list<T, W>(sh, words, cfg, lt, nb, par, nlt);
   __syncthreads();
   if (tid == 0) sh.count = 0;   // the list is consumed; the step loop's next pushes come after its kBarAgent
 }
@@ -905,11 +907,13 @@ __device__ __forceinline__ long long load_action_index(const Params& p, long lon
 //               alone and go straight to their next moves.
 //   kBarStore : the storing threads among themselves: the staged rows of the step are complete (bulk store below).
 constexpr int kBarAgent = 1, kBarNear = 2, kBarDone = 3, kBarRaster = 4, kBarStore = 5;
+template <int kCount = kBlock>
 __device__ __forceinline__ void bar_sync(int id) {
-  asm volatile("barrier.sync %0, %1;" ::"r"(id), "n"(kBlock) : "memory");
+  asm volatile("barrier.sync %0, %1;" ::"r"(id), "n"(kCount) : "memory");
 }
+template <int kCount = kBlock>
 __device__ __forceinline__ void bar_arrive(int id) {
-  asm volatile("barrier.arrive %0, %1;" ::"r"(id), "n"(kBlock) : "memory");
+  asm volatile("barrier.arrive %0, %1;" ::"r"(id), "n"(kCount) : "memory");
 }
 __device__ __forceinline__ void bar_sync_n(int id, int count) {
   asm volatile("barrier.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
@@ -989,8 +993,10 @@ __device__ __forceinline__ char* obs_block(const Params& p, long long e0, int t)
 
 __device__ __forceinline__ long long e0_ll(unsigned block) { return (long long)block * kEnvsPerBlock; }
 
-template <typename T, int W, bool kFast, bool kRollout>
-__global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __grid_constant__ Params p) {
+template <typename T, int W, bool kFast, bool kRollout, int kLW = kLanes>
+__global__ void __launch_bounds__(32 + 32 * kLW, kMinBlocks<T, kLW>) ballenv_kernel(const __grid_constant__ Params p) {
+  constexpr int kLT = 32 * kLW;   // obstacle threads of this instantiation (kLaneThreads = 256 by default)
+  constexpr int kB = 32 + kLT;    // block size
   __shared__ BlockShared<T, W> sh;
   // staged rows of a step: rollout kernels with a compile-time window only (13 KB for WINDOW = 10).  One buffer:
   // every kilobyte of shared memory is a kilobyte less L1, and the spilled loop state lives there.
@@ -1007,8 +1013,8 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
   const int n_steps = kRollout ? p.n_steps : 1;
   // threads that store the observation rows: the static-quad threads (no draws, no moves) when they are at least
   // two and not all of the warps, otherwise every obstacle thread; see kBarRaster
-  const int n_store = (kRollout && p.n_stat >= 64 && p.n_stat < kLaneThreads) ? p.n_stat : kLaneThreads;
-  const bool split = n_store != kLaneThreads;
+  const int n_store = (kRollout && p.n_stat >= 64 && p.n_stat < kLT) ? p.n_stat : kLT;
+  const bool split = n_store != kLT;
   // bulk store of the rows: full blocks whose span of every step is 16-byte aligned (n_store is 64 or 128 then)
   const bool bulk = kStageVec > 0 && split && (n_store == 64 || n_store == 128) && p.n - e0_ll(blockIdx.x) >= kEnvsPerBlock &&
                     ((reinterpret_cast<uintptr_t>(p.obs) + (size_t)e0_ll(blockIdx.x) * (size_t)p.obs_row_bytes) & 15) == 0 &&
@@ -1150,7 +1156,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
           atomicOr(&words[b >> 5], 1u << (b & 31));
         }
         BALLENV_STAMP(tid == 0, 1);
-        bar_arrive(kBarAgent);
+        bar_arrive<kB>(kBarAgent);
 
         // ---- while the obstacle threads move and test: distance, progress reward, goal and time-limit flags of
         //      this step (ballenv_env.py:268-286, 200-206 | ballenv_pygame.py:652-706)
@@ -1174,7 +1180,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
           }
         }
         BALLENV_STAMP(tid == 0, 2);
-        bar_sync(kBarNear);
+        bar_sync<kB>(kBarNear);
         BALLENV_STAMP(tid == 0, 3);
 
         // ---- critical: apply the hits, decide the resets
@@ -1211,12 +1217,12 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
         if (tid == 0) sh.any_reset = any_reset ? 1 : 0;
         BALLENV_STAMP(tid == 0, 4);
         if (!split) {
-          if (any_reset) bar_sync(kBarDone);   // the reset stage rewrites what the raster of this step still reads
-          else bar_arrive(kBarDone);
+          if (any_reset) bar_sync<kB>(kBarDone);   // the reset stage rewrites what the raster of this step still reads
+          else bar_arrive<kB>(kBarDone);
         } else {
-          bar_arrive_n(kBarDone, 32 + kLaneThreads - n_store);
-          if (any_reset) bar_sync(kBarRaster);
-          else bar_arrive(kBarRaster);
+          bar_arrive_n(kBarDone, 32 + kLT - n_store);
+          if (any_reset) bar_sync<kB>(kBarRaster);
+          else bar_arrive<kB>(kBarRaster);
         }
 
         // ---- outputs of the step (the scalar warp is past the barrier: nobody waits for these), next state
@@ -1272,9 +1278,9 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
         // (rare) the step that is being finished is t: reset, then its observation
         const bool want_obs = kFast ? (p.obs_all_steps != 0 || t == n_steps - 1) : p.obs != nullptr;
         uint32_t* words = sh.words[t & 1];
-        reset_stage<T, W>(p, sh, words, e0, cnt_env, want_obs, t & 1);
+        reset_stage<T, W>(p, sh, words, e0, cnt_env, want_obs, t & 1, kLT);
         if (want_obs && !(p.debug & 8))
-          store_obs<W, kFast>(p, obs_block<kRollout>(p, e0, t), words, sh.lut, cnt_env, tid, kBlock);
+          store_obs<W, kFast>(p, obs_block<kRollout>(p, e0, t), words, sh.lut, cnt_env, tid, kB);
         reset_req = false;
         if (++t >= n_steps) break;
       }
@@ -1314,7 +1320,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
     }
     // block setup shared by the obstacle threads: cleared bit-stream; goal and move tables.  Every warp writes the
     // (identical) table entries it is going to read, so a warp-level sync is all the moves below need.
-    for (int i = lt; i < nb; i += kLaneThreads) sh.words[0][i] = 0;
+    for (int i = lt; i < nb; i += kLT) sh.words[0][i] = 0;
     if (lt == 0) sh.count = 0;
     {
       const int l32 = tid & 31;
@@ -1360,10 +1366,10 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
         // (the copy engine has had a move phase to read the staged rows of the previous step: free for the next)
         if (kStageVec > 0 && bulk && lt == 0) bulk_wait_read<0>();
         BALLENV_STAMP(tr >= 0, tr + 1);
-        bar_sync(kBarAgent);   // agent positions published; everybody is done with the previous step's bit-stream
+        bar_sync<kB>(kBarAgent);   // agent positions published; everybody is done with the previous step's bit-stream
         BALLENV_STAMP(tr >= 0, tr + 2);
         if (t + 1 < n_steps)
-          for (int i = lt; i < nb; i += kLaneThreads) sh.words[(t + 1) & 1][i] = 0;
+          for (int i = lt; i < nb; i += kLT) sh.words[(t + 1) & 1][i] = 0;
 
         // bounding-box test every obstacle against the agent; near ones are hit-tested and queued
         if (q_have && !(p.debug & 4)) {
@@ -1381,7 +1387,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
                                 want_obs, nb);
           }
         }
-        for (int slot = lt + kLaneThreads; slot < n_slot; slot += kLaneThreads) {   // more than 8 quads per environment
+        for (int slot = lt + kLT; slot < n_slot; slot += kLT) {   // more than 8 quads per environment
           const bool dyn = slot >= n_stat;
           const int sl = dyn ? slot - n_stat : slot;
           const int per = dyn ? qd : qs;
@@ -1409,22 +1415,22 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
               near_test<T, W>(sh, words, cfg, el, ax, ay, margin, x[i], y[i], k0 + i, stepping, want_obs, nb);
         }
         BALLENV_STAMP(tr >= 0, tr + 3);
-        bar_sync(kBarNear);
+        bar_sync<kB>(kBarNear);
         BALLENV_STAMP(tr >= 0, tr + 4);
 
         // cooperative raster of the near list, then the reset decision (see kBarRaster)
         if (!split) {
-          if (want_obs) raster_list<T, W>(sh, words, cfg, lt, nb, t & 1);
+          if (want_obs) raster_list<T, W>(sh, words, cfg, lt, nb, t & 1, kLT);
           BALLENV_STAMP(tr >= 0, tr + 5);
-          bar_sync(kBarDone);
+          bar_sync<kB>(kBarDone);
         } else {
-          if (want_obs) raster_list<T, W>(sh, words, cfg, lt, nb, t & 1);   // everybody takes a share of the list
+          if (want_obs) raster_list<T, W>(sh, words, cfg, lt, nb, t & 1, kLT);   // everybody takes a share of the list
           BALLENV_STAMP(tr >= 0, tr + 5);
           if (lt < n_store) {
-            bar_sync(kBarRaster);    // storing threads: the whole raster and the decision
+            bar_sync<kB>(kBarRaster);    // storing threads: the whole raster and the decision
           } else {
-            bar_arrive(kBarRaster);  // the others: their share is done; they wait for the decision alone
-            bar_sync_n(kBarDone, 32 + kLaneThreads - n_store);
+            bar_arrive<kB>(kBarRaster);  // the others: their share is done; they wait for the decision alone
+            bar_sync_n(kBarDone, 32 + kLT - n_store);
           }
         }
         BALLENV_STAMP(tr >= 0, tr + 6);
@@ -1447,8 +1453,8 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
                 bulk_store_rows(obs_block<kRollout>(p, e0, t), st, (uint32_t)(kStageVec * sizeof(float4)));
               }
             }
-          } else if (n_store == kLaneThreads) {
-            store_obs<W, kFast, true>(p, obs_block<kRollout>(p, e0, t), words, sh.lut, cnt_env, lt, kLaneThreads);
+          } else if (n_store == kLT) {
+            store_obs<W, kFast, true>(p, obs_block<kRollout>(p, e0, t), words, sh.lut, cnt_env, lt, kLT);
           } else if (lt < n_store) {
             store_obs<W, kFast, true>(p, obs_block<kRollout>(p, e0, t), words, sh.lut, cnt_env, lt, n_store);
           }
@@ -1462,9 +1468,9 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks<T>) ballenv_kernel(const __
       {
         const bool want_obs = kFast ? (p.obs_all_steps != 0 || t == n_steps - 1) : p.obs != nullptr;
         uint32_t* words = sh.words[t & 1];
-        reset_stage<T, W>(p, sh, words, e0, cnt_env, want_obs, t & 1);
+        reset_stage<T, W>(p, sh, words, e0, cnt_env, want_obs, t & 1, kLT);
         if (want_obs && !(p.debug & 8))
-          store_obs<W, kFast>(p, obs_block<kRollout>(p, e0, t), words, sh.lut, cnt_env, tid, kBlock);
+          store_obs<W, kFast>(p, obs_block<kRollout>(p, e0, t), words, sh.lut, cnt_env, tid, kB);
         if (!kFast && lt < n_slot) q_have = q_el < cnt_env;   // Reset mode: the environment has state now
         if (++t >= n_steps) break;
       }
