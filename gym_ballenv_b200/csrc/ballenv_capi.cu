@@ -211,8 +211,16 @@ int launch(BallenvHandle* h, const Params& p_in, cudaStream_t s) {
   Params p = p_in;   // + the constants the kernels would otherwise derive per step
   p.obs_row_bytes = (long long)p.cfg.obs_row_elems * (p.cfg.obs_format == BALLENV_OBS_U8 ? 1 : 4);
   p.obs_step_bytes = (p.n_steps > 1 && p.obs_all_steps) ? p.n * p.obs_row_bytes : 0;
-  p.n_stat = kEnvsPerBlock * ((p.cfg.ks + 3) / 4);
-  p.n_slot = p.n_stat + kEnvsPerBlock * ((p.cfg.kd + 3) / 4);
+  {
+    // obstacle threads of a block: one per quad.  In the fast single-step kernel a static-quad thread takes two
+    // quads when that makes the block fit 4 obstacle warps (kernel parameter kSQ = 2: seven resident blocks; measured
+    // 16.4 -> 15.0 us per launch for the reference's default 13 + 5 obstacles).  Not for rollouts, and not for C3
+    // (one static warp instead of two becomes the long pole of the step: 9.1 -> 10.2 us, measured).
+    const int qs = (p.cfg.ks + 3) / 4, qd = (p.cfg.kd + 3) / 4;
+    p.sq = (fast_eligible(h, p) && p.n_steps == 1 && (qs == 2 || qs == 4) && qs / 2 + qd <= 4) ? 2 : 1;
+    p.n_stat = kEnvsPerBlock * (qs / p.sq);
+    p.n_slot = p.n_stat + kEnvsPerBlock * qd;
+  }
   const unsigned grid = (unsigned)((p.n + kEnvsPerBlock - 1) / kEnvsPerBlock);
   const bool f64 = h->cfg.precision == BALLENV_F64;
   const bool fast = fast_eligible(h, p);

@@ -16,9 +16,9 @@ namespace ballenv {
 #if BALLENV_FAST
 // The rollout kernel stages its rows in shared memory (13 KB for WINDOW = 10): ask for the smallest carve-out that keeps
 // its resident blocks, and no more - the rest of the array is the L1 the spilled loop state lives in.
-template <int kLW>
+template <int kLW, int kSQ>
 static void launch_rollout(const Params& p, unsigned grid, cudaStream_t s) {
-  auto kern = ballenv_kernel<BALLENV_T, BALLENV_W, true, true, kLW>;
+  auto kern = ballenv_kernel<BALLENV_T, BALLENV_W, true, true, kLW, kSQ>;
   static int carveout = -1;
   if (carveout < 0) {
     cudaFuncAttributes fa;
@@ -30,20 +30,25 @@ static void launch_rollout(const Params& p, unsigned grid, cudaStream_t s) {
   cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carveout);
   kern<<<grid, 32 + 32 * kLW, 0, s>>>(p);
 }
+template <int kLW, int kSQ>
+static void launch_fast(const Params& p, unsigned grid, cudaStream_t s) {
+  if (p.n_steps > 1) launch_rollout<kLW, kSQ>(p, grid, s);
+  else ballenv_kernel<BALLENV_T, BALLENV_W, true, false, kLW, kSQ><<<grid, 32 + 32 * kLW, 0, s>>>(p);
+}
 #endif
 
 void BALLENV_NAME(const Params& p, unsigned grid, cudaStream_t s) {
 #if BALLENV_FAST
-  // at most six quads per environment (the reference's default 13 + 5 obstacles): blocks of 6 obstacle warps, five
-  // of them resident per SM instead of four
-  const bool six = p.n_slot <= 6 * kEnvsPerBlock;
-  if (p.n_steps > 1) {
-    if (six) launch_rollout<6>(p, grid, s);
-    else launch_rollout<kLanes>(p, grid, s);
-  } else if (six) {
-    ballenv_kernel<BALLENV_T, BALLENV_W, true, false, 6><<<grid, 32 + 32 * 6, 0, s>>>(p);
+  // The smallest block that holds the configuration's obstacle threads: more resident blocks hide more of a step's
+  // phase chain.  6 obstacle warps for at most six quads per environment, else 8; p.sq = 2 (ballenv_capi.cu: launch,
+  // single-step launches of small configurations only): a static-quad thread takes two quads, 4 obstacle warps.
+  const int warps = (p.n_slot + 31) / 32;
+  if (p.sq == 2 && p.n_steps == 1 && warps <= 4) {
+    ballenv_kernel<BALLENV_T, BALLENV_W, true, false, 4, 2><<<grid, 32 + 32 * 4, 0, s>>>(p);
+  } else if (warps <= 6) {
+    launch_fast<6, 1>(p, grid, s);
   } else {
-    ballenv_kernel<BALLENV_T, BALLENV_W, true, false><<<grid, kBlock, 0, s>>>(p);
+    launch_fast<kLanes, 1>(p, grid, s);
   }
 #else
   ballenv_kernel<BALLENV_T, BALLENV_W, false, false><<<grid, kBlock, 0, s>>>(p);

@@ -50,7 +50,7 @@ constexpr int kBlock = 32 + kLaneThreads;          // + warp 0, the scalar warp:
 // resident blocks per SM the register budget is held to; kLW = obstacle warps of the block (8, or 6 for
 // configurations of at most six quads per environment: 224 threads, five blocks at the same 56 registers)
 template <typename T, int kLW = kLanes>
-constexpr int kMinBlocks = sizeof(T) == 4 ? (kLW == 6 ? 5 : BALLENV_MINBLOCKS) : 2;
+constexpr int kMinBlocks = sizeof(T) == 4 ? (kLW == 6 ? 5 : kLW == 4 ? 7 : BALLENV_MINBLOCKS) : 2;
 // near-obstacle list entries per block (typically one or two are in use; a longer list only takes L1 away from the
 // spilled loop state: 768 -> 192 measured 1 % faster for C3); overflow is rasterised in-lane
 constexpr int kListCap = 192;
@@ -113,7 +113,8 @@ struct Params {
   // derived per launch by the host (ballenv_capi.cu: launch) so that the step loop re-reads one constant instead of
   // recomputing it when registers are short
   long long obs_row_bytes, obs_step_bytes;   // bytes of one observation row; of one step's rows ([T][n][row]) or 0
-  int n_stat, n_slot;                        // static / all quad slots of a block (32 environments)
+  int n_stat, n_slot;                        // static-quad threads / all busy obstacle threads of a block (32 environments)
+  int sq;                                    // static quads per static-quad thread: 1, or 2 (kernels instantiated with kSQ = 2)
   void *agent_x, *agent_y, *goal_x, *goal_y;
   double *dist, *total, *acc;
   int *ep_len;
@@ -993,10 +994,17 @@ __device__ __forceinline__ char* obs_block(const Params& p, long long e0, int t)
 
 __device__ __forceinline__ long long e0_ll(unsigned block) { return (long long)block * kEnvsPerBlock; }
 
-template <typename T, int W, bool kFast, bool kRollout, int kLW = kLanes>
+// kSQ = 2 (fast single-step kernel, two or four static quads per environment): a static-quad thread tests TWO quads
+// of its environment against the agent and keeps their (constant) coordinates in shared memory instead of
+// registers, so the reference's default 13 + 5 obstacles fit blocks of 5 warps (kLW = 4, seven blocks per SM).
+// In the rollout loop, and for C3, halving the static-quad threads makes them the long pole of the step (measured
+// slower), so the host only selects it for single-step launches of small configurations.
+template <typename T, int W, bool kFast, bool kRollout, int kLW = kLanes, int kSQ = 1>
 __global__ void __launch_bounds__(32 + 32 * kLW, kMinBlocks<T, kLW>) ballenv_kernel(const __grid_constant__ Params p) {
   constexpr int kLT = 32 * kLW;   // obstacle threads of this instantiation (kLaneThreads = 256 by default)
   constexpr int kB = 32 + kLT;    // block size
+  constexpr bool kS2 = kSQ == 2;
+  __shared__ __align__(16) T ssx[kS2 ? 64 * 8 : 4], ssy[kS2 ? 64 * 8 : 4];   // static quads of up to 64 threads
   __shared__ BlockShared<T, W> sh;
   // staged rows of a step: rollout kernels with a compile-time window only (13 KB for WINDOW = 10).  One buffer:
   // every kilobyte of shared memory is a kilobyte less L1, and the spilled loop state lives there.
@@ -1013,10 +1021,10 @@ __global__ void __launch_bounds__(32 + 32 * kLW, kMinBlocks<T, kLW>) ballenv_ker
   const int n_steps = kRollout ? p.n_steps : 1;
   // threads that store the observation rows: the static-quad threads (no draws, no moves) when they are at least
   // two and not all of the warps, otherwise every obstacle thread; see kBarRaster
-  const int n_store = (kRollout && p.n_stat >= 64 && p.n_stat < kLT) ? p.n_stat : kLT;
+  const int n_store = (kRollout && p.n_stat >= (kS2 ? 32 : 64) && p.n_stat < kLT) ? p.n_stat : kLT;
   const bool split = n_store != kLT;
   // bulk store of the rows: full blocks whose span of every step is 16-byte aligned (n_store is 64 or 128 then)
-  const bool bulk = kStageVec > 0 && split && (n_store == 64 || n_store == 128) && p.n - e0_ll(blockIdx.x) >= kEnvsPerBlock &&
+  const bool bulk = kStageVec > 0 && split && (n_store == 32 || n_store == 64 || n_store == 128) && p.n - e0_ll(blockIdx.x) >= kEnvsPerBlock &&
                     ((reinterpret_cast<uintptr_t>(p.obs) + (size_t)e0_ll(blockIdx.x) * (size_t)p.obs_row_bytes) & 15) == 0 &&
                     (p.obs_step_bytes & 15) == 0;
   if (p.debug & 1) return;
@@ -1305,9 +1313,10 @@ __global__ void __launch_bounds__(32 + 32 * kLW, kMinBlocks<T, kLW>) ballenv_ker
     uint32_t q_valid = 0;      // which of the quad's four slots hold obstacles (the last quad of a kind may be padded)
     bool q_have = false;
     const bool q_dyn = lt >= n_stat;
-    const uint32_t q_off = q_dyn ? dyn0 + 4u * (uint32_t)(lt - n_stat) : stat0 + 4u * (uint32_t)lt;
+    const uint32_t q_off = q_dyn ? dyn0 + 4u * (uint32_t)(lt - n_stat) : stat0 + (kS2 ? 8u : 4u) * (uint32_t)lt;
     if (lt < n_slot) {
-      const int sl = q_dyn ? lt - n_stat : lt;          // slot within its kind
+      // slot within its kind; a static-quad thread of a kSQ = 2 kernel owns the quads 2 lt and 2 lt + 1 (qs is even)
+      const int sl = q_dyn ? lt - n_stat : (kS2 ? 2 * lt : lt);
       const int per = q_dyn ? qd : qs;
       q_el = div_slot(sl, q_dyn ? cfg.rcp_qd : cfg.rcp_qs);
       const int qq = sl - q_el * per;
@@ -1316,7 +1325,8 @@ __global__ void __launch_bounds__(32 + 32 * kLW, kMinBlocks<T, kLW>) ballenv_ker
         q_have = p.reset_mask == nullptr ? false : p.reset_mask[e0 + q_el] == 0;
       q_jq = qq;
       const int left = (q_dyn ? kd : ks) - 4 * qq;
-      q_valid = left >= 4 ? 15u : (1u << left) - 1u;
+      q_valid = left >= 4 ? 15u : (left > 0 ? (1u << left) - 1u : 0u);
+      if (kS2 && !q_dyn) q_valid |= (left >= 8 ? 15u : (left > 4 ? (1u << (left - 4)) - 1u : 0u)) << 4;
     }
     // block setup shared by the obstacle threads: cleared bit-stream; goal and move tables.  Every warp writes the
     // (identical) table entries it is going to read, so a warp-level sync is all the moves below need.
@@ -1340,6 +1350,15 @@ __global__ void __launch_bounds__(32 + 32 * kLW, kMinBlocks<T, kLW>) ballenv_ker
         if (!q_dyn) {
           load4(stat_x + q_off, qx);
           load4(stat_y + q_off, qy);
+          if (kS2) {   // both quads go to shared memory: they never change while the loop runs, and nothing stays in registers
+            T rx[4], ry[4];
+            load4(stat_x + q_off + 4, rx);
+            load4(stat_y + q_off + 4, ry);
+            store4(ssx + 8 * lt, qx);
+            store4(ssy + 8 * lt, qy);
+            store4(ssx + 8 * lt + 4, rx);
+            store4(ssy + 8 * lt + 4, ry);
+          }
         } else {
           if (stepping) tick = p.tick[e0 + q_el] - (uint32_t)t;   // tick of step 0 of this launch
           dynamic_load<T>(p, q_off, stepping, qx, qy, qm);
@@ -1372,7 +1391,26 @@ __global__ void __launch_bounds__(32 + 32 * kLW, kMinBlocks<T, kLW>) ballenv_ker
           for (int i = lt; i < nb; i += kLT) sh.words[(t + 1) & 1][i] = 0;
 
         // bounding-box test every obstacle against the agent; near ones are hit-tested and queued
-        if (q_have && !(p.debug & 4)) {
+        if (kS2 && q_have && !q_dyn && !(p.debug & 4)) {
+          const T ax = sh.ax[t & 1][q_el], ay = sh.ay[t & 1][q_el];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            T x[4], y[4];
+            load4(ssx + 8 * lt + 4 * h, x);
+            load4(ssy + 8 * lt + 4 * h, y);
+            uint32_t near = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              near |= (r_abs(r_sub(ax, x[i])) <= margin && r_abs(r_sub(ay, y[i])) <= margin ? 1u : 0u) << i;
+            near &= (q_valid >> (4 * h)) & 15u;
+            if (near != 0) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                if (near >> i & 1u)
+                  near_push<T, W>(sh, words, cfg, q_el, ax, ay, x[i], y[i], 4 * (q_jq + h) + i, stepping, want_obs, nb);
+            }
+          }
+        } else if (q_have && !(p.debug & 4)) {
           const T ax = sh.ax[t & 1][q_el], ay = sh.ay[t & 1][q_el];
           uint32_t near = 0;   // one branch for the quad: the four tests are almost always all false
 #pragma unroll
@@ -1445,7 +1483,8 @@ __global__ void __launch_bounds__(32 + 32 * kLW, kMinBlocks<T, kLW>) ballenv_ker
           if (kStageVec > 0 && bulk) {
             if (lt < n_store) {
               float4* st = stage;
-              if (n_store == 64) store_rows_f32<W, 64, false>(st, words, sh.lut, kStageVec, lt);
+              if (n_store == 32) store_rows_f32<W, 32, false>(st, words, sh.lut, kStageVec, lt);
+              else if (n_store == 64) store_rows_f32<W, 64, false>(st, words, sh.lut, kStageVec, lt);
               else store_rows_f32<W, 128, false>(st, words, sh.lut, kStageVec, lt);
               bulk_fence_smem_writes();
               bar_sync_n(kBarStore, n_store);
