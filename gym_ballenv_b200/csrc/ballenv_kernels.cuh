@@ -1049,8 +1049,8 @@ __global__ void __launch_bounds__(32 + 32 * kLW, kMinBlocks<T, kLW>) ballenv_ker
     if (tid < 16)
       sh.lut[tid] = make_float4(tid & 1 ? 1.0f : 0.0f, tid & 2 ? 1.0f : 0.0f, tid & 4 ? 1.0f : 0.0f, tid & 8 ? 1.0f : 0.0f);
 
-    __syncthreads();   // block setup done: the bit-stream of step 0 is cleared before anyone ORs into it
     int t = 0, t_fetch = 0;   // t_fetch: the step whose action has to be loaded directly (no fetch in flight)
+    bool setup_pending = true;
     for (;;) {
       // (re)load: at launch, and after a reset went through global memory
       if (mine) {
@@ -1067,6 +1067,10 @@ __global__ void __launch_bounds__(32 + 32 * kLW, kMinBlocks<T, kLW>) ballenv_ker
           len = p.ep_len[e];
           tick = p.tick[e];
         }
+      }
+      if (setup_pending) {   // the state loads above are in flight while the block finishes its setup
+        __syncthreads();     // block setup done: the bit-stream of step 0 is cleared before anyone ORs into it
+        setup_pending = false;
       }
       // Integral coordinates (what the gym ruleset produces: integer draws, unit steps) stay integral while the
       // loop runs, and the squared distance to the goal is then an exact small integer: sqrt_int22 applies.
@@ -1340,9 +1344,8 @@ __global__ void __launch_bounds__(32 + 32 * kLW, kMinBlocks<T, kLW>) ballenv_ker
       }
       for (int i = l32; i < cfg.n_goals; i += 32) sh.goal[i] = CfgV<T>::goal(cfg, i);
     }
-    __syncthreads();   // block setup done (pairs with the scalar warp's)
-
     int t = 0, t_load = 0;
+    bool setup_pending = true;
     for (;;) {
       // (re)load the quad: at launch, and after a reset went through global memory
       t_load = t;
@@ -1363,6 +1366,10 @@ __global__ void __launch_bounds__(32 + 32 * kLW, kMinBlocks<T, kLW>) ballenv_ker
           if (stepping) tick = p.tick[e0 + q_el] - (uint32_t)t;   // tick of step 0 of this launch
           dynamic_load<T>(p, q_off, stepping, qx, qy, qm);
         }
+      }
+      if (setup_pending) {   // the quad loads above are in flight while the block finishes its setup
+        __syncthreads();     // block setup done (pairs with the scalar warp's)
+        setup_pending = false;
       }
       bool pending_reset = false;
       // ------------------------------------------- hot loop: no calls inside -------------------------------------
