@@ -54,7 +54,7 @@ class BallenvStatePtrs(C.Structure):
 EXPORTS = (
     "ballenv_abi_version", "ballenv_last_error", "ballenv_config_default", "ballenv_state_bytes",
     "ballenv_create", "ballenv_destroy", "ballenv_state_ptrs", "ballenv_reset", "ballenv_step",
-    "ballenv_step_many", "ballenv_observe", "ballenv_observe_features", "ballenv_step_host", "ballenv_set_draw_tape", "ballenv_stats",
+    "ballenv_step_many", "ballenv_observe", "ballenv_observe_features", "ballenv_observe_blocks", "ballenv_step_host", "ballenv_set_draw_tape", "ballenv_stats",
     "ballenv_stats_reset", "ballenv_error_flags", "ballenv_launch_count", "ballenv_selftest",
 )
 
@@ -75,6 +75,7 @@ def _bind(lib):
     lib.ballenv_step_many.argtypes = [vp, vp, C.c_int, i32, vp, i32, vp, vp, vp]
     lib.ballenv_observe.argtypes = [vp, vp, vp]
     lib.ballenv_observe_features.argtypes = [vp, vp, vp]
+    lib.ballenv_observe_blocks.argtypes = [vp, vp, vp]
     lib.ballenv_step_host.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp]
     lib.ballenv_set_draw_tape.argtypes = [vp, vp, i64, vp, i64, i32]
     lib.ballenv_stats.argtypes = [vp, vp, vp]

@@ -542,6 +542,17 @@ int ballenv_observe_features(BallenvHandle* h, float* out, ballenv_stream_t stre
   return BALLENV_OK;
 }
 
+int ballenv_observe_blocks(BallenvHandle* h, float* out, ballenv_stream_t stream) {
+  if (h == nullptr || out == nullptr) return fail(BALLENV_EINVAL, "NULL argument");
+  DeviceGuard guard(h->device);
+  const unsigned grid = (unsigned)((h->n + 127) / 128);
+  if (h->cfg.precision == BALLENV_F64) ballenv_blocks_kernel<double><<<grid, 128, 0, (cudaStream_t)stream>>>(h->base, out);
+  else ballenv_blocks_kernel<float><<<grid, 128, 0, (cudaStream_t)stream>>>(h->base, out);
+  h->launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  return BALLENV_OK;
+}
+
 int ballenv_step(BallenvHandle* h, const void* actions, int action_kind, void* obs_out, void* reward_out,
                  uint8_t* done_out, ballenv_stream_t stream) {
   if (h == nullptr || actions == nullptr) return fail(BALLENV_EINVAL, "NULL argument");

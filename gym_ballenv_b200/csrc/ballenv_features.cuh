@@ -87,4 +87,54 @@ __global__ void __launch_bounds__(128) ballenv_features_kernel(const __grid_cons
   for (int i = 0; i < 5; ++i) o[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
 }
 
+// Legacy 29-float observation of the REINFORCE / imitation / supervised scripts: prep_state2 + block_to_arrpos of
+// examples/ball_env_reinforce.py:130-172 (the same function in ball_env_imitate.py and test_model.py; the shipped
+// path logs hold these vectors).  [0:4] goal-quadrant bits (:139-150); [4:29] a 5 x 5 grid of obstacle COUNTS in
+// 20-pixel blocks around the agent, row = y block, the agent's own cell (index 4 + 12) starting at 1 (:138).
+//   dx = agent_x - obstacle_x; block_x = sign(dx) * (dx - 10) // 20, likewise y, unless dx == 0 or dy == 0 -> (0, 0)
+//   (:153-158: dx > 0 gives floor((dx - 10) / 20), dx < 0 gives floor((|dx| + 10) / 20));
+//   counted if |block_x| < 3 and |block_y| < 3 at index 4 + 12 + 5 * block_y + block_x (:160-164, :169-172).
+// One thread per environment, obstacles in list order (static, then dynamic); a secondary observe mode.
+template <typename T>
+__global__ void __launch_bounds__(128) ballenv_blocks_kernel(const __grid_constant__ Params p, float* __restrict__ out) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= p.n) return;
+  const double ax = (double)reinterpret_cast<const T*>(p.agent_x)[e], ay = (double)reinterpret_cast<const T*>(p.agent_y)[e];
+  const double gx = (double)reinterpret_cast<const T*>(p.goal_x)[e], gy = (double)reinterpret_cast<const T*>(p.goal_y)[e];
+  float f[29];
+#pragma unroll
+  for (int i = 0; i < 29; ++i) f[i] = 0.0f;
+  f[12 + 4] = 1.0f;
+  const int q = goal_quadrant_bit(gx - ax < 0.0, gy - ay < 0.0);
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if (i == q) f[i] = 1.0f;
+  const int K = p.cfg.ks + p.cfg.kd;
+  for (int k = 0; k < K; ++k) {
+    double ox, oy;
+    if (k < p.cfg.ks) {
+      ox = (double)reinterpret_cast<const T*>(p.stat_x)[e * p.stat_stride + k];
+      oy = (double)reinterpret_cast<const T*>(p.stat_y)[e * p.stat_stride + k];
+    } else {
+      ox = (double)reinterpret_cast<const T*>(p.dyn_x)[e * p.dyn_stride + (k - p.cfg.ks)];
+      oy = (double)reinterpret_cast<const T*>(p.dyn_y)[e * p.dyn_stride + (k - p.cfg.ks)];
+    }
+    const double xd = ax - ox, yd = ay - oy;
+    double xb = 0.0, yb = 0.0;
+    if (xd != 0.0 && yd != 0.0) {
+      xb = floor((xd > 0.0 ? 1.0 : -1.0) * (xd - 10.0) / 20.0);
+      yb = floor((yd > 0.0 ? 1.0 : -1.0) * (yd - 10.0) / 20.0);
+    }
+    if (fabs(xb) < 3.0 && fabs(yb) < 3.0) {
+      const int pos = 4 + 12 + 5 * (int)yb + (int)xb;
+#pragma unroll
+      for (int i = 4; i < 29; ++i)   // registers, not a local array
+        if (i == pos) f[i] += 1.0f;
+    }
+  }
+  float* o = out + e * 29;
+#pragma unroll
+  for (int i = 0; i < 29; ++i) o[i] = f[i];
+}
+
 }  // namespace ballenv

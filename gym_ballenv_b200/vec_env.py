@@ -161,6 +161,14 @@ class BallVecEnv:
         check(LIB.ballenv_observe_features(self._h, C.c_void_p(out.data_ptr()), self._stream()))
         return out
 
+    def block_counts(self) -> torch.Tensor:
+        """The legacy 29-float observation of the REINFORCE / imitation scripts (``prep_state2`` of
+        examples/ball_env_reinforce.py:130-172): 4 goal-quadrant bits + a 5 x 5 grid of obstacle counts in 20-pixel
+        blocks around the agent.  float32 [N, 29] on the device, of the current state."""
+        out = torch.empty((self.num_envs, 29), dtype=torch.float32, device=self.device)
+        check(LIB.ballenv_observe_blocks(self._h, C.c_void_p(out.data_ptr()), self._stream()))
+        return out
+
     def _next_buf(self):
         self._flip ^= 1
         return self._bufs[self._flip]

@@ -206,6 +206,14 @@ int ballenv_observe(BallenvHandle *h, void *obs_out, ballenv_stream_t stream);
 int ballenv_observe_features(BallenvHandle *h, float *out, ballenv_stream_t stream);
 
 /*
+ * Replaces: prep_state2(state) of the REINFORCE / imitation / supervised scripts (examples/ball_env_reinforce.py:130-172
+ * with block_to_arrpos; the same function in ball_env_imitate.py and test_model.py) - the legacy 29-float observation:
+ * 4 goal-quadrant bits, then a 5 x 5 grid of obstacle counts in 20-pixel blocks around the agent (the agent's own
+ * cell starts at 1).  out : device float32 [n][29] of the CURRENT state.
+ */
+int ballenv_observe_blocks(BallenvHandle *h, float *out, ballenv_stream_t stream);
+
+/*
  * Same as ballenv_step but with HOST buffers (pinned or pageable): copies actions host->device, steps,
  * copies obs/reward/done device->host and synchronises `stream` before returning.  This is the call the
  * end-to-end number of bench.py is measured through.

@@ -429,3 +429,25 @@ def features20(agent, goal, obstacles, agent_rad=10, obstacle_rad=20, agent_vel=
         if fsoc > 1:                                                                   # :191-192
             f[17 + obin] += fsoc
     return f
+
+
+def blocks29(agent, goal, obstacles):
+    """-> list of 29 floats: the legacy observation of the REINFORCE / imitation scripts
+    (examples/ball_env_reinforce.py:130-172, prep_state2 + block_to_arrpos): 4 goal-quadrant bits, then a 5 x 5 grid
+    of obstacle COUNTS in 20-pixel blocks around the agent, the agent's own cell (index 4 + 12) starting at 1.
+
+    x_block = sign(dx) * (dx - 10) // 20 with dx = agent_x - obstacle_x (and the same for y) unless dx or dy is 0, in
+    which case both blocks are 0 (:153-157).  The formula is not symmetric: dx > 0 gives floor((dx - 10) / 20), dx < 0
+    gives floor((|dx| + 10) / 20) - obstacles to the right of the agent never land in a negative block."""
+    ref = [0.0] * 29
+    ref[12 + 4] = 1.0                                                                  # :138
+    ref[goal_quadrant(agent, goal)] = 1.0                                              # :139-150
+    for o in obstacles:                                                                # :152 (state[3:], list order)
+        xd, yd = agent[0] - o[0], agent[1] - o[1]
+        xb = yb = 0
+        if xd != 0 and yd != 0:                                                        # :156
+            xb = math.floor((1 if xd > 0 else -1) * (xd - 10) / 20)                   # :157
+            yb = math.floor((1 if yd > 0 else -1) * (yd - 10) / 20)                   # :158
+        if abs(xb) < 3 and abs(yb) < 3:                                                # :160
+            ref[4 + 12 + 5 * int(yb) + int(xb)] += 1.0                                 # :163-164, :169-172
+    return ref

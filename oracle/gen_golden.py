@@ -19,6 +19,7 @@ Fixture families
                         slot-addressed tapes (parity / tape mode).
   edge_gym.npz          hand-built single-step cases on injected states.
   window_kat.npz        RNG-free window-observation known answers (W=5,10,21).
+  blocks_kat.npz        legacy 29-float block-count observation of the REINFORCE scripts, 200 states.
 """
 from __future__ import annotations
 
@@ -307,6 +308,61 @@ def features_kats():
                 features=np.array(feats), meta=json.dumps(dict(K=K, n=len(agents), obstacle_rad=20)))
 
 
+def blocks_kats():
+    """States -> the legacy 29-float block-count observation (examples/ball_env_reinforce.py:130-172, lifted)."""
+    prep = R.load_legacy_block_state()
+    rng = np.random.RandomState(29)
+    K = 8
+    agents, goals, obsts, outs = [], [], [], []
+    for i in range(200):
+        if i % 5 == 4:     # non-integral coordinates (the pygame ruleset moves by floats)
+            agent = tuple(float(v) for v in rng.uniform(20, 480, 2).round(2))
+            goal = tuple(float(v) for v in rng.uniform(0, 500, 2).round(2))
+            ob = [tuple(float(v) for v in (np.array(agent) + rng.uniform(-75, 75, 2)).round(2)) for _ in range(K)]
+        else:
+            agent = tuple(int(v) for v in rng.randint(20, 480, 2))
+            goal = tuple(int(v) for v in rng.randint(0, 500, 2))
+            ob = [tuple(int(v) for v in (np.array(agent) + rng.randint(-75, 76, 2))) for _ in range(K)]
+        if i % 4 == 0:
+            ob[0] = (agent[0], agent[1] + 33)            # dx == 0: both blocks 0 whatever dy is
+            ob[1] = (agent[0] - 47, agent[1])            # dy == 0
+            ob[2] = (agent[0] - 10, agent[1] - 10)       # dx - 10 == 0 on the positive side
+            ob[3] = (agent[0] + 10, agent[1] + 50)       # |dx| + 10 == 20: block 1; |dy| + 10 == 60: block 3, outside
+            ob[4] = (agent[0] - 69, agent[1] - 70)       # (69 - 10) // 20 == 2 inside, (70 - 10) // 20 == 3 outside
+        if i == 3:
+            goal = agent
+        agents.append(agent); goals.append(goal); obsts.append(ob)
+        outs.append(np.asarray(prep([agent, goal, 0.0] + ob), np.float64))
+    return dict(agent=np.array(agents, np.float64), goal=np.array(goals, np.float64), obst=np.array(obsts, np.float64),
+                blocks=np.array(outs), meta=json.dumps(dict(K=K, n=len(agents),
+                made_by="oracle/gen_golden.py: prep_state2 of examples/ball_env_reinforce.py:130-172, AST-lifted")))
+
+
+def pathlog_kat():
+    """The head of the shipped demonstration log (examples/State_info_trail_no2 + Trial_no_2, Python 2 pickles) and
+    the labels examples/train_supervise.py:43-59 derives from its actions (restated here: that script is Python 2
+    syntax and cannot be lifted): action / 10 as a tuple -> its index in move_list, 8 if it is not there."""
+    import pickle
+    ex = os.path.join(R.REFERENCE_ROOT, "examples")
+    with open(os.path.join(ex, "State_info_trail_no2"), "rb") as f:
+        X = pickle.load(f, encoding="latin1")
+    with open(os.path.join(ex, "Trial_no_2"), "rb") as f:
+        Y = pickle.load(f, encoding="latin1")
+    move_list = [(1, 1), (1, -1), (1, 0), (0, 1), (0, -1), (0, 0), (-1, 1), (-1, 0), (-1, -1)]
+    labels = []
+    for a in Y:
+        tup = (int(a[0] // 10), int(a[1] // 10))
+        j = 8
+        for k in range(9):
+            if move_list[k] == tup:
+                j = k
+                break
+        labels.append(j)
+    n = 96
+    return dict(states=np.asarray(X[:n], np.float64), actions=np.asarray(Y[:n], np.int64), labels=np.asarray(labels[:n], np.int64),
+                meta=json.dumps(dict(n=n, total=len(X), label_histogram=np.bincount(labels, minlength=9).tolist())))
+
+
 def compress_rollout(out):
     """Shrink dtypes where the values are integral (checked)."""
     for k in list(out):
@@ -482,6 +538,8 @@ def main(argv):
         "rollout_philox_dense": lambda: compress_rollout(rollout(CFG_DENSE, 8, 120, 3, "philox", 1000, windows=(10,))),
         "rollout_mt_default": lambda: compress_rollout(rollout(CFG_DEFAULT, 8, 150, 0, "mt", 60)),
         "features_kat": lambda: features_kats(),
+        "blocks_kat": lambda: blocks_kats(),
+        "pathlog_kat": lambda: pathlog_kat(),
         "rollout_pygame": lambda: rollout_pygame(9, 12, 200, 21, g0=40),
     }
     only = set(argv[1:])

@@ -255,6 +255,24 @@ def load_prep_state(env, names=("prep_state2", "prep_state4")):
     return tuple(ns[n] for n in names)
 
 
+def load_legacy_block_state():
+    """AST-lift the legacy 29-float observation of examples/ball_env_reinforce.py:130-172 (prep_state2 + block_to_arrpos).
+    The script is Python 2: with integer coordinates ``x_dist/abs(x_dist)`` is an integer there and the array index
+    ``4+pos`` an int; under Python 3 the same expressions are floats and numpy refuses the index.  The lifted
+    ``block_to_arrpos`` is therefore wrapped in ``int()`` (the value is integral in both) - nothing else is touched."""
+    if "legacy" not in _loaded:
+        path = os.path.join(REFERENCE_ROOT, "examples", "ball_env_reinforce.py")
+        with open(path) as f:
+            tree = ast.parse(f.read(), path)
+        keep = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in ("prep_state2", "block_to_arrpos")]
+        ns = {"np": _np, "math": math}
+        exec(compile(ast.Module(body=keep, type_ignores=[]), path, "exec"), ns)
+        raw = ns["block_to_arrpos"]
+        ns["block_to_arrpos"] = lambda x, y: int(raw(x, y))
+        _loaded["legacy"] = ns["prep_state2"]
+    return _loaded["legacy"]
+
+
 def default_args(**over):
     """Defaults of examples/ball_cnn_ac3.py:40-51 as the Namespace the
     reference's customize_environment (ballenv_env.py:87-109) consumes."""

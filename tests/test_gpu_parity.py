@@ -596,3 +596,31 @@ def test_near_list_overflow(parity):
         assert np.array_equal(obs[e], np.asarray(exp, dtype=obs.dtype)), e
     assert env.error_flags() == 0
     env.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("parity", [True, False])
+def test_block_counts_kernel_against_the_reference_vectors(parity):
+    """ballenv_observe_blocks vs prep_state2 of examples/ball_env_reinforce.py for 200 injected states
+    (tests/golden/blocks_kat.npz): counts and one-hots, bit-exact (the non-integral fixtures are exact in fp32)."""
+    from gym_ballenv_b200 import BallVecEnv, EnvConfig
+    z, meta = load_golden("blocks_kat")
+    n, K = meta["n"], meta["K"]
+    half = K // 2   # first half static, second half dynamic: the count runs over both lists in order
+    cfg = EnvConfig(static_obstacles=half, dynamic_obstacles=K - half, obstacle_speed=(1,) * (K - half),
+                    obs_goal_position=tuple("%d,%d" % (10 + 7 * j, 20 + 3 * j) for j in range(K - half)))
+    env = BallVecEnv(n, window=5, config=cfg, parity=parity, auto_reset=False, max_episode_steps=0)
+    env.reset()
+    agent, goal, obst = z["agent"], z["goal"], z["obst"]
+    if not parity:   # fp32 state: keep the fixtures whose coordinates survive the cast
+        ok = np.all(agent == agent.astype(np.float32), 1) & np.all(goal == goal.astype(np.float32), 1) & \
+            np.all(obst == obst.astype(np.float32), (1, 2))
+        assert ok.sum() >= 150
+    else:
+        ok = np.ones(n, bool)
+    env.set_state(agent_x=agent[:, 0], agent_y=agent[:, 1], goal_x=goal[:, 0], goal_y=goal[:, 1],
+                  static_x=obst[:, :half, 0].T, static_y=obst[:, :half, 1].T,
+                  dynamic_x=obst[:, half:, 0].T, dynamic_y=obst[:, half:, 1].T)
+    got = env.block_counts().cpu().numpy().astype(np.float64)
+    assert np.array_equal(got[ok], z["blocks"][ok])
+    env.close()

@@ -80,3 +80,31 @@ def test_bench_byte_model_matches_survey():
     assert bench.moved_bytes_per_env_step(bench.workload_spec("c3"), 200) == pytest.approx(io + (1121 - io) / 200)
     a = bench.config_dict(bench.workload_spec("c3"), 65536, 8, 200)
     assert a["total_envs"] == 8 * 65536 and "workload" in a and "l2" in a
+
+
+def test_path_log_reader_roundtrip_and_reference_head(tmp_path):
+    """gym_ballenv_b200.pathlogs: the reference's demonstration-log layout (lists of 29-float prep_state2 vectors and
+    [+-10, +-10] actions) written and read back; labels as examples/train_supervise.py derives them; and, where the
+    reference tree is present, the shipped Python 2 pickles themselves against the recorded head of the log."""
+    import json
+    import numpy as np
+    import torch
+    from gym_ballenv_b200 import pathlogs as P
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "pathlog_kat.npz"))
+    meta = json.loads(str(z["meta"]))
+    assert np.array_equal(P.action_labels(z["actions"]), z["labels"])
+    assert P.action_labels(np.array([[20, 0], [0, 0]]))[0] == 8          # not in move_list: the search falls through
+    sf, af = str(tmp_path / "states"), str(tmp_path / "actions")
+    P.save_path_log(torch.from_numpy(z["states"]), torch.from_numpy(z["labels"]), sf, af)
+    x, y = P.load_path_log(sf, af)
+    assert x.dtype == torch.float32 and tuple(x.shape) == (meta["n"], 29)
+    assert np.array_equal(x.numpy(), z["states"].astype(np.float32)) and np.array_equal(y.numpy(), z["labels"])
+    # every logged vector is a prep_state2 output: one goal-quadrant bit, the agent's own cell counted
+    assert np.all(z["states"][:, :4].sum(1) == 1) and np.all(z["states"][:, 16] >= 1)
+    ref = "/root/reference/examples"
+    if os.path.exists(os.path.join(ref, "State_info_trail_no2")):
+        x, y = P.load_path_log(os.path.join(ref, "State_info_trail_no2"), os.path.join(ref, "Trial_no_2"))
+        assert len(x) == meta["total"] == len(y)
+        assert np.array_equal(x[:meta["n"]].numpy(), z["states"].astype(np.float32))
+        assert np.array_equal(y[:meta["n"]].numpy(), z["labels"])
+        assert np.bincount(y.numpy(), minlength=9).tolist() == meta["label_histogram"]

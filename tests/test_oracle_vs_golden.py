@@ -150,3 +150,15 @@ def test_features20_against_the_reference_helpers():
                          agent_rad=float(z["agent_rad"][i]), obstacle_rad=meta["obstacle_rad"])
         np.testing.assert_allclose(got, z["features"][i], rtol=1e-12, atol=1e-12, err_msg=str(i))
     assert z["features"][:, 17:].max() > 1 and set(np.unique(z["features"][:, 0])) >= {0.0, 5.0}
+
+
+def test_blocks29_against_the_reference_prep_state2():
+    """The legacy 29-float block-count observation: prep_state2 of examples/ball_env_reinforce.py (lifted by the shim,
+    tests/golden/blocks_kat.npz) vs the oracle's restatement, 200 states incl. dx == 0, dy == 0 and the block edges."""
+    from oracle.ballenv_oracle import blocks29
+    z, meta = load_golden("blocks_kat")
+    assert z["blocks"].shape == (meta["n"], 29)
+    for i in range(meta["n"]):
+        got = blocks29(tuple(z["agent"][i]), tuple(z["goal"][i]), [tuple(o) for o in z["obst"][i]])
+        assert np.array_equal(np.asarray(got), z["blocks"][i]), i
+    assert np.all(z["blocks"][:, :4].sum(1) == 1) and z["blocks"][:, 16].min() >= 1 and z["blocks"][:, 4:].max() >= 3
