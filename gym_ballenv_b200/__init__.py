@@ -16,9 +16,9 @@ from .config import EnvConfig
 from .env import BallEnv, TimeLimit, createBoard, make, make_prep_state
 from .vec_env import MOVE_LIST, BallVecEnv
 from .distributed import allreduce_stats, make_sharded_env, shard_bounds
-from . import pathlogs
+from . import legacy, pathlogs
 
-__all__ = ["pathlogs", "BallVecEnv", "BallEnv", "createBoard", "TimeLimit", "make", "make_prep_state", "EnvConfig", "MOVE_LIST",
+__all__ = ["legacy", "pathlogs", "BallVecEnv", "BallEnv", "createBoard", "TimeLimit", "make", "make_prep_state", "EnvConfig", "MOVE_LIST",
            "allreduce_stats", "make_sharded_env", "shard_bounds", "BallenvError", "FLAG_GOAL", "FLAG_HIT", "FLAG_TRUNCATED", "FLAG_HIT_DYNAMIC", "STAT_NAMES", "LIB_PATH"]
 
 

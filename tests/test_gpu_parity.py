@@ -624,3 +624,31 @@ def test_block_counts_kernel_against_the_reference_vectors(parity):
     got = env.block_counts().cpu().numpy().astype(np.float64)
     assert np.array_equal(got[ok], z["blocks"][ok])
     env.close()
+
+
+@pytest.mark.gpu
+def test_legacy_block_observation_closed_loop_against_the_oracle():
+    """rollout_blocks (the REINFORCE scripts' loop on the 29-float observation): a greedy policy drives 256 GPU
+    environments for 40 steps; the oracle replays the same actions, and after every step the kernel's block counts
+    equal blocks29 of the oracle's state for every environment."""
+    from gym_ballenv_b200 import BallVecEnv
+    from gym_ballenv_b200.legacy import BlockPolicy
+    from oracle import draws as D
+    from oracle.ballenv_oracle import OracleVec, blocks29
+    from oracle.gen_golden import CFG_DEFAULT
+    n, seed = 256, 9
+    torch.manual_seed(1)
+    policy = BlockPolicy().cuda()
+    env = BallVecEnv(n, window=5, config=_env_config(CFG_DEFAULT), seed=seed, parity=True, max_episode_steps=30)
+    env.reset()
+    orc = OracleVec(oracle_config(CFG_DEFAULT, 5, 30), D.PhiloxDraws(seed), n)
+    orc.reset()
+    for t in range(40):
+        obs = env.block_counts()
+        want = np.array([blocks29(st[0], st[1], st[3:]) for st in (e.state() for e in orc.envs)])
+        assert np.array_equal(obs.cpu().numpy().astype(np.float64), want), t
+        with torch.no_grad():
+            action = policy(obs).argmax(-1)
+        env.step(action)
+        orc.step(action.cpu().numpy())
+    env.close()

@@ -108,3 +108,30 @@ def test_path_log_reader_roundtrip_and_reference_head(tmp_path):
         assert np.array_equal(x[:meta["n"]].numpy(), z["states"].astype(np.float32))
         assert np.array_equal(y[:meta["n"]].numpy(), z["labels"])
         assert np.bincount(y.numpy(), minlength=9).tolist() == meta["label_histogram"]
+
+
+def test_legacy_block_policy_supervised_fit_and_reference_checkpoint():
+    """gym_ballenv_b200.legacy: the 29 -> 128 -> 128 -> 9 net of the older scripts fits the head of the shipped
+    demonstration log (the supervised loop of examples/train_supervise.py), and, where the reference tree is present,
+    loads its supervised checkpoint by parameter name and labels that log better than chance."""
+    import json
+    import numpy as np
+    import torch
+    from gym_ballenv_b200 import pathlogs as P
+    from gym_ballenv_b200.legacy import BlockPolicy, train_supervised
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "pathlog_kat.npz"))
+    x, y = torch.from_numpy(z["states"]).float(), torch.from_numpy(z["labels"])
+    torch.manual_seed(0)
+    model = BlockPolicy(logits=True)
+    first = train_supervised(model, x, y, epochs=1, batch_size=32)
+    last = train_supervised(model, x, y, epochs=150, batch_size=32)
+    assert last < first
+    probs = BlockPolicy()(x)
+    assert probs.shape == (len(x), 9) and torch.allclose(probs.sum(-1), torch.ones(len(x)), atol=1e-6)
+    ckpt = "/root/reference/examples/stored_models/supervised/episode_9999.pth"
+    if os.path.exists(ckpt):
+        ref = BlockPolicy(logits=True)
+        ref.load_state_dict(torch.load(ckpt, map_location="cpu"))
+        xs, ys = P.load_path_log("/root/reference/examples/State_info_trail_no2", "/root/reference/examples/Trial_no_2")
+        acc = (ref(xs).argmax(-1) == ys).float().mean().item()
+        assert acc > 0.3, acc          # nine classes; the net was trained on logs like this one
