@@ -10,7 +10,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BALLENV_LIB_PATH") or os.path.join(HERE, "libballenv_b200.so")   # override: A/B experiments
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_DYNAMIC = 64
 MAX_GOALS = 64
 MAX_STATIC = 1024
@@ -23,6 +23,7 @@ OBS_F32, OBS_U8, OBS_BITS = 0, 1, 2
 ACT_INDEX_I64, ACT_INDEX_I32, ACT_INDEX_U8, ACT_XY_F32, ACT_XY_F64 = 0, 1, 2, 3, 4
 FLAG_GOAL, FLAG_HIT, FLAG_TRUNCATED, FLAG_HIT_DYNAMIC = 1, 2, 4, 8
 DEVERR_BAD_ACTION, DEVERR_TAPE_EXHAUSTED, DEVERR_RESET_STUCK = 1, 2, 4
+KERNEL_GENERIC, KERNEL_ROLES, KERNEL_LEAN = 0, 1, 2
 STAT_NAMES = ("episodes", "return_sum", "length_sum", "goals", "hits_static", "hits_dynamic", "timeouts", "steps")
 
 
@@ -55,7 +56,7 @@ EXPORTS = (
     "ballenv_abi_version", "ballenv_last_error", "ballenv_config_default", "ballenv_state_bytes",
     "ballenv_create", "ballenv_destroy", "ballenv_state_ptrs", "ballenv_reset", "ballenv_step",
     "ballenv_step_many", "ballenv_observe", "ballenv_observe_features", "ballenv_observe_blocks", "ballenv_step_host", "ballenv_set_draw_tape", "ballenv_stats",
-    "ballenv_stats_reset", "ballenv_error_flags", "ballenv_launch_count", "ballenv_selftest",
+    "ballenv_stats_reset", "ballenv_error_flags", "ballenv_launch_count", "ballenv_selftest", "ballenv_kernel_variant",
 )
 
 
@@ -83,6 +84,8 @@ def _bind(lib):
     lib.ballenv_error_flags.argtypes = [vp, vp, vp]
     lib.ballenv_launch_count.argtypes = [vp]
     lib.ballenv_launch_count.restype = i64
+    lib.ballenv_kernel_variant.argtypes = [vp, C.c_int, i32]
+    lib.ballenv_kernel_variant.restype = C.c_int
     lib.ballenv_selftest.argtypes = [C.c_int, i64, C.c_int, C.POINTER(i64)]
     lib.ballenv_selftest.restype = C.c_int
     for name in EXPORTS:

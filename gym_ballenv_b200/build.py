@@ -32,13 +32,22 @@ INSTANCES = [("float", 5, 0, "launch_f32_w5"), ("float", 10, 0, "launch_f32_w10"
              ("float", 0, 1, "launch_f32_wany_fast")]
 
 
+# thread-per-environment kernels (ballenv_lean.cuh): (window, static obstacles, dynamic obstacles)
+LEAN_INSTANCES = [(5, 13, 5), (10, 13, 5), (10, 8, 24), (5, 8, 24)]
+
+
 def _sources():
-    deps = [os.path.join(CSRC, f) for f in ("ballenv_kernels.cuh", "ballenv_rng.cuh")]
+    deps = [os.path.join(CSRC, f) for f in ("ballenv_kernels.cuh", "ballenv_rng.cuh", "ballenv_lean.cuh",
+                                            "ballenv_features.cuh")]
     deps.append(os.path.join(os.path.dirname(HERE), "include", "ballenv.h"))
     jobs = [(os.path.join(CSRC, "ballenv_capi.cu"), os.path.join(OBJ, "ballenv_capi.o"), [])]
     for t, w, fast, name in INSTANCES:
         jobs.append((os.path.join(CSRC, "ballenv_inst.cu"), os.path.join(OBJ, name + ".o"),
                      ["-DBALLENV_T=" + t, "-DBALLENV_W=%d" % w, "-DBALLENV_FAST=%d" % fast, "-DBALLENV_NAME=" + name]))
+    for w, ks, kd in LEAN_INSTANCES:
+        name = "launch_lean_w%d_s%d_d%d" % (w, ks, kd)
+        jobs.append((os.path.join(CSRC, "ballenv_lean_inst.cu"), os.path.join(OBJ, name + ".o"),
+                     ["-DBALLENV_W=%d" % w, "-DBALLENV_KS=%d" % ks, "-DBALLENV_KD=%d" % kd, "-DBALLENV_NAME=" + name]))
     return deps, jobs
 
 
@@ -65,7 +74,7 @@ def build(force=False, verbose=False):
     os.makedirs(OBJ, exist_ok=True)
     deps, jobs = _sources()
     log = []
-    with ThreadPoolExecutor(max_workers=min(10, len(jobs))) as ex:
+    with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
         objs = list(ex.map(lambda j: _compile(j, deps, force, log), jobs))
     if force or _stale(LIB, objs):
         cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + objs

@@ -10,6 +10,7 @@
 
 #include "ballenv_kernels.cuh"
 #include "ballenv_features.cuh"
+#include "ballenv_lean.cuh"
 
 using namespace ballenv;
 
@@ -23,6 +24,11 @@ void launch_f64_wany(const Params&, unsigned, cudaStream_t);
 void launch_f32_w5_fast(const Params&, unsigned, cudaStream_t);
 void launch_f32_w10_fast(const Params&, unsigned, cudaStream_t);
 void launch_f32_wany_fast(const Params&, unsigned, cudaStream_t);
+// ballenv_lean_inst.cu: thread-per-environment kernels, one per (window, static, dynamic obstacle count)
+void launch_lean_w5_s13_d5(const Params&, unsigned, cudaStream_t);
+void launch_lean_w10_s13_d5(const Params&, unsigned, cudaStream_t);
+void launch_lean_w10_s8_d24(const Params&, unsigned, cudaStream_t);
+void launch_lean_w5_s8_d24(const Params&, unsigned, cudaStream_t);
 }  // namespace ballenv
 
 __global__ void selftest_sqrt_kernel(long long n, unsigned long long* bad) {
@@ -132,7 +138,7 @@ int validate(const BallenvConfig* c) {
 
 struct Layout {
   size_t agent_x, agent_y, goal_x, goal_y, dist, total, acc, ep_len, episode, tick;
-  size_t stat_x, stat_y, dyn_x, dyn_y, dyn_meta, flags, stats, errors, bytes;
+  size_t stat_x, stat_y, dyn_x, dyn_y, dyn_meta, flags, stats, errors, lean_tab, lean_tab_entries, bytes;
   long long stride, stat_stride, dyn_stride;
 };
 
@@ -167,6 +173,13 @@ Layout make_layout(const BallenvConfig& c, long long n) {
   L.flags = take(S);
   L.stats = take(8 * BALLENV_NUM_STATS);
   L.errors = take(256);
+  // column-mask table of the thread-per-environment kernels (ballenv_lean.cuh: LeanTab<W>), gym ruleset only
+  L.lean_tab_entries = 0;
+  if (c.ruleset == BALLENV_RULESET_GYM && c.window > 1 && c.window <= 16) {
+    const int m = 25 + c.window / 2 + 2;
+    L.lean_tab_entries = (size_t)(2 * m + 1) * (size_t)(2 * m + c.window - 1);
+  }
+  L.lean_tab = take(2 * L.lean_tab_entries + 16);
   L.bytes = off;
   return L;
 }
@@ -192,6 +205,7 @@ struct BallenvHandle {
   size_t stage_act = 0, stage_obs = 0, stage_rew = 0, stage_done = 0;
   long long launches = 0;
   bool no_rollout = false;      // BALLENV_NO_ROLLOUT=1: ballenv_step_many launches one kernel per step (tests, profiling)
+  bool no_lean = false;         // BALLENV_NO_LEAN=1: never pick the thread-per-environment kernels (tests, A/B runs)
   bool force_generic = false;   // BALLENV_FORCE_GENERIC=1 in the environment: never pick the fast specialisation (tests)
 };
 
@@ -207,6 +221,22 @@ bool fast_eligible(const BallenvHandle* h, const Params& p) {
          !h->force_generic;
 }
 
+// thread-per-environment kernels (ballenv_lean.cuh): the production configuration with one of the instantiated
+// obstacle counts, integral geometry and a change step that fits a byte
+typedef void (*LeanLauncher)(const Params&, unsigned, cudaStream_t);
+LeanLauncher lean_launcher(const BallenvHandle* h, const Params& p) {
+  if (!fast_eligible(h, p) || h->no_lean || p.lean_tab == nullptr) return nullptr;
+  const DevConfig& c = p.cfg;
+  if (c.change_step > 254 || c.n_goals < 2 || c.step_x != 1.0 || c.step_y != 1.0 || c.radius_sum != 25.0) return nullptr;
+  if (c.margin != (double)(25 + c.window / 2 + 2)) return nullptr;
+  struct Inst { int w, ks, kd; LeanLauncher fn; };
+  static const Inst kInst[] = {{5, 13, 5, launch_lean_w5_s13_d5}, {10, 13, 5, launch_lean_w10_s13_d5},
+                               {10, 8, 24, launch_lean_w10_s8_d24}, {5, 8, 24, launch_lean_w5_s8_d24}};
+  for (const Inst& i : kInst)
+    if (i.w == c.window && i.ks == c.ks && i.kd == c.kd) return i.fn;
+  return nullptr;
+}
+
 int launch(BallenvHandle* h, const Params& p_in, cudaStream_t s) {
   Params p = p_in;   // + the constants the kernels would otherwise derive per step
   p.obs_row_bytes = (long long)p.cfg.obs_row_elems * (p.cfg.obs_format == BALLENV_OBS_U8 ? 1 : 4);
@@ -220,6 +250,12 @@ int launch(BallenvHandle* h, const Params& p_in, cudaStream_t s) {
     p.sq = (fast_eligible(h, p) && p.n_steps == 1 && (qs == 2 || qs == 4) && qs / 2 + qd <= 4) ? 2 : 1;
     p.n_stat = kEnvsPerBlock * (qs / p.sq);
     p.n_slot = p.n_stat + kEnvsPerBlock * qd;
+  }
+  if (LeanLauncher lean = lean_launcher(h, p)) {
+    lean(p, (unsigned)((p.n + kLeanBlock - 1) / kLeanBlock), s);
+    h->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    return BALLENV_OK;
   }
   const unsigned grid = (unsigned)((p.n + kEnvsPerBlock - 1) / kEnvsPerBlock);
   const bool f64 = h->cfg.precision == BALLENV_F64;
@@ -295,9 +331,13 @@ void fill_dev_config(const BallenvConfig& c, DevConfig* d) {
   }
   d->goals_distinct = distinct ? 1 : 0;
   for (int i = 0; i < d->n_goals; ++i) d->f_goal[i] = make_float2((float)c.obs_goal_x[i], (float)c.obs_goal_y[i]);
+  d->lean_integral_speeds = 1;
   for (int j = 0; j < c.dynamic_obstacles; ++j) {
     d->speed[j] = c.obstacle_speed[j];
     d->f_speed[j] = (float)c.obstacle_speed[j];
+    if (c.obstacle_speed[j] != (double)(long long)c.obstacle_speed[j] || c.obstacle_speed[j] > 1024.0 ||
+        c.obstacle_speed[j] < -1024.0)
+      d->lean_integral_speeds = 0;
   }
 }
 
@@ -404,6 +444,8 @@ int ballenv_create(const BallenvConfig* cfg, int64_t n_envs, int64_t global_env_
   h->L = make_layout(*cfg, n_envs);
   const char* fg = getenv("BALLENV_FORCE_GENERIC");
   h->force_generic = fg != nullptr && fg[0] == '1';
+  const char* nl = getenv("BALLENV_NO_LEAN");
+  h->no_lean = nl != nullptr && nl[0] == '1';
   const char* nr = getenv("BALLENV_NO_ROLLOUT");
   h->no_rollout = nr != nullptr && nr[0] == '1';
   if (arena != nullptr) {
@@ -422,10 +464,31 @@ int ballenv_create(const BallenvConfig* cfg, int64_t n_envs, int64_t global_env_
   }
   cudaError_t e = cudaMemset(h->arena, 0, h->L.bytes);
   if (e == cudaSuccess) e = cudaMemset(h->arena + h->L.episode, 0xff, 4 * (size_t)h->L.stride);  // episode = -1: none yet
+  if (e == cudaSuccess && h->L.lean_tab_entries > 0) {
+    // column masks of the exact raster (LeanTab<W> in ballenv_lean.cuh): entry [ui][s] = columns c of the window with
+    // (c - u)^2 + dv^2 <= 25^2, u = ui + h - M, dv = s - h - M (examples/ball_cnn_ac3.py:396-409 for integral coordinates)
+    const int w = cfg->window, hh = w / 2, m = 25 + hh + 2, U = 2 * m + 1, S = 2 * m + w - 1;
+    uint16_t* tab = (uint16_t*)malloc(sizeof(uint16_t) * (size_t)U * S);
+    if (tab == nullptr) e = cudaErrorMemoryAllocation;
+    else {
+      for (int ui = 0; ui < U; ++ui)
+        for (int si = 0; si < S; ++si) {
+          const int u = ui + hh - m, dv = si - hh - m;
+          uint16_t mask = 0;
+          for (int cc = 0; cc < w; ++cc)
+            if ((cc - u) * (cc - u) + dv * dv <= 625) mask |= (uint16_t)(1u << cc);
+          tab[(size_t)ui * S + si] = mask;
+        }
+      e = cudaMemcpy(h->arena + h->L.lean_tab, tab, sizeof(uint16_t) * (size_t)U * S, cudaMemcpyHostToDevice);
+      free(tab);
+    }
+  }
+  // everything above ran on the legacy stream: a caller that launches on a non-blocking stream next must see it done
+  if (e == cudaSuccess) e = cudaStreamSynchronize(0);
   if (e != cudaSuccess) {
     if (h->owns_arena) cudaFree(h->arena);
     delete h;
-    return fail(BALLENV_ECUDA, "cudaMemset failed: %s", cudaGetErrorString(e));
+    return fail(BALLENV_ECUDA, "arena initialisation failed: %s", cudaGetErrorString(e));
   }
   Params& p = h->base;
   memset(&p, 0, sizeof(p));
@@ -459,6 +522,11 @@ int ballenv_create(const BallenvConfig* cfg, int64_t n_envs, int64_t global_env_
   p.flags = (uint8_t*)(a + L.flags);
   p.stats = (double*)(a + L.stats);
   p.errors = (uint32_t*)(a + L.errors);
+  p.lean_tab = L.lean_tab_entries > 0 ? (const uint16_t*)(a + L.lean_tab) : nullptr;
+  for (int r = 0; r < 10; ++r) {   // Philox4x32 key schedule (ballenv_rng.cuh)
+    p.rk[2 * r] = p.k0 + (uint32_t)r * kPhiloxW0;
+    p.rk[2 * r + 1] = p.k1 + (uint32_t)r * kPhiloxW1;
+  }
   *out = h;
   return BALLENV_OK;
 }
@@ -718,6 +786,20 @@ int ballenv_error_flags(BallenvHandle* h, uint32_t* out, ballenv_stream_t stream
 }
 
 int64_t ballenv_launch_count(BallenvHandle* h) { return h ? h->launches : 0; }
+
+int ballenv_kernel_variant(BallenvHandle* h, int action_kind, int32_t n_steps) {
+  if (h == nullptr) return fail(BALLENV_EINVAL, "handle is NULL");
+  Params p = h->base;
+  p.mode = kModeStep;
+  p.n_steps = n_steps > 1 ? n_steps : 1;
+  p.action_kind = action_kind;
+  p.obs = h->arena;   // any non-null pointer: rows requested
+  p.reset_tape = h->reset_tape;
+  p.step_tape = h->step_tape;
+  if (p.n_steps > 1 && h->no_rollout) p.n_steps = 1;
+  if (lean_launcher(h, p) != nullptr) return BALLENV_KERNEL_LEAN;
+  return fast_eligible(h, p) ? BALLENV_KERNEL_ROLES : BALLENV_KERNEL_GENERIC;
+}
 
 int ballenv_selftest(int which, int64_t arg, int device, int64_t* mismatches) {
   if (mismatches == nullptr) return fail(BALLENV_EINVAL, "mismatches is null");

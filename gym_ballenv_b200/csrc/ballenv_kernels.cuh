@@ -73,6 +73,7 @@ struct DevConfig {
   uint32_t rcp_qs, rcp_qd;   // ceil(2^32 / quads per environment) (0 when there is one quad: identity)
   float f_speed[BALLENV_MAX_DYNAMIC];
   float2 f_goal[BALLENV_MAX_GOALS];
+  int lean_integral_speeds;  // every obstacle speed is an integer (integral coordinates then stay integral: ballenv_lean.cuh)
 };
 
 template <typename T>
@@ -133,6 +134,10 @@ struct Params {
   const uint32_t* reset_tape;  // [episodes][n][width], or null
   long long reset_tape_episodes;
   int tape_attempts, reset_tape_width;
+  // thread-per-environment kernels (ballenv_lean.cuh): Philox round keys k + r * W of the handle's seed, and the table
+  // of window column masks (LeanTab<W>, in the arena)
+  uint32_t rk[20];
+  const uint16_t* lean_tab;
 };
 
 // ---- arithmetic that must not be contracted into FMAs (the reference squares, then adds) -------------------

@@ -1,0 +1,34 @@
+// Instantiations of the thread-per-environment kernel (ballenv_lean.cuh), one translation unit per
+// (window, static obstacles, dynamic obstacles) so that they build in parallel:
+//   -DBALLENV_W=5|10 -DBALLENV_KS=.. -DBALLENV_KD=.. -DBALLENV_NAME=launch_lean_w.._s.._d..
+#include <cuda_runtime.h>
+
+#include "ballenv_lean.cuh"
+
+#if !defined(BALLENV_W) || !defined(BALLENV_KS) || !defined(BALLENV_KD) || !defined(BALLENV_NAME)
+#error "compile with -DBALLENV_W -DBALLENV_KS -DBALLENV_KD -DBALLENV_NAME"
+#endif
+
+namespace ballenv {
+
+template <bool kRollout>
+static void launch_lean(const Params& p, unsigned grid, cudaStream_t s) {
+  auto kern = ballenv_lean_kernel<BALLENV_W, BALLENV_KS, BALLENV_KD, kRollout>;
+  static bool configured[64] = {};   // per device: function attributes belong to the device's copy of the kernel
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !configured[dev]) {
+    // seven blocks of 64 threads with their obstacle slices in shared memory: ask for the whole array
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    configured[dev] = true;
+  }
+  kern<<<grid, kLeanBlock, 0, s>>>(p);
+}
+
+// grid = blocks of kLeanBlock environments
+void BALLENV_NAME(const Params& p, unsigned grid, cudaStream_t s) {
+  if (p.n_steps > 1) launch_lean<true>(p, grid, s);
+  else launch_lean<false>(p, grid, s);
+}
+
+}  // namespace ballenv

@@ -309,6 +309,13 @@ class BallVecEnv:
         check(LIB.ballenv_error_flags(self._h, C.byref(out), self._stream()))
         return int(out.value)
 
+    def kernel_variant(self, n_steps: int = 1, action_dtype=torch.int64) -> str:
+        """Which kernel step() (n_steps = 1) / step_many() launches for index actions of this dtype:
+        "lean" (thread per environment), "roles" (block of roles, production specialisation) or "generic"."""
+        kind = {torch.int64: L.ACT_INDEX_I64, torch.int32: L.ACT_INDEX_I32, torch.uint8: L.ACT_INDEX_U8,
+                torch.float32: L.ACT_XY_F32, torch.float64: L.ACT_XY_F64}[action_dtype]
+        return ("generic", "roles", "lean")[check(LIB.ballenv_kernel_variant(self._h, kind, int(n_steps)))]
+
     @property
     def launch_count(self) -> int:
         return int(LIB.ballenv_launch_count(self._h))

@@ -17,8 +17,9 @@
  * State layout (struct-of-arrays, resident in HBM, owned by the handle or by a caller arena):
  *   per-env scalars are arrays of n_stride elements (one thread per environment reads them: a warp
  *   touches whole 128-byte lines); per-obstacle fields are environment-major rows [n_stride][K padded
- *   to a multiple of 4] so that the 8 lanes that own one environment move its obstacles as 128-bit
- *   quads and a warp (4 environments) touches 4 * K contiguous elements per field.
+ *   to a multiple of 4]: the rows of 32 consecutive environments are one contiguous slice per field, which
+ *   the thread-per-environment kernels move as one bulk copy per warp and the block-of-roles kernels as
+ *   consecutive 128-bit quads (one quad of four obstacles per thread).
  */
 #ifndef BALLENV_H_
 #define BALLENV_H_
@@ -29,7 +30,7 @@
 extern "C" {
 #endif
 
-#define BALLENV_ABI_VERSION 3
+#define BALLENV_ABI_VERSION 4
 
 #define BALLENV_MAX_DYNAMIC 64
 #define BALLENV_MAX_GOALS 64
@@ -238,6 +239,13 @@ int ballenv_stats_reset(BallenvHandle *h, ballenv_stream_t stream);
 int ballenv_error_flags(BallenvHandle *h, uint32_t *out /* host */, ballenv_stream_t stream);
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
 int64_t ballenv_launch_count(BallenvHandle *h);
+/* Which kernel a ballenv_step (n_steps = 1) or ballenv_step_many (n_steps > 1) call with this action kind and
+ * observation rows requested launches (no reference counterpart; diagnostics, bench.py, tests):
+ * BALLENV_KERNEL_GENERIC, _ROLES (block of roles, production specialisation) or _LEAN (thread per environment). */
+#define BALLENV_KERNEL_GENERIC 0
+#define BALLENV_KERNEL_ROLES 1
+#define BALLENV_KERNEL_LEAN 2
+int ballenv_kernel_variant(BallenvHandle *h, int action_kind, int32_t n_steps);
 /* Device self-tests of the arithmetic shortcuts the step kernel takes (no reference counterpart; run by the GPU
  * tests).  which = 0: the integer square root used for the distance to the goal when all coordinates are integral
  * (sqrt_int22) against sqrt() for every integer 0 <= s < arg; *mismatches receives the number of differing

@@ -1,0 +1,236 @@
+"""The thread-per-environment kernels (gym_ballenv_b200/csrc/ballenv_lean.cuh) against the block-of-roles
+specialisation, the generic kernel and the oracle: same draws, same arithmetic, bit-identical results - on generated
+rollouts with auto-resets and on injected states that reach the kernel's rare paths (near-list overflow, counters out
+of lockstep, duplicate-free goal changes, non-integral coordinates, ragged last warps)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import oracle_config
+
+pytestmark = pytest.mark.gpu
+
+
+def _env_config(cfg):
+    from gym_ballenv_b200 import EnvConfig
+    return EnvConfig(static_obstacles=cfg["static_obstacles"], dynamic_obstacles=cfg["dynamic_obstacles"],
+                     obstacle_speed=cfg["obstacle_speed"], obs_goal_position=cfg["obs_goal_position"],
+                     time_step_for_change=cfg["time_step_for_change"], rd_th_obs=cfg["rd_th_obs"],
+                     static_penalty=cfg["static_penalty"], dynamic_penalty=cfg["dynamic_penalty"])
+
+
+def _cfg(name):
+    from oracle.gen_golden import CFG_DEFAULT, CFG_DENSE
+    return CFG_DEFAULT if name == "default" else CFG_DENSE
+
+
+def _pair(monkeypatch, n, w, cfgname, other="roles", **kw):
+    """(lean env, comparison env) with identical seeds; `other` = "roles" | "generic"."""
+    from gym_ballenv_b200 import BallVecEnv
+    cfg = _env_config(_cfg(cfgname))
+    lean = BallVecEnv(n, window=w, config=cfg, **kw)
+    monkeypatch.setenv("BALLENV_NO_LEAN" if other == "roles" else "BALLENV_FORCE_GENERIC", "1")
+    ref = BallVecEnv(n, window=w, config=cfg, **kw)
+    monkeypatch.delenv("BALLENV_NO_LEAN" if other == "roles" else "BALLENV_FORCE_GENERIC")
+    assert lean.kernel_variant(1) == "lean" and lean.kernel_variant(8) == "lean"
+    assert ref.kernel_variant(1) == other
+    return lean, ref
+
+
+def _same_state(a, b):
+    sa, sb = a.get_state(), b.get_state()
+    for k in sa:
+        assert torch.equal(sa[k], sb[k]), k
+    sta, stb = a.stats(), b.stats()
+    for k in sta:   # sums of doubles are accumulated with atomics: order, hence the last bits, may differ
+        assert sta[k] == pytest.approx(stb[k], rel=1e-12), k
+    assert a.error_flags() == 0 and b.error_flags() == 0
+
+
+@pytest.mark.parametrize("w,cfgname,n,other", [(5, "default", 1000, "roles"), (10, "dense", 777, "roles"),
+                                               (10, "default", 33, "generic"), (5, "dense", 65, "generic"),
+                                               (10, "dense", 4096, "generic")])
+def test_lean_single_step_matches_the_other_kernels(w, cfgname, n, other, monkeypatch):
+    lean, ref = _pair(monkeypatch, n, w, cfgname, other, seed=5, max_episode_steps=15)
+    assert torch.equal(lean.reset(), ref.reset())
+    g = torch.Generator().manual_seed(11)
+    for t in range(60):
+        a = torch.randint(0, 9, (n,), generator=g).cuda()
+        ol, rl, dl, il = lean.step(a)
+        orf, rr, dr, ir = ref.step(a)
+        assert torch.equal(ol, orf), t
+        assert torch.equal(rl, rr), t
+        assert torch.equal(dl, dr), t
+        assert torch.equal(il["flags"], ir["flags"]), t
+    _same_state(lean, ref)
+    assert lean.stats()["episodes"] > n
+    lean.close()
+    ref.close()
+
+
+@pytest.mark.parametrize("w,cfgname,n,keep", [(5, "default", 1000, True), (10, "dense", 777, True), (10, "dense", 96, False),
+                                              (5, "dense", 31, True)])
+def test_lean_rollout_matches_per_step_launches_of_the_other_kernel(w, cfgname, n, keep, monkeypatch):
+    """ballenv_step_many through the lean rollout kernel (state in registers for all T steps) == T single-step
+    launches of the block-of-roles kernel, with auto-resets inside the rollout and action dtypes int64 / int32 / uint8."""
+    from gym_ballenv_b200 import BallVecEnv
+    cfg = _env_config(_cfg(cfgname))
+    T = 64
+    one = BallVecEnv(n, window=w, config=cfg, seed=21, max_episode_steps=17)
+    monkeypatch.setenv("BALLENV_NO_LEAN", "1")
+    monkeypatch.setenv("BALLENV_NO_ROLLOUT", "1")
+    per = BallVecEnv(n, window=w, config=cfg, seed=21, max_episode_steps=17)
+    monkeypatch.delenv("BALLENV_NO_LEAN")
+    monkeypatch.delenv("BALLENV_NO_ROLLOUT")
+    assert one.kernel_variant(T) == "lean" and per.kernel_variant(T) == "roles"
+    assert torch.equal(one.reset(), per.reset())
+    g = torch.Generator().manual_seed(5)
+    for chunk, dt in enumerate((torch.int64, torch.int32, torch.uint8)):
+        a = torch.randint(0, 9, (T, n), generator=g).to(dt).cuda()
+        o1, r1, d1 = one.step_many(a, keep_all_obs=keep)
+        o2, r2, d2 = per.step_many(a, keep_all_obs=keep)
+        assert torch.equal(o1, o2), chunk
+        assert torch.equal(r1, r2), chunk
+        assert torch.equal(d1, d2), chunk
+    assert one.launch_count == 1 + 3
+    _same_state(one, per)
+    one.close()
+    per.close()
+
+
+def test_lean_against_the_c_oracle_with_resets():
+    """4096 envs x 120 steps, W=10 dense, TimeLimit 13: lean single-step launches vs oracle/ballenv_oracle.c, every
+    observation / done / flag byte, then the whole state."""
+    from gym_ballenv_b200 import BallVecEnv
+    from oracle.c_oracle import COracleVec
+    from oracle.gen_golden import CFG_DENSE
+    n, T, seed = 4096, 120, 99
+    env = BallVecEnv(n, window=10, config=_env_config(CFG_DENSE), seed=seed, max_episode_steps=13)
+    assert env.kernel_variant(1) == "lean"
+    c = COracleVec(oracle_config(CFG_DENSE, 10, 13), seed, n)
+    obs = env.reset()
+    c.reset()
+    assert np.array_equal(obs.cpu().numpy(), c.observe())
+    g = torch.Generator().manual_seed(8)
+    for t in range(T):
+        a = torch.randint(0, 9, (n,), generator=g)
+        obs, rew, done, info = env.step(a.cuda())
+        r, d, f = c.step(a.numpy())
+        assert np.array_equal(obs.cpu().numpy(), c.observe()), t
+        assert np.array_equal(done.cpu().numpy(), d), t
+        assert np.array_equal(info["flags"].cpu().numpy(), f), t
+        np.testing.assert_allclose(rew.cpu().numpy(), r, rtol=1e-5, atol=0)
+    st, ref = env.get_state(), c.state()
+    assert np.array_equal(st["dist"].cpu().numpy(), ref["dist"])
+    assert np.array_equal(st["dynamic_x"].cpu().numpy().T, ref["obstacles"][:, 8:, 0].astype(np.float32))
+    assert np.array_equal(st["dynamic_goal"].cpu().numpy().T, ref["dyn_goal"])
+    assert np.array_equal(st["dynamic_counter"].cpu().numpy().T, ref["dyn_counter"])
+    assert env.error_flags() == 0
+    env.close()
+
+
+def _inject(envs, **fields):
+    for e in envs:
+        e.set_state(**fields)
+
+
+@pytest.mark.parametrize("w,cfgname", [(10, "dense"), (5, "default")])
+def test_lean_near_list_overflow_and_hits(w, cfgname, monkeypatch):
+    """Every obstacle of every environment piled onto the agent's window: more near obstacles than the per-lane list
+    holds (rescan path), hits on the first step, resets right after."""
+    n = 200
+    lean, ref = _pair(monkeypatch, n, w, cfgname, "generic", seed=3, max_episode_steps=40)
+    lean.reset()
+    ref.reset()
+    rng = np.random.RandomState(3)
+    ks, kd = lean.config.static_obstacles, lean.config.dynamic_obstacles
+    agent = rng.randint(60, 440, size=(n, 2)).astype(np.float32)
+    sx = agent[:, 0][None, :] + rng.randint(-33, 34, size=(ks, n))
+    sy = agent[:, 1][None, :] + rng.randint(-33, 34, size=(ks, n))
+    dx = agent[:, 0][None, :] + rng.randint(-33, 34, size=(kd, n))
+    dy = agent[:, 1][None, :] + rng.randint(-33, 34, size=(kd, n))
+    _inject((lean, ref), agent_x=agent[:, 0], agent_y=agent[:, 1], static_x=sx, static_y=sy, dynamic_x=dx, dynamic_y=dy)
+    g = torch.Generator().manual_seed(2)
+    for t in range(6):
+        a = torch.randint(0, 9, (n,), generator=g).cuda()
+        ol, rl, dl, il = lean.step(a)
+        orf, rr, dr, ir = ref.step(a)
+        assert torch.equal(ol, orf), t
+        assert torch.equal(rl, rr), t
+        assert torch.equal(dl, dr), t
+        assert torch.equal(il["flags"], ir["flags"]), t
+    _same_state(lean, ref)
+    lean.close()
+    ref.close()
+
+
+def test_lean_counters_out_of_lockstep_and_stale_counters(monkeypatch):
+    """Injected change counters that differ inside a quad (the per-obstacle path), sit at the change step, or lie
+    beyond it (treated like the change step, as the reference's `<` test does)."""
+    n, w = 96, 10
+    lean, ref = _pair(monkeypatch, n, w, "dense", "generic", seed=8, max_episode_steps=0, auto_reset=False)
+    lean.reset()
+    ref.reset()
+    rng = np.random.RandomState(1)
+    kd = lean.config.dynamic_obstacles
+    cnt = rng.randint(0, 52, size=(kd, n))
+    cnt[:, :8] = 50                     # whole environments at the change step
+    cnt[::3, 8:16] = 50                 # mixed quads
+    cnt[1, 16:24] = 300                 # stale counter beyond the change step
+    _inject((lean, ref), dynamic_counter=cnt)
+    g = torch.Generator().manual_seed(4)
+    for t in range(110):
+        a = torch.randint(0, 9, (n,), generator=g).cuda()
+        ol, rl, dl, il = lean.step(a)
+        orf, rr, dr, ir = ref.step(a)
+        assert torch.equal(ol, orf), t
+        assert torch.equal(rl, rr), t
+    sl, sr = lean.get_state(), ref.get_state()
+    for k in sl:
+        assert torch.equal(sl[k], sr[k]), k
+    lean.close()
+    ref.close()
+
+
+def test_lean_non_integral_coordinates_take_the_general_path(monkeypatch):
+    """Fractional agent / obstacle positions (injected; the gym ruleset never produces them): the table raster and the
+    integer square root do not apply, the per-cell arithmetic of the generic kernel does - same fp32 results as the
+    block-of-roles kernel, which shares that arithmetic."""
+    n, w = 128, 10
+    lean, ref = _pair(monkeypatch, n, w, "dense", "roles", seed=12, max_episode_steps=0, auto_reset=False)
+    lean.reset()
+    ref.reset()
+    st = lean.get_state()
+    rng = np.random.RandomState(5)
+    ax = st["agent_x"].cpu().numpy() + rng.randint(0, 4, size=n) * 0.25
+    dx = st["dynamic_x"].cpu().numpy() + rng.randint(0, 4, size=st["dynamic_x"].shape) * 0.25
+    sy = st["static_y"].cpu().numpy()
+    sy[:, : n // 2] = st["agent_y"].cpu().numpy()[None, : n // 2] + 7.5     # near, fractional
+    _inject((lean, ref), agent_x=ax, dynamic_x=dx, static_y=sy)
+    g = torch.Generator().manual_seed(6)
+    a = torch.randint(0, 9, (30, n), generator=g).cuda()
+    o1, r1, d1 = lean.step_many(a, keep_all_obs=True)
+    o2, r2, d2 = ref.step_many(a, keep_all_obs=True)
+    assert torch.equal(o1, o2)
+    assert torch.equal(r1, r2)
+    assert torch.equal(d1, d2)
+    assert o1[:, :, 4:].sum() > 0
+    _same_state(lean, ref)
+    lean.close()
+    ref.close()
+
+
+def test_lean_is_not_selected_outside_its_domain():
+    from gym_ballenv_b200 import BallVecEnv, EnvConfig
+    env = BallVecEnv(64, window=7)                                   # window without an instantiation
+    assert env.kernel_variant(1) == "roles"
+    env.close()
+    env = BallVecEnv(64, window=5, config=EnvConfig(time_step_for_change=300))   # counter does not fit a byte
+    assert env.kernel_variant(1) == "roles"
+    env.close()
+    env = BallVecEnv(64, window=5, parity=True)                      # fp64 parity mode
+    assert env.kernel_variant(1) == "generic"
+    env.close()
+    env = BallVecEnv(64, window=5)
+    assert env.kernel_variant(1) == "lean" and env.kernel_variant(1, torch.float32) == "generic"
+    env.close()

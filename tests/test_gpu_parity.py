@@ -287,15 +287,19 @@ def test_bad_action_flag_and_errors():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("no_lean", [False, True])
 @pytest.mark.parametrize("w,cfgname,n", [(5, "default", 1000), (10, "dense", 777), (7, "default", 100)])
-def test_fast_and_generic_kernels_agree(w, cfgname, n, monkeypatch):
+def test_fast_and_generic_kernels_agree(w, cfgname, n, no_lean, monkeypatch):
     """The production specialisation (ballenv_kernel<..., kFast=true>) and the generic kernel are the same
     function: bit-identical observations, rewards, flags and state over a rollout with auto-resets, including a
     ragged last block (n not a multiple of 32)."""
     from gym_ballenv_b200 import BallVecEnv
     from oracle.gen_golden import CFG_DEFAULT, CFG_DENSE
     cfg = CFG_DEFAULT if cfgname == "default" else CFG_DENSE
+    if no_lean:   # the block-of-roles specialisation instead of the thread-per-environment kernel
+        monkeypatch.setenv("BALLENV_NO_LEAN", "1")
     fast = BallVecEnv(n, window=w, config=_env_config(cfg), seed=5, max_episode_steps=15)
+    assert fast.kernel_variant(1) == ("roles" if no_lean or w == 7 else "lean")
     monkeypatch.setenv("BALLENV_FORCE_GENERIC", "1")
     slow = BallVecEnv(n, window=w, config=_env_config(cfg), seed=5, max_episode_steps=15)
     monkeypatch.delenv("BALLENV_FORCE_GENERIC")
@@ -320,14 +324,17 @@ def test_fast_and_generic_kernels_agree(w, cfgname, n, monkeypatch):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("no_lean", [False, True])
 @pytest.mark.parametrize("w,cfgname,n,keep", [(5, "default", 1000, True), (10, "dense", 777, True), (5, "default", 96, False)])
-def test_rollout_kernel_matches_per_step_launches(w, cfgname, n, keep, monkeypatch):
+def test_rollout_kernel_matches_per_step_launches(w, cfgname, n, keep, no_lean, monkeypatch):
     """ballenv_step_many as ONE launch (state held on chip for all T steps) == T single-step launches: every
     observation, reward, done, the final state and the statistics, with auto-resets inside the rollout."""
     from gym_ballenv_b200 import BallVecEnv
     from oracle.gen_golden import CFG_DEFAULT, CFG_DENSE
     cfg = CFG_DEFAULT if cfgname == "default" else CFG_DENSE
     T = 64
+    if no_lean:
+        monkeypatch.setenv("BALLENV_NO_LEAN", "1")
     one = BallVecEnv(n, window=w, config=_env_config(cfg), seed=21, max_episode_steps=17)
     monkeypatch.setenv("BALLENV_NO_ROLLOUT", "1")
     per = BallVecEnv(n, window=w, config=_env_config(cfg), seed=21, max_episode_steps=17)
