@@ -252,7 +252,7 @@ int launch(BallenvHandle* h, const Params& p_in, cudaStream_t s) {
     p.n_slot = p.n_stat + kEnvsPerBlock * qd;
   }
   if (LeanLauncher lean = lean_launcher(h, p)) {
-    lean(p, (unsigned)((p.n + kLeanBlock - 1) / kLeanBlock), s);
+    lean(p, (unsigned)((p.n + kLeanEnvsPerBlock - 1) / kLeanEnvsPerBlock), s);
     h->launches += 1;
     CUDA_TRY(cudaGetLastError());
     return BALLENV_OK;

@@ -18,14 +18,14 @@ static void launch_lean(const Params& p, unsigned grid, cudaStream_t s) {
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !configured[dev]) {
-    // seven blocks of 64 threads with their obstacle slices in shared memory: ask for the whole array
+    // seven blocks of 128 threads with their obstacle slices in shared memory: ask for the whole array
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     configured[dev] = true;
   }
-  kern<<<grid, kLeanBlock, 0, s>>>(p);
+  kern<<<grid, kLeanThreads, 0, s>>>(p);
 }
 
-// grid = blocks of kLeanBlock environments
+// grid = blocks of kLeanEnvsPerBlock environments
 void BALLENV_NAME(const Params& p, unsigned grid, cudaStream_t s) {
   if (p.n_steps > 1) launch_lean<true>(p, grid, s);
   else launch_lean<false>(p, grid, s);
