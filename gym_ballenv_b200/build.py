@@ -45,9 +45,11 @@ def _sources():
         jobs.append((os.path.join(CSRC, "ballenv_inst.cu"), os.path.join(OBJ, name + ".o"),
                      ["-DBALLENV_T=" + t, "-DBALLENV_W=%d" % w, "-DBALLENV_FAST=%d" % fast, "-DBALLENV_NAME=" + name]))
     for w, ks, kd in LEAN_INSTANCES:
-        name = "launch_lean_w%d_s%d_d%d" % (w, ks, kd)
-        jobs.append((os.path.join(CSRC, "ballenv_lean_inst.cu"), os.path.join(OBJ, name + ".o"),
-                     ["-DBALLENV_W=%d" % w, "-DBALLENV_KS=%d" % ks, "-DBALLENV_KD=%d" % kd, "-DBALLENV_NAME=" + name]))
+        for g in (1, 2):   # lanes per environment
+            name = "launch_lean_w%d_s%d_d%d_g%d" % (w, ks, kd, g)
+            jobs.append((os.path.join(CSRC, "ballenv_lean_inst.cu"), os.path.join(OBJ, name + ".o"),
+                         ["-DBALLENV_W=%d" % w, "-DBALLENV_KS=%d" % ks, "-DBALLENV_KD=%d" % kd, "-DBALLENV_G=%d" % g,
+                          "-DBALLENV_NAME=" + name]))
     return deps, jobs
 
 

@@ -25,10 +25,15 @@ void launch_f32_w5_fast(const Params&, unsigned, cudaStream_t);
 void launch_f32_w10_fast(const Params&, unsigned, cudaStream_t);
 void launch_f32_wany_fast(const Params&, unsigned, cudaStream_t);
 // ballenv_lean_inst.cu: thread-per-environment kernels, one per (window, static, dynamic obstacle count)
-void launch_lean_w5_s13_d5(const Params&, unsigned, cudaStream_t);
-void launch_lean_w10_s13_d5(const Params&, unsigned, cudaStream_t);
-void launch_lean_w10_s8_d24(const Params&, unsigned, cudaStream_t);
-void launch_lean_w5_s8_d24(const Params&, unsigned, cudaStream_t);
+// and lanes per environment (g1 / g2)
+#define BALLENV_LEAN_DECL(w, ks, kd)                                          \
+  void launch_lean_w##w##_s##ks##_d##kd##_g1(const Params&, unsigned, cudaStream_t); \
+  void launch_lean_w##w##_s##ks##_d##kd##_g2(const Params&, unsigned, cudaStream_t);
+BALLENV_LEAN_DECL(5, 13, 5)
+BALLENV_LEAN_DECL(10, 13, 5)
+BALLENV_LEAN_DECL(10, 8, 24)
+BALLENV_LEAN_DECL(5, 8, 24)
+#undef BALLENV_LEAN_DECL
 }  // namespace ballenv
 
 __global__ void selftest_sqrt_kernel(long long n, unsigned long long* bad) {
@@ -205,6 +210,7 @@ struct BallenvHandle {
   size_t stage_act = 0, stage_obs = 0, stage_rew = 0, stage_done = 0;
   long long launches = 0;
   bool no_rollout = false;      // BALLENV_NO_ROLLOUT=1: ballenv_step_many launches one kernel per step (tests, profiling)
+  int lean_g = 0;               // BALLENV_LEAN_G=1|2: lanes per environment of the lean kernels (0: the measured best)
   bool no_lean = false;         // BALLENV_NO_LEAN=1: never pick the thread-per-environment kernels (tests, A/B runs)
   bool force_generic = false;   // BALLENV_FORCE_GENERIC=1 in the environment: never pick the fast specialisation (tests)
 };
@@ -229,11 +235,15 @@ LeanLauncher lean_launcher(const BallenvHandle* h, const Params& p) {
   const DevConfig& c = p.cfg;
   if (c.change_step > 254 || c.n_goals < 2 || c.step_x != 1.0 || c.step_y != 1.0 || c.radius_sum != 25.0) return nullptr;
   if (c.margin != (double)(25 + c.window / 2 + 2)) return nullptr;
-  struct Inst { int w, ks, kd; LeanLauncher fn; };
-  static const Inst kInst[] = {{5, 13, 5, launch_lean_w5_s13_d5}, {10, 13, 5, launch_lean_w10_s13_d5},
-                               {10, 8, 24, launch_lean_w10_s8_d24}, {5, 8, 24, launch_lean_w5_s8_d24}};
+  // g = lanes per environment the configuration runs best with (measured, tools/rollout_rate.py with BALLENV_LEAN_G):
+  // a pair for the 32-obstacle configurations, one lane for the reference's default 13 + 5
+  struct Inst { int w, ks, kd, g; LeanLauncher g1, g2; };
+  static const Inst kInst[] = {{5, 13, 5, 1, launch_lean_w5_s13_d5_g1, launch_lean_w5_s13_d5_g2},
+                               {10, 13, 5, 1, launch_lean_w10_s13_d5_g1, launch_lean_w10_s13_d5_g2},
+                               {10, 8, 24, 2, launch_lean_w10_s8_d24_g1, launch_lean_w10_s8_d24_g2},
+                               {5, 8, 24, 2, launch_lean_w5_s8_d24_g1, launch_lean_w5_s8_d24_g2}};
   for (const Inst& i : kInst)
-    if (i.w == c.window && i.ks == c.ks && i.kd == c.kd) return i.fn;
+    if (i.w == c.window && i.ks == c.ks && i.kd == c.kd) return (h->lean_g ? h->lean_g : i.g) == 2 ? i.g2 : i.g1;
   return nullptr;
 }
 
@@ -446,6 +456,8 @@ int ballenv_create(const BallenvConfig* cfg, int64_t n_envs, int64_t global_env_
   h->force_generic = fg != nullptr && fg[0] == '1';
   const char* nl = getenv("BALLENV_NO_LEAN");
   h->no_lean = nl != nullptr && nl[0] == '1';
+  const char* lg = getenv("BALLENV_LEAN_G");
+  h->lean_g = lg != nullptr && (lg[0] == '1' || lg[0] == '2') ? lg[0] - '0' : 0;
   const char* nr = getenv("BALLENV_NO_ROLLOUT");
   h->no_rollout = nr != nullptr && nr[0] == '1';
   if (arena != nullptr) {

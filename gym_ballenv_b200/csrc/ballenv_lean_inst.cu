@@ -1,28 +1,28 @@
 // Instantiations of the thread-per-environment kernel (ballenv_lean.cuh), one translation unit per
 // (window, static obstacles, dynamic obstacles) so that they build in parallel:
-//   -DBALLENV_W=5|10 -DBALLENV_KS=.. -DBALLENV_KD=.. -DBALLENV_NAME=launch_lean_w.._s.._d..
+//   -DBALLENV_W=5|10 -DBALLENV_KS=.. -DBALLENV_KD=.. -DBALLENV_G=1|2 -DBALLENV_NAME=launch_lean_w.._s.._d.._g..
 #include <cuda_runtime.h>
 
 #include "ballenv_lean.cuh"
 
-#if !defined(BALLENV_W) || !defined(BALLENV_KS) || !defined(BALLENV_KD) || !defined(BALLENV_NAME)
-#error "compile with -DBALLENV_W -DBALLENV_KS -DBALLENV_KD -DBALLENV_NAME"
+#if !defined(BALLENV_W) || !defined(BALLENV_KS) || !defined(BALLENV_KD) || !defined(BALLENV_G) || !defined(BALLENV_NAME)
+#error "compile with -DBALLENV_W -DBALLENV_KS -DBALLENV_KD -DBALLENV_G -DBALLENV_NAME"
 #endif
 
 namespace ballenv {
 
 template <bool kRollout>
 static void launch_lean(const Params& p, unsigned grid, cudaStream_t s) {
-  auto kern = ballenv_lean_kernel<BALLENV_W, BALLENV_KS, BALLENV_KD, kRollout>;
+  auto kern = ballenv_lean_kernel<BALLENV_W, BALLENV_KS, BALLENV_KD, BALLENV_G, kRollout>;
   static bool configured[64] = {};   // per device: function attributes belong to the device's copy of the kernel
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !configured[dev]) {
-    // seven blocks of 128 threads with their obstacle slices in shared memory: ask for the whole array
+    // seven blocks of 64 environments with their obstacle slices in shared memory: ask for the whole array
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     configured[dev] = true;
   }
-  kern<<<grid, kLeanThreads, 0, s>>>(p);
+  kern<<<grid, kLeanEnvsPerBlock * BALLENV_G, 0, s>>>(p);
 }
 
 // grid = blocks of kLeanEnvsPerBlock environments

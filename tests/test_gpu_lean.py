@@ -24,11 +24,15 @@ def _cfg(name):
     return CFG_DEFAULT if name == "default" else CFG_DENSE
 
 
-def _pair(monkeypatch, n, w, cfgname, other="roles", **kw):
-    """(lean env, comparison env) with identical seeds; `other` = "roles" | "generic"."""
+def _pair(monkeypatch, n, w, cfgname, other="roles", lanes=0, **kw):
+    """(lean env, comparison env) with identical seeds; `other` = "roles" | "generic"; lanes = lanes per environment of
+    the lean kernel (0: the library's choice for the configuration)."""
     from gym_ballenv_b200 import BallVecEnv
     cfg = _env_config(_cfg(cfgname))
+    if lanes:
+        monkeypatch.setenv("BALLENV_LEAN_G", str(lanes))
     lean = BallVecEnv(n, window=w, config=cfg, **kw)
+    monkeypatch.delenv("BALLENV_LEAN_G", raising=False)
     monkeypatch.setenv("BALLENV_NO_LEAN" if other == "roles" else "BALLENV_FORCE_GENERIC", "1")
     ref = BallVecEnv(n, window=w, config=cfg, **kw)
     monkeypatch.delenv("BALLENV_NO_LEAN" if other == "roles" else "BALLENV_FORCE_GENERIC")
@@ -47,11 +51,12 @@ def _same_state(a, b):
     assert a.error_flags() == 0 and b.error_flags() == 0
 
 
+@pytest.mark.parametrize("lanes", [1, 2])
 @pytest.mark.parametrize("w,cfgname,n,other", [(5, "default", 1000, "roles"), (10, "dense", 777, "roles"),
                                                (10, "default", 33, "generic"), (5, "dense", 65, "generic"),
                                                (10, "dense", 4096, "generic")])
-def test_lean_single_step_matches_the_other_kernels(w, cfgname, n, other, monkeypatch):
-    lean, ref = _pair(monkeypatch, n, w, cfgname, other, seed=5, max_episode_steps=15)
+def test_lean_single_step_matches_the_other_kernels(w, cfgname, n, other, lanes, monkeypatch):
+    lean, ref = _pair(monkeypatch, n, w, cfgname, other, lanes, seed=5, max_episode_steps=15)
     assert torch.equal(lean.reset(), ref.reset())
     g = torch.Generator().manual_seed(11)
     for t in range(60):
@@ -68,15 +73,18 @@ def test_lean_single_step_matches_the_other_kernels(w, cfgname, n, other, monkey
     ref.close()
 
 
+@pytest.mark.parametrize("lanes", [1, 2])
 @pytest.mark.parametrize("w,cfgname,n,keep", [(5, "default", 1000, True), (10, "dense", 777, True), (10, "dense", 96, False),
                                               (5, "dense", 31, True)])
-def test_lean_rollout_matches_per_step_launches_of_the_other_kernel(w, cfgname, n, keep, monkeypatch):
+def test_lean_rollout_matches_per_step_launches_of_the_other_kernel(w, cfgname, n, keep, lanes, monkeypatch):
     """ballenv_step_many through the lean rollout kernel (state in registers for all T steps) == T single-step
     launches of the block-of-roles kernel, with auto-resets inside the rollout and action dtypes int64 / int32 / uint8."""
     from gym_ballenv_b200 import BallVecEnv
     cfg = _env_config(_cfg(cfgname))
     T = 64
+    monkeypatch.setenv("BALLENV_LEAN_G", str(lanes))
     one = BallVecEnv(n, window=w, config=cfg, seed=21, max_episode_steps=17)
+    monkeypatch.delenv("BALLENV_LEAN_G")
     monkeypatch.setenv("BALLENV_NO_LEAN", "1")
     monkeypatch.setenv("BALLENV_NO_ROLLOUT", "1")
     per = BallVecEnv(n, window=w, config=cfg, seed=21, max_episode_steps=17)
@@ -134,12 +142,13 @@ def _inject(envs, **fields):
         e.set_state(**fields)
 
 
+@pytest.mark.parametrize("lanes", [1, 2])
 @pytest.mark.parametrize("w,cfgname", [(10, "dense"), (5, "default")])
-def test_lean_near_list_overflow_and_hits(w, cfgname, monkeypatch):
+def test_lean_near_list_overflow_and_hits(w, cfgname, lanes, monkeypatch):
     """Every obstacle of every environment piled onto the agent's window: more near obstacles than the per-lane list
     holds (rescan path), hits on the first step, resets right after."""
     n = 200
-    lean, ref = _pair(monkeypatch, n, w, cfgname, "generic", seed=3, max_episode_steps=40)
+    lean, ref = _pair(monkeypatch, n, w, cfgname, "generic", lanes, seed=3, max_episode_steps=40)
     lean.reset()
     ref.reset()
     rng = np.random.RandomState(3)
@@ -164,11 +173,12 @@ def test_lean_near_list_overflow_and_hits(w, cfgname, monkeypatch):
     ref.close()
 
 
-def test_lean_counters_out_of_lockstep_and_stale_counters(monkeypatch):
+@pytest.mark.parametrize("lanes", [1, 2])
+def test_lean_counters_out_of_lockstep_and_stale_counters(lanes, monkeypatch):
     """Injected change counters that differ inside a quad (the per-obstacle path), sit at the change step, or lie
     beyond it (treated like the change step, as the reference's `<` test does)."""
     n, w = 96, 10
-    lean, ref = _pair(monkeypatch, n, w, "dense", "generic", seed=8, max_episode_steps=0, auto_reset=False)
+    lean, ref = _pair(monkeypatch, n, w, "dense", "generic", lanes, seed=8, max_episode_steps=0, auto_reset=False)
     lean.reset()
     ref.reset()
     rng = np.random.RandomState(1)
@@ -192,12 +202,13 @@ def test_lean_counters_out_of_lockstep_and_stale_counters(monkeypatch):
     ref.close()
 
 
-def test_lean_non_integral_coordinates_take_the_general_path(monkeypatch):
+@pytest.mark.parametrize("lanes", [1, 2])
+def test_lean_non_integral_coordinates_take_the_general_path(lanes, monkeypatch):
     """Fractional agent / obstacle positions (injected; the gym ruleset never produces them): the table raster and the
     integer square root do not apply, the per-cell arithmetic of the generic kernel does - same fp32 results as the
     block-of-roles kernel, which shares that arithmetic."""
     n, w = 128, 10
-    lean, ref = _pair(monkeypatch, n, w, "dense", "roles", seed=12, max_episode_steps=0, auto_reset=False)
+    lean, ref = _pair(monkeypatch, n, w, "dense", "roles", lanes, seed=12, max_episode_steps=0, auto_reset=False)
     lean.reset()
     ref.reset()
     st = lean.get_state()
