@@ -235,15 +235,20 @@ LeanLauncher lean_launcher(const BallenvHandle* h, const Params& p) {
   const DevConfig& c = p.cfg;
   if (c.change_step > 254 || c.n_goals < 2 || c.step_x != 1.0 || c.step_y != 1.0 || c.radius_sum != 25.0) return nullptr;
   if (c.margin != (double)(25 + c.window / 2 + 2)) return nullptr;
-  // g = lanes per environment the configuration runs best with (measured, tools/rollout_rate.py with BALLENV_LEAN_G):
-  // a pair for the 32-obstacle configurations, one lane for the reference's default 13 + 5
+  // g = lanes per environment the configuration runs best with (measured, tools/lean_ab.sh): rollouts - a pair for the
+  // 32-obstacle configurations (C3: 6.5 us per step against 8.2), one lane for the reference's default 13 + 5 (3.3
+  // against 3.7); single-step launches - always a pair (13 + 5: 12.2 us per launch against 15.2: the launch is a
+  // chain of latencies, and a pair halves every lane's share of it)
   struct Inst { int w, ks, kd, g; LeanLauncher g1, g2; };
   static const Inst kInst[] = {{5, 13, 5, 1, launch_lean_w5_s13_d5_g1, launch_lean_w5_s13_d5_g2},
                                {10, 13, 5, 1, launch_lean_w10_s13_d5_g1, launch_lean_w10_s13_d5_g2},
                                {10, 8, 24, 2, launch_lean_w10_s8_d24_g1, launch_lean_w10_s8_d24_g2},
                                {5, 8, 24, 2, launch_lean_w5_s8_d24_g1, launch_lean_w5_s8_d24_g2}};
   for (const Inst& i : kInst)
-    if (i.w == c.window && i.ks == c.ks && i.kd == c.kd) return (h->lean_g ? h->lean_g : i.g) == 2 ? i.g2 : i.g1;
+    if (i.w == c.window && i.ks == c.ks && i.kd == c.kd) {
+      const int g = h->lean_g ? h->lean_g : (p.n_steps > 1 ? i.g : 2);
+      return g == 2 ? i.g2 : i.g1;
+    }
   return nullptr;
 }
 

@@ -2,6 +2,7 @@
 // (window, static obstacles, dynamic obstacles) so that they build in parallel:
 //   -DBALLENV_W=5|10 -DBALLENV_KS=.. -DBALLENV_KD=.. -DBALLENV_G=1|2 -DBALLENV_NAME=launch_lean_w.._s.._d.._g..
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 #include "ballenv_lean.cuh"
 
@@ -22,7 +23,20 @@ static void launch_lean(const Params& p, unsigned grid, cudaStream_t s) {
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     configured[dev] = true;
   }
-  kern<<<grid, kLeanEnvsPerBlock * BALLENV_G, 0, s>>>(p);
+  // programmatic stream serialisation: the grid may begin while its predecessor on the stream drains; the kernel
+  // itself waits (griddepcontrol.wait) before it reads anything (BALLENV_NO_PDL=1 launches it the plain way)
+  static const bool no_pdl = getenv("BALLENV_NO_PDL") != nullptr && getenv("BALLENV_NO_PDL")[0] == '1';
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = dim3(grid);
+  lc.blockDim = dim3(kLeanEnvsPerBlock * BALLENV_G);
+  lc.dynamicSmemBytes = 0;
+  lc.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = attr;
+  lc.numAttrs = no_pdl ? 0 : 1;
+  cudaLaunchKernelEx(&lc, kern, p);
 }
 
 // grid = blocks of kLeanEnvsPerBlock environments
