@@ -347,6 +347,7 @@ void fill_dev_config(const BallenvConfig& c, DevConfig* d) {
   d->goals_distinct = distinct ? 1 : 0;
   for (int i = 0; i < d->n_goals; ++i) d->f_goal[i] = make_float2((float)c.obs_goal_x[i], (float)c.obs_goal_y[i]);
   d->lean_integral_speeds = 1;
+  d->lean_cs4 = (uint32_t)(c.time_step_for_change & 0xff) * 0x01010101u;
   for (int j = 0; j < c.dynamic_obstacles; ++j) {
     d->speed[j] = c.obstacle_speed[j];
     d->f_speed[j] = (float)c.obstacle_speed[j];

@@ -74,6 +74,7 @@ struct DevConfig {
   float f_speed[BALLENV_MAX_DYNAMIC];
   float2 f_goal[BALLENV_MAX_GOALS];
   int lean_integral_speeds;  // every obstacle speed is an integer (integral coordinates then stay integral: ballenv_lean.cuh)
+  uint32_t lean_cs4;         // change_step in every byte (when it fits one)
 };
 
 template <typename T>
