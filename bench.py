@@ -4,11 +4,12 @@
     python bench.py --gpus N --steps K --warmup W [--workload c3|w5] [--impl reference]
 
 One bench "step" = one rollout chunk: every environment of the job advances CHUNK env-steps through ONE
-``ballenv_step_many`` call (one launch of the rollout kernel: the block keeps its 32 environments on chip for
-the whole chunk), writing the whole chunk's observations / rewards / dones into a rollout buffer.
+``ballenv_step_many`` call (one launch of the rollout kernel: a warp keeps its environments on chip for the whole
+chunk), writing the whole chunk's observations / rewards / dones into a rollout buffer.
 ``value`` = env-steps of all ranks / max-over-ranks device time.  ``closed_loop`` repeats the measurement with one
-launch per env-step (``ballenv_step``, what a policy-in-the-loop trainer calls).  See DESIGN.md (Measurement) for
-the byte model behind ``roofline``.
+launch per env-step (``ballenv_step``, what a policy-in-the-loop trainer calls); ``c5`` is that trainer (BASELINE.json
+config 5); ``e2e`` goes through the host-buffer entry point of the C ABI; with N > 1 ``c4`` is BASELINE.json config 4.
+See DESIGN.md (Measurement) for the byte model behind ``roofline``.
 
 Workloads:
   c3  65 536 envs/GPU, WINDOW=10, 8 static + 24 moving obstacles ("dense moving")   <- headline
@@ -80,8 +81,8 @@ def config_dict(spec, n, world, chunk):
     streamed = chunk * n * (8 + 4 * row + 4 + 1)
     return {"workload": spec["text"], "envs_per_gpu": n, "window": spec["window"],
             "env_steps_per_bench_step": chunk, "total_envs": world * n,
-            "sharding": "envs partitioned by global id, %d per GPU, no data-path collective; one async NCCL "
-                        "all-reduce of the 16-double episode statistics per bench step" % n,
+            "sharding": "envs partitioned by global id, %d per GPU, no data-path collective; one NCCL all-reduce of the "
+                        "16-double episode statistics after the timed region, checked against the rank-local vectors" % n,
             "l2": "inputs larger than L2: every bench step streams %.2f GB of int64 actions + rollout "
                   "obs/reward/done per GPU through HBM (L2 is 126 MB); the env state itself is revisited every "
                   "env-step by design" % (streamed / 1e9)}
@@ -212,15 +213,39 @@ def run_reference(args, spec):
 
 
 # ----------------------------------------------------------------------------------------- GPU arm
-def measure(env, torch, spec, n, steps, warmup, chunk, dist, world, sampler=None):
-    """Device-timed rollout: returns (elapsed_ms max over ranks, launches in the timed region)."""
-    from gym_ballenv_b200 import allreduce_stats
+def kernel_facts(env, spec, n_steps):
+    """Name of the kernel a step() / step_many() call launches and its ptxas figures (gym_ballenv_b200/build_info.json,
+    written by build.py from `-Xptxas -v`)."""
+    variant, lanes = env.kernel_variant(n_steps), env.kernel_lanes(n_steps)
+    w, ks, kd = spec["window"], spec["static_obstacles"], spec["dynamic_obstacles"]
+    roll = n_steps > 1
+    if variant == "lean":
+        name = "ballenv_lean_kernel<%d,%d,%d,lanes=%d,%s>" % (w, ks, kd, lanes, "rollout" if roll else "single-step")
+        key = "_ZN7ballenv19ballenv_lean_kernelILi%dELi%dELi%dELi%dELb%dEEEvNS_6ParamsE" % (w, ks, kd, lanes, 1 if roll else 0)
+    else:
+        name = "ballenv_kernel<float,%d,%s,%s>" % (w, "fast" if variant == "roles" else "generic",
+                                                   "rollout" if roll else "single-step")
+        key = None
+    facts = {"kernel": name, "registers_per_thread": None, "spill_bytes": None}
+    try:
+        info = json.load(open(os.path.join(ROOT, "gym_ballenv_b200", "build_info.json")))
+        if key in info:
+            facts["registers_per_thread"] = info[key].get("registers")
+            facts["spill_bytes"] = {"stores": info[key].get("spill_store_bytes"), "loads": info[key].get("spill_load_bytes")}
+    except Exception:
+        pass
+    return facts
+
+
+def measure(env, torch, spec, n, steps, warmup, chunk, dist, world, sampler=None, segments=5):
+    """Device-timed rollout: EXACTLY `steps` bench steps between two events, barrier + synchronize on both sides, max
+    over ranks.  The region is also cut into `segments` event-timed segments (best of 5) whose best rate
+    is reported beside the whole-region value.  -> dict(ms, launches, clocks, best_launch_us)."""
     dev = env.device
     g = torch.Generator(device=dev).manual_seed(1 + env.global_env_offset)
     ring = min(ACTION_RING, steps + warmup)
     actions = torch.randint(0, 9, (ring, chunk, n), generator=g, device=dev, dtype=torch.int64)
     out = env.alloc_rollout(chunk, keep_all_obs=True)
-    stats_work = None
     for k in range(warmup):
         env.step_many(actions[k % ring], keep_all_obs=True, out=out)
     torch.cuda.synchronize(dev)
@@ -230,50 +255,88 @@ def measure(env, torch, spec, n, steps, warmup, chunk, dist, world, sampler=None
     if sampler is not None:
         sampler.start()
     l0 = env.launch_count
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
+    segments = max(1, min(segments, steps))
+    cuts = [steps * i // segments for i in range(segments + 1)]
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(segments + 1)]
+    evs[0].record()
+    si = 1
     for k in range(steps):
         env.step_many(actions[(warmup + k) % ring], keep_all_obs=True, out=out)
-        if world > 1:   # the job's only collective: episode statistics, off the critical path
-            _, stats_work = allreduce_stats(env.stats_tensor, async_op=True)
-    ev1.record()
+        if k + 1 == cuts[si]:
+            evs[si].record()
+            si += 1
     torch.cuda.synchronize(dev)
-    if stats_work is not None:
-        stats_work.wait()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(dev)
     clocks = sampler.stop() if sampler is not None else None
-    ms = ev0.elapsed_time(ev1)
+    ms = evs[0].elapsed_time(evs[-1])
+    seg_us = [evs[i].elapsed_time(evs[i + 1]) * 1e3 / max(1, cuts[i + 1] - cuts[i]) for i in range(segments)]
+    best = min(seg_us)
     launches = env.launch_count - l0
     if world > 1:
-        t = torch.tensor([ms, float(launches)], device=dev, dtype=torch.float64)
-        dist.all_reduce(t[:1], op=dist.ReduceOp.MAX)
-        dist.all_reduce(t[1:], op=dist.ReduceOp.SUM)
-        ms, launches = float(t[0]), int(t[1])
-    bytes_streamed = actions[0].numel() * 8 + sum(o.numel() * o.element_size() for o in out)
-    return ms, launches, clocks, bytes_streamed
+        t = torch.tensor([ms, best, float(launches)], device=dev, dtype=torch.float64)
+        dist.all_reduce(t[:2], op=dist.ReduceOp.MAX)
+        dist.all_reduce(t[2:], op=dist.ReduceOp.SUM)
+        ms, best, launches = float(t[0]), float(t[1]), int(t[2])
+    return dict(ms=ms, launches=launches, clocks=clocks, best_launch_us=best)
 
 
-def measure_e2e(env, torch, n, steps, chunk, dist, world):
-    """Same rollout through ballenv_step_host: pinned host actions in, host obs/reward/done out, every env-step."""
+def reduced_stats(env, torch, dist, world):
+    """The job's only collective, checked: one all-reduce (NCCL over NVLink) of the 16-double statistics vector, and
+    the same sum computed from an all-gather of the rank-local vectors.  -> (summed vector as dict, check dict)."""
+    from gym_ballenv_b200 import STAT_NAMES, allreduce_stats
+    local = env.stats_tensor.detach().clone()
+    torch.cuda.synchronize(env.device)
+    total, work = allreduce_stats(env.stats_tensor, async_op=True)
+    if work is not None:
+        work.wait()
+    torch.cuda.synchronize(env.device)
+    check = {"collective": "none (1 rank)" if world == 1 else "nccl all_reduce(SUM) of float64[16]", "ok": True}
+    if world > 1:
+        parts = [torch.empty_like(local) for _ in range(world)]
+        dist.all_gather(parts, local)
+        ref = torch.stack(parts).sum(0)
+        check["ok"] = bool(torch.equal(ref, total))
+        check["episodes_per_rank"] = [float(p_[0]) for p_ in parts]
+    vec = total.cpu().tolist()
+    return {name: vec[i] for i, name in enumerate(STAT_NAMES)}, check
+
+
+def measure_e2e(env, torch, n, steps, chunk, dist, world, mode="many", t_call=25):
+    """The same rollout through the host-buffer entry points of the C ABI: pinned host actions in, host obs / reward /
+    done out, EVERY env-step.  mode "many": ballenv_step_many_host, t_call env-steps per call, copies and kernels of
+    consecutive steps overlapped; mode "step": one synchronous ballenv_step_host per env-step."""
+    from gym_ballenv_b200.hostmem import pinned_empty
     dev = env.device
     g = torch.Generator().manual_seed(7 + env.global_env_offset)
-    act = torch.randint(0, 9, (chunk, n), generator=g, dtype=torch.int64).pin_memory()
-    obs = torch.empty((n, env.obs_row), dtype=env._bufs[0]["obs"].dtype).pin_memory()
-    rew = torch.empty(n, dtype=torch.float32).pin_memory()
-    done = torch.empty(n, dtype=torch.uint8).pin_memory()
-    for t in range(3):
-        env.step_host(act[t], obs, rew, done)
+    obs_dtype = env._bufs[0]["obs"].dtype
+    t_call = max(1, min(t_call, chunk))
+    calls = max(1, chunk // t_call)
+    act = pinned_empty((t_call, n), torch.int64)
+    act.copy_(torch.randint(0, 9, (t_call, n), generator=g, dtype=torch.int64))
+    if mode == "many":
+        obs = pinned_empty((t_call, n, env.obs_row), obs_dtype)
+        rew = pinned_empty((t_call, n), torch.float32)
+        done = pinned_empty((t_call, n), torch.uint8)
+        run = lambda: env.step_many_host(act, obs, rew, done)
+    else:
+        obs = pinned_empty((n, env.obs_row), obs_dtype)
+        rew = pinned_empty((n,), torch.float32)
+        done = pinned_empty((n,), torch.uint8)
+
+        def run():
+            for t in range(t_call):
+                env.step_host(act[t], obs, rew, done)
+    run()
     torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = env.launch_count
     ev0.record()
-    for k in range(steps):
-        for t in range(chunk):
-            env.step_host(act[t], obs, rew, done)
+    for k in range(steps * calls):
+        run()
     ev1.record()
     torch.cuda.synchronize(dev)
     ms = ev0.elapsed_time(ev1)
@@ -281,9 +344,56 @@ def measure_e2e(env, torch, n, steps, chunk, dist, world):
         tt = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms = float(tt[0])
-    h2d = chunk * act[0].numel() * 8
-    d2h = chunk * (obs.numel() * obs.element_size() + rew.numel() * 4 + done.numel())
-    return ms, h2d, d2h, env.launch_count - l0
+    env_steps = steps * calls * t_call
+    row_b = env.obs_row * (4 if obs_dtype in (torch.float32, torch.int32) else 1)
+    h2d = calls * t_call * n * 8
+    d2h = calls * t_call * n * (row_b + 4 + 1)
+    return dict(ms=ms, env_steps_per_env=env_steps, h2d=h2d, d2h=d2h, launches=env.launch_count - l0)
+
+
+def measure_c5(torch, dev, iterations=12, n_steps=32, n=16384):
+    """BASELINE.json config 5: the actor-critic loop of examples/ball_cnn_ac3.py:528-646 driving 16 K GPU environments
+    end to end - torch Policy forward + Categorical sampling + ballenv_step per env-step (the T-step rollout replayed as
+    one CUDA graph), then the batched finish_episode update (forward, loss, backward, Adam) every n_steps."""
+    from gym_ballenv_b200 import BallVecEnv
+    from gym_ballenv_b200.a2c import GraphedRollout, Policy, a2c_loss
+    torch.manual_seed(0)
+    env = BallVecEnv(n, window=5, seed=0, device=dev)
+    policy = Policy(5).to(dev)
+    opt = torch.optim.Adam(policy.parameters(), lr=1e-3)
+    env.reset()
+    roll = GraphedRollout(env, policy, n_steps)
+
+    def iteration():
+        raw = roll.run()
+        batch = roll.evaluate(raw)
+        with torch.no_grad():
+            _, v_last = policy(raw["obs"][n_steps])
+        loss = a2c_loss(batch, 0.99, bootstrap=v_last.squeeze(-1))
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        return loss
+
+    for _ in range(3):
+        iteration()
+    torch.cuda.synchronize(dev)
+    l0 = env.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(iterations):
+        loss = iteration()
+    ev1.record()
+    torch.cuda.synchronize(dev)
+    ms = ev0.elapsed_time(ev1)
+    out = {"workload": "config 5: 16384 envs, WINDOW=5, reference defaults (13 + 5 obstacles), Policy(5) MLP 29-128-{9,1} in "
+                       "the loop (on-device Categorical), %d-step graphed rollouts, batched finish_episode + Adam per rollout"
+                       % n_steps,
+           "value": n * n_steps * iterations / (ms * 1e-3), "unit": UNIT, "ms_per_iteration": ms / iterations,
+           "env_kernel": env.kernel_variant(1), "env_launches": env.launch_count - l0, "iterations": iterations,
+           "loss_finite": bool(torch.isfinite(loss).item()), "device_error_flags": env.error_flags()}
+    env.close()
+    return out
 
 
 def run_gpu(args, spec):
@@ -293,6 +403,10 @@ def run_gpu(args, spec):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    # pinned host buffers of the end-to-end legs: this rank's CPUs and pages on the GPU's NUMA node (torchrun does not bind)
+    from gym_ballenv_b200.hostmem import bind_to_gpu_numa, copy_ceiling_gbs
+    all_cpus = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
+    numa = bind_to_gpu_numa(local)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist = None
@@ -304,10 +418,11 @@ def run_gpu(args, spec):
     n = args.envs_per_gpu
     chunk = args.chunk
 
-    def make_env(sp):   # weak scaling: n envs per GPU, global ids [rank * n, (rank + 1) * n)
-        e = make_sharded_env(world * n, rank=rank, world=world, device=dev, window=sp["window"],
-                             config=env_config(sp), seed=0)
-        assert e.num_envs == n and e.global_env_offset == rank * n
+    def make_env(sp, n_=None, **kw):   # weak scaling: n envs per GPU, global ids [rank * n, (rank + 1) * n)
+        n_ = n if n_ is None else n_
+        e = make_sharded_env(world * n_, rank=rank, world=world, device=dev, window=sp["window"],
+                             config=env_config(sp), seed=0, **kw)
+        assert e.num_envs == n_ and e.global_env_offset == rank * n_
         e.reset()
         return e
 
@@ -316,9 +431,14 @@ def run_gpu(args, spec):
     props = torch.cuda.get_device_properties(dev)
     uuid = "GPU-%s" % props.uuid if hasattr(props, "uuid") else ""
     sampler = ClockSampler(uuid, local)
-    ms, launches, clocks, streamed = measure(env, torch, spec, n, args.steps, args.warmup, chunk, dist, world, sampler)
+    m = measure(env, torch, spec, n, args.steps, args.warmup, chunk, dist, world, sampler)
+    ms, launches, clocks = m["ms"], m["launches"], m["clocks"]
     env_steps = float(world) * n * chunk * args.steps
     value = env_steps / (ms * 1e-3)
+    # the job's only collective, checked: summed statistics == sum of the rank-local vectors, and every step counted
+    stats, stats_check = reduced_stats(env, torch, dist, world)
+    stats_check["steps_expected"] = float(world) * n * chunk * (args.steps + args.warmup)
+    stats_check["ok"] = bool(stats_check["ok"] and stats["steps"] == stats_check["steps_expected"])
     balg = alg_bytes_per_env_step(spec)
     peaks = {}
     try:
@@ -327,65 +447,106 @@ def run_gpu(args, spec):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     kernel_us = ms * 1e3 / args.steps                      # average duration of one rollout launch (CHUNK env-steps)
-    achieved = balg * n * chunk / (kernel_us * 1e-6) / 1e9
     moved = moved_bytes_per_env_step(spec, chunk)
-    traffic = None
+    achieved = moved * n * chunk / (kernel_us * 1e-6) / 1e9            # bytes that must cross HBM, per second
+    achieved_alg = balg * n * chunk / (kernel_us * 1e-6) / 1e9         # the contract's algorithmic bytes, per second
+    traffic, traffic_source = None, None
     try:   # per-launch DRAM bytes of the step kernel from the committed ncu capture (profiles/)
         tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(spec["name"])
-        if tr:   # measured DRAM bytes per env-step (ncu --set full, see profiles/) x env-steps of one launch
+        if tr:
             traffic = tr["dram_bytes_per_env_step"] * n * chunk
+            traffic_source = ("not measured in this run: %s (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set "
+                              "full` launch, per env-step) x env-steps of one launch" % tr.get("source", "profiles/traffic.json"))
     except Exception:
         pass
+    facts = kernel_facts(env, spec, chunk)
 
     launches_per_step = launches / float(world * args.steps)
-    # closed loop: the same rollout with one launch per env-step (ballenv_step), i.e. what a trainer with the policy
-    # in the loop pays; bounded to a few chunks
+    # closed loop: the same rollout with one launch per env-step (ballenv_step), i.e. what a trainer with the policy in
+    # the loop pays; bounded to a few chunks
     closed = None
     if args.closed_loop_steps > 0:
         os.environ["BALLENV_NO_ROLLOUT"] = "1"
         env_c = make_env(spec)
         os.environ["BALLENV_NO_ROLLOUT"] = "0"
         cs = args.closed_loop_steps
-        msc, lc, _, _ = measure(env_c, torch, spec, n, cs, 3, chunk, dist, world)
-        us = msc * 1e3 / (cs * chunk)
-        closed = {"value": float(world) * n * chunk * cs / (msc * 1e-3), "unit": UNIT, "avg_launch_us": us,
-                  "gpu_launches": lc, "kernel": "ballenv_kernel<float,%d,fast,single-step>" % spec["window"],
-                  "roofline_frac": balg * n / (us * 1e-6) / 1e9 / peak, "alg_bytes_per_env_step": balg}
+        mc = measure(env_c, torch, spec, n, cs, 3, chunk, dist, world)
+        us = mc["ms"] * 1e3 / (cs * chunk)
+        closed = {"value": float(world) * n * chunk * cs / (mc["ms"] * 1e-3), "unit": UNIT, "avg_launch_us": us,
+                  "best_of_5_launch_us": mc["best_launch_us"] / chunk, "gpu_launches": mc["launches"],
+                  "roofline_frac_alg": balg * n / (us * 1e-6) / 1e9 / peak, "alg_bytes_per_env_step": balg,
+                  "note": "one launch per env-step, state through L2 / HBM every step (programmatic dependent launch: the "
+                          "next launch's blocks start while this one drains)"}
+        closed.update(kernel_facts(env_c, spec, 1))
         env_c.close()
 
+    # ---- end to end through the C ABI with host buffers
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    ems, h2d, d2h, e2e_launches = measure_e2e(env, torch, n, e2e_steps, chunk, dist, world)
-    e2e_value = float(world) * n * chunk * e2e_steps / (ems * 1e-3)
+    row_bytes = env.obs_row * 4
+    ceiling = copy_ceiling_gbs(dev, n * row_bytes, iters=10)          # all ranks at once: the box's D2H ceiling per GPU
+    if world > 1:
+        tt = torch.tensor([ceiling], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MIN)
+        ceiling = float(tt[0])
+    em = measure_e2e(env, torch, n, e2e_steps, chunk, dist, world, "many")
+    e2e_value = float(world) * n * em["env_steps_per_env"] / (em["ms"] * 1e-3)
+    e2e_gbs = em["d2h"] * e2e_steps / (em["ms"] * 1e-3) / 1e9
+    es = measure_e2e(env, torch, n, 1, chunk, dist, world, "step")
+    e2e_serial = {"value": float(world) * n * es["env_steps_per_env"] / (es["ms"] * 1e-3), "unit": UNIT,
+                  "api": "ballenv_step_host, one synchronous call per env-step (round 1's e2e)"}
     errs = env.error_flags()
-    stats = env.stats()
-    # the same host round trip with the observation rows as uint8 (identical 0/1 values, a quarter of the PCIe bytes;
-    # the reference casts its observation with .float() anyway, examples/ball_cnn_ac3.py:211) - reported beside e2e
-    e2e_u8 = None
-    if args.e2e_u8:
-        from gym_ballenv_b200 import make_sharded_env as _mk
-        env8 = _mk(world * n, rank=rank, world=world, device=dev, window=spec["window"], config=env_config(spec),
-                   seed=0, obs_dtype=torch.uint8)
-        env8.reset()
-        ms8, h8, d8, _ = measure_e2e(env8, torch, n, e2e_steps, chunk, dist, world)
-        e2e_u8 = {"value": float(world) * n * chunk * e2e_steps / (ms8 * 1e-3), "unit": UNIT,
-                  "h2d_bytes_per_step": h8, "d2h_bytes_per_step": d8, "obs": "uint8"}
-        env8.close()
+    e2e_alt = {}
+    if args.e2e_u8:   # the same host round trip with narrower observation rows (identical 0 / 1 values)
+        for key, dt in (("e2e_uint8_obs", torch.uint8), ("e2e_bits_obs", "bits")):
+            env8 = make_env(spec, obs_dtype=dt)
+            m8 = measure_e2e(env8, torch, n, e2e_steps, chunk, dist, world, "many")
+            e2e_alt[key] = {"value": float(world) * n * m8["env_steps_per_env"] / (m8["ms"] * 1e-3), "unit": UNIT,
+                            "h2d_bytes_per_step": m8["h2d"], "d2h_bytes_per_step": m8["d2h"],
+                            "obs": "uint8 rows" if key == "e2e_uint8_obs" else "bit-packed rows (uint32 words)",
+                            "kernel": env8.kernel_variant(1)}
+            env8.close()
 
     secondary = None
     if args.secondary and spec["name"] == "c3":
         sp2 = workload_spec("w5")
         env.close()
         env2 = make_env(sp2)
-        ms2, _, _, _ = measure(env2, torch, sp2, n, max(3, args.steps // 4), 3, chunk, dist, world)
-        v2 = float(world) * n * chunk * max(3, args.steps // 4) / (ms2 * 1e-3)
+        st2 = max(5, args.steps // 4)
+        m2 = measure(env2, torch, sp2, n, st2, 3, chunk, dist, world)
+        v2 = float(world) * n * chunk * st2 / (m2["ms"] * 1e-3)
         b2 = alg_bytes_per_env_step(sp2)
         secondary = {"workload": sp2["text"], "value": v2, "unit": UNIT,
-                     "roofline_frac": (v2 / world) * b2 / 1e9 / peak, "alg_bytes_per_env_step": b2,
-                     "frac_moved": (v2 / world) * moved_bytes_per_env_step(sp2, chunk) / 1e9 / peak}
+                     "frac": (v2 / world) * moved_bytes_per_env_step(sp2, chunk) / 1e9 / peak,
+                     "frac_alg": (v2 / world) * b2 / 1e9 / peak, "alg_bytes_per_env_step": b2,
+                     "hbm_bytes_per_env_step_moved": moved_bytes_per_env_step(sp2, chunk)}
+        secondary.update(kernel_facts(env2, sp2, chunk))
         env2.close()
+
+    # BASELINE.json config 4: 2^20 environments over the job's GPUs (W=5, reference defaults), stats all-reduced
+    c4 = None
+    if world > 1 and args.c4:
+        sp4 = workload_spec("w5")
+        n4 = (1 << 20) // world
+        env4 = make_env(sp4, n_=n4)
+        st4 = max(5, args.steps // 10)
+        m4 = measure(env4, torch, sp4, n4, st4, 3, chunk, dist, world)
+        stats4, check4 = reduced_stats(env4, torch, dist, world)
+        check4["steps_expected"] = float(world) * n4 * chunk * (st4 + 3)
+        check4["ok"] = bool(check4["ok"] and stats4["steps"] == check4["steps_expected"])
+        c4 = {"workload": "config 4: %d envs total = %d per GPU, WINDOW=5, 13 + 5 obstacles" % (world * n4, n4),
+              "value": float(world) * n4 * chunk * st4 / (m4["ms"] * 1e-3), "unit": UNIT, "steps": st4,
+              "episode_stats": {k: stats4[k] for k in ("episodes", "goals", "hits_static", "hits_dynamic", "timeouts", "steps")},
+              "stats_check": check4}
+        env4.close()
+
+    c5 = measure_c5(torch, dev) if (rank == 0 and args.c5) else None
+    if world > 1:
+        dist.barrier()
 
     base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        if all_cpus is not None:
+            os.sched_setaffinity(0, all_cpus)   # the CPU baseline runs on all host cores, not on the GPU's node only
         base = cpu_baseline(spec, seconds=args.cpu_seconds)
 
     if rank == 0:
@@ -394,30 +555,42 @@ def run_gpu(args, spec):
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config_dict(spec, n, world, chunk),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic,
-                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650",
-                         "kernel": "ballenv_kernel<float,%d,fast,rollout>" % spec["window"],
-                         "alg_bytes_per_env_step": balg, "env_steps_per_launch": n * chunk,
-                         "avg_launch_us": kernel_us, "launches_per_bench_step": launches_per_step,
-                         "note": "achieved = SURVEY 8(d) algorithmic bytes x env-steps per launch / launch time; the "
-                                 "rollout kernel keeps the state on chip, so only hbm_bytes_per_env_step_moved must "
-                                 "cross HBM per env-step (frac_moved is that stream against the same peak)",
-                         "hbm_bytes_per_env_step_moved": moved,
-                         "frac_moved": moved * n * chunk / (kernel_us * 1e-6) / 1e9 / peak},
+            "roofline": dict({"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                              "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_source,
+                              "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650",
+                              "hbm_bytes_per_env_step_moved": moved, "env_steps_per_launch": n * chunk,
+                              "avg_launch_us": kernel_us, "best_of_5_launch_us": m["best_launch_us"],
+                              "launches_per_bench_step": launches_per_step,
+                              "achieved_alg": achieved_alg, "frac_alg": achieved_alg / peak, "alg_bytes_per_env_step": balg,
+                              "note": "achieved / frac = the bytes that must cross HBM (action in; observation, reward, "
+                                      "done out; the state once per launch) per second, against the measured copy peak. "
+                                      "achieved_alg / frac_alg use SURVEY 8(d)'s algorithmic bytes, which count the state "
+                                      "as read and written every env-step although the rollout kernel keeps it on chip: "
+                                      "that figure can exceed 1 and is not an HBM fraction."}, **facts),
             "closed_loop": closed,
+            "c5": c5,
             "cpu_baseline": base,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "api": "ballenv_step_host (C ABI), pinned host buffers, fp32 obs to host "
-                                               "every env-step"},
-            "e2e_uint8_obs": e2e_u8,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": em["h2d"], "d2h_bytes_per_step": em["d2h"],
+                    "steps": e2e_steps,
+                    "api": "ballenv_step_many_host (C ABI), 25 env-steps per call: pinned host actions in and fp32 obs / "
+                           "reward / done out EVERY env-step, copies of consecutive steps overlapped with the kernels",
+                    "pcie": {"d2h_ceiling_gbs_per_gpu": ceiling, "achieved_d2h_gbs_per_gpu": e2e_gbs,
+                             "pcie_frac": e2e_gbs / ceiling if ceiling else None,
+                             "how": "ceiling = bare cudaMemcpyAsync of one step's rows (%d MB) device -> pinned host, all "
+                                    "ranks at once, min over ranks" % (n * row_bytes // (1 << 20))},
+                    "numa": numa},
+            "e2e_step_host": e2e_serial,
             "gpu_launches": launches,
             "clocks": clocks,
-            "episode_stats": {k: stats[k] for k in ("episodes", "goals", "hits_static", "hits_dynamic", "timeouts")},
+            "episode_stats": {k: stats[k] for k in ("episodes", "goals", "hits_static", "hits_dynamic", "timeouts", "steps")},
+            "stats_check": stats_check,
             "device_error_flags": errs,
         }
+        line.update(e2e_alt)
         if secondary is not None:
             line["secondary"] = secondary
+        if c4 is not None:
+            line["c4"] = c4
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -439,6 +612,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--secondary", type=int, default=1)
+    ap.add_argument("--c4", type=int, default=1, help="N > 1: also run config 4 (2^20 envs over the job's GPUs)")
+    ap.add_argument("--c5", type=int, default=1, help="also run config 5 (A2C loop, 16 K envs) on rank 0")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

@@ -23,7 +23,7 @@ OBS_F32, OBS_U8, OBS_BITS = 0, 1, 2
 ACT_INDEX_I64, ACT_INDEX_I32, ACT_INDEX_U8, ACT_XY_F32, ACT_XY_F64 = 0, 1, 2, 3, 4
 FLAG_GOAL, FLAG_HIT, FLAG_TRUNCATED, FLAG_HIT_DYNAMIC = 1, 2, 4, 8
 DEVERR_BAD_ACTION, DEVERR_TAPE_EXHAUSTED, DEVERR_RESET_STUCK = 1, 2, 4
-KERNEL_GENERIC, KERNEL_ROLES, KERNEL_LEAN = 0, 1, 2
+KERNEL_GENERIC, KERNEL_ROLES, KERNEL_LEAN, KERNEL_LEAN2 = 0, 1, 2, 3
 STAT_NAMES = ("episodes", "return_sum", "length_sum", "goals", "hits_static", "hits_dynamic", "timeouts", "steps")
 
 
@@ -57,6 +57,7 @@ EXPORTS = (
     "ballenv_create", "ballenv_destroy", "ballenv_state_ptrs", "ballenv_reset", "ballenv_step",
     "ballenv_step_many", "ballenv_observe", "ballenv_observe_features", "ballenv_observe_blocks", "ballenv_step_host", "ballenv_set_draw_tape", "ballenv_stats",
     "ballenv_stats_reset", "ballenv_error_flags", "ballenv_launch_count", "ballenv_selftest", "ballenv_kernel_variant",
+    "ballenv_step_many_host",
 )
 
 
@@ -78,6 +79,7 @@ def _bind(lib):
     lib.ballenv_observe_features.argtypes = [vp, vp, vp]
     lib.ballenv_observe_blocks.argtypes = [vp, vp, vp]
     lib.ballenv_step_host.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp]
+    lib.ballenv_step_many_host.argtypes = [vp, vp, C.c_int, i32, vp, vp, vp, vp]
     lib.ballenv_set_draw_tape.argtypes = [vp, vp, i64, vp, i64, i32]
     lib.ballenv_stats.argtypes = [vp, vp, vp]
     lib.ballenv_stats_reset.argtypes = [vp, vp]

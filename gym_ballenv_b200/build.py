@@ -69,7 +69,39 @@ def _compile(job, deps, force, log):
     log.append((os.path.basename(obj), r.stderr))
     if r.returncode != 0:
         raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (obj, " ".join(cmd), r.stderr))
+    with open(obj + ".ptxas", "w") as f:   # `-Xptxas -v` of this object: registers, spills, shared memory per kernel
+        f.write(r.stderr)
     return obj
+
+
+def _kernel_info(objs):
+    """{demangled-ish kernel key: {registers, spill_store_bytes, spill_load_bytes, stack_bytes, smem_bytes}} from the
+    ptxas logs kept beside the objects (bench.py quotes the step kernels' figures in its roofline object)."""
+    import re
+    info = {}
+    for obj in objs:
+        try:
+            text = open(obj + ".ptxas").read()
+        except OSError:
+            continue
+        cur = None
+        for line in text.splitlines():
+            m = re.search(r"Compiling entry function '([^']+)'", line)
+            if m:
+                cur = m.group(1)
+                info[cur] = {"object": os.path.basename(obj)}
+                continue
+            if cur is None:
+                continue
+            m = re.search(r"(\d+) bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads", line)
+            if m and "stack_bytes" not in info[cur]:   # the entry function's own line (those of its callees follow)
+                info[cur].update(stack_bytes=int(m.group(1)), spill_store_bytes=int(m.group(2)), spill_load_bytes=int(m.group(3)))
+            m = re.search(r"Used (\d+) registers", line)
+            if m:
+                info[cur]["registers"] = int(m.group(1))
+                ms = re.search(r"(\d+) bytes smem", line)
+                info[cur]["smem_bytes"] = int(ms.group(1)) if ms else 0
+    return info
 
 
 def build(force=False, verbose=False):
@@ -83,6 +115,9 @@ def build(force=False, verbose=False):
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n%s\n%s" % (" ".join(cmd), r.stderr))
+    import json
+    with open(os.path.join(HERE, "build_info.json"), "w") as f:
+        json.dump(_kernel_info(objs), f, indent=0, sort_keys=True)
     if verbose:
         for name, err in log:
             for line in err.splitlines():

@@ -205,9 +205,12 @@ struct BallenvHandle {
   long long step_tape_steps = 0, step_tape_pos = 0;
   uint32_t* reset_tape = nullptr;
   // device staging for ballenv_step_host
-  char* stage = nullptr;
-  size_t stage_bytes = 0;
+  char* stage = nullptr;        // two staging sets (ballenv_step_many_host alternates between them)
+  size_t stage_bytes = 0, stage_set = 0;
   size_t stage_act = 0, stage_obs = 0, stage_rew = 0, stage_done = 0;
+  // ballenv_step_many_host: copy streams either way and the events that order them against the compute stream
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_k[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr}, ev_start = nullptr;
   long long launches = 0;
   bool no_rollout = false;      // BALLENV_NO_ROLLOUT=1: ballenv_step_many launches one kernel per step (tests, profiling)
   int lean_g = 0;               // BALLENV_LEAN_G=1|2: lanes per environment of the lean kernels (0: the measured best)
@@ -230,7 +233,7 @@ bool fast_eligible(const BallenvHandle* h, const Params& p) {
 // thread-per-environment kernels (ballenv_lean.cuh): the production configuration with one of the instantiated
 // obstacle counts, integral geometry and a change step that fits a byte
 typedef void (*LeanLauncher)(const Params&, unsigned, cudaStream_t);
-LeanLauncher lean_launcher(const BallenvHandle* h, const Params& p) {
+LeanLauncher lean_launcher(const BallenvHandle* h, const Params& p, int* lanes = nullptr) {
   if (!fast_eligible(h, p) || h->no_lean || p.lean_tab == nullptr) return nullptr;
   const DevConfig& c = p.cfg;
   if (c.change_step > 254 || c.n_goals < 2 || c.step_x != 1.0 || c.step_y != 1.0 || c.radius_sum != 25.0) return nullptr;
@@ -247,6 +250,7 @@ LeanLauncher lean_launcher(const BallenvHandle* h, const Params& p) {
   for (const Inst& i : kInst)
     if (i.w == c.window && i.ks == c.ks && i.kd == c.kd) {
       const int g = h->lean_g ? h->lean_g : (p.n_steps > 1 ? i.g : 2);
+      if (lanes != nullptr) *lanes = g;
       return g == 2 ? i.g2 : i.g1;
     }
   return nullptr;
@@ -363,7 +367,7 @@ int ensure_stage(BallenvHandle* h, int action_kind) {
   const size_t o = align_up(n * (size_t)obs_row_elems(h->cfg) * obs_elem_bytes(h->cfg), 256);
   const size_t r = align_up(n * 8, 256);
   const size_t d = align_up(n, 256);
-  const size_t need = a + o + r + d;
+  const size_t need = 2 * (a + o + r + d);
   (void)action_kind;
   if (h->stage_bytes < need) {
     if (h->stage) cudaFree(h->stage);
@@ -371,6 +375,7 @@ int ensure_stage(BallenvHandle* h, int action_kind) {
     h->stage_bytes = 0;
     CUDA_TRY(cudaMalloc(&h->stage, need));
     h->stage_bytes = need;
+    h->stage_set = a + o + r + d;
     h->stage_act = 0;
     h->stage_obs = a;
     h->stage_rew = a + o;
@@ -557,6 +562,14 @@ int ballenv_destroy(BallenvHandle* h) {
   if (h->step_tape) cudaFree(h->step_tape);
   if (h->reset_tape) cudaFree(h->reset_tape);
   if (h->stage) cudaFree(h->stage);
+  if (h->s_in) cudaStreamDestroy(h->s_in);
+  if (h->s_out) cudaStreamDestroy(h->s_out);
+  for (int i = 0; i < 2; ++i) {
+    if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]);
+    if (h->ev_k[i]) cudaEventDestroy(h->ev_k[i]);
+    if (h->ev_out[i]) cudaEventDestroy(h->ev_out[i]);
+  }
+  if (h->ev_start) cudaEventDestroy(h->ev_start);
   delete h;
   return BALLENV_OK;
 }
@@ -745,6 +758,64 @@ int ballenv_step_host(BallenvHandle* h, const void* actions_host, int action_kin
   return BALLENV_OK;
 }
 
+int ballenv_step_many_host(BallenvHandle* h, const void* actions_host, int action_kind, int32_t n_steps, void* obs_host,
+                           void* reward_host, uint8_t* done_host, ballenv_stream_t stream) {
+  if (h == nullptr || actions_host == nullptr) return fail(BALLENV_EINVAL, "NULL argument");
+  const int ab = action_bytes(action_kind);
+  if (ab == 0) return fail(BALLENV_EINVAL, "unknown action_kind %d", action_kind);
+  if (n_steps < 0) return fail(BALLENV_EINVAL, "n_steps < 0");
+  if (n_steps == 0) return BALLENV_OK;
+  DeviceGuard guard(h->device);
+  int rc = ensure_stage(h, action_kind);
+  if (rc != BALLENV_OK) return rc;
+  if (h->s_in == nullptr) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      CUDA_TRY(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
+      CUDA_TRY(cudaEventCreateWithFlags(&h->ev_k[i], cudaEventDisableTiming));
+      CUDA_TRY(cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming));
+    }
+    CUDA_TRY(cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming));
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t n = (size_t)h->n;
+  const size_t obs_b = n * (size_t)obs_row_elems(h->cfg) * obs_elem_bytes(h->cfg);
+  const size_t rew_b = n * (h->cfg.precision == BALLENV_F64 ? 8 : 4);
+  // Three streams, two staging sets: while the kernel of step t runs on `stream`, the actions of step t + 1 travel
+  // host -> device and the rows / rewards / dones of step t - 1 device -> host.  A set is reused two steps later: its
+  // actions once the kernel that read them has run, its outputs once they have been copied out.
+  CUDA_TRY(cudaEventRecord(h->ev_start, s));          // the copy streams start behind whatever the caller had enqueued
+  CUDA_TRY(cudaStreamWaitEvent(h->s_in, h->ev_start, 0));
+  CUDA_TRY(cudaStreamWaitEvent(h->s_out, h->ev_start, 0));
+  for (int t = 0; t < n_steps; ++t) {
+    const int b = t & 1;
+    char* st = h->stage + (size_t)b * h->stage_set;
+    if (t >= 2) CUDA_TRY(cudaStreamWaitEvent(h->s_in, h->ev_k[b], 0));      // kernel t - 2 has read this set's actions
+    CUDA_TRY(cudaMemcpyAsync(st + h->stage_act, (const char*)actions_host + (size_t)t * n * ab, n * ab,
+                             cudaMemcpyHostToDevice, h->s_in));
+    CUDA_TRY(cudaEventRecord(h->ev_in[b], h->s_in));
+    CUDA_TRY(cudaStreamWaitEvent(s, h->ev_in[b], 0));
+    if (t >= 2) CUDA_TRY(cudaStreamWaitEvent(s, h->ev_out[b], 0));          // outputs of step t - 2 have left this set
+    rc = ballenv_step(h, st + h->stage_act, action_kind, obs_host ? st + h->stage_obs : nullptr,
+                      reward_host ? st + h->stage_rew : nullptr, done_host ? (uint8_t*)(st + h->stage_done) : nullptr, stream);
+    if (rc != BALLENV_OK) return rc;
+    CUDA_TRY(cudaEventRecord(h->ev_k[b], s));
+    CUDA_TRY(cudaStreamWaitEvent(h->s_out, h->ev_k[b], 0));
+    if (obs_host)
+      CUDA_TRY(cudaMemcpyAsync((char*)obs_host + (size_t)t * obs_b, st + h->stage_obs, obs_b, cudaMemcpyDeviceToHost, h->s_out));
+    if (reward_host)
+      CUDA_TRY(cudaMemcpyAsync((char*)reward_host + (size_t)t * rew_b, st + h->stage_rew, rew_b, cudaMemcpyDeviceToHost,
+                               h->s_out));
+    if (done_host)
+      CUDA_TRY(cudaMemcpyAsync(done_host + (size_t)t * n, st + h->stage_done, n, cudaMemcpyDeviceToHost, h->s_out));
+    CUDA_TRY(cudaEventRecord(h->ev_out[b], h->s_out));
+  }
+  CUDA_TRY(cudaStreamSynchronize(h->s_out));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return BALLENV_OK;
+}
+
 int ballenv_set_draw_tape(BallenvHandle* h, const uint32_t* step_tape, int64_t n_steps, const uint32_t* reset_tape,
                           int64_t n_episodes, int32_t attempts) {
   if (h == nullptr) return fail(BALLENV_EINVAL, "handle is NULL");
@@ -815,7 +886,8 @@ int ballenv_kernel_variant(BallenvHandle* h, int action_kind, int32_t n_steps) {
   p.reset_tape = h->reset_tape;
   p.step_tape = h->step_tape;
   if (p.n_steps > 1 && h->no_rollout) p.n_steps = 1;
-  if (lean_launcher(h, p) != nullptr) return BALLENV_KERNEL_LEAN;
+  int lanes = 1;
+  if (lean_launcher(h, p, &lanes) != nullptr) return lanes == 2 ? BALLENV_KERNEL_LEAN2 : BALLENV_KERNEL_LEAN;
   return fast_eligible(h, p) ? BALLENV_KERNEL_ROLES : BALLENV_KERNEL_GENERIC;
 }
 

@@ -250,6 +250,25 @@ class BallVecEnv:
                                     self._stream()))
         return obs_out, reward_out, done_out
 
+    def step_many_host(self, actions, obs_out, reward_out, done_out):
+        """T host-buffer steps as one pipelined call (ballenv_step_many_host): ``actions`` [T, N] and the outputs
+        ``obs_out`` [T, N, row], ``reward_out`` [T, N], ``done_out`` [T, N] uint8 are CPU tensors (pinned for speed).
+        Copies in, kernels and copies out of consecutive steps overlap; the call returns synchronised."""
+        T = int(actions.shape[0])
+        kind = self._action_kind(actions[0], self.num_envs)
+        n = self.num_envs
+        if (not actions.is_contiguous() or tuple(obs_out.shape) != (T, n, self.obs_row) or tuple(reward_out.shape) != (T, n)
+                or tuple(done_out.shape) != (T, n) or done_out.dtype != torch.uint8 or reward_out.dtype != self._real
+                or obs_out.dtype != self._bufs[0]["obs"].dtype
+                or not (obs_out.is_contiguous() and reward_out.is_contiguous() and done_out.is_contiguous())
+                or any(t.device.type != "cpu" for t in (actions, obs_out, reward_out, done_out))):
+            raise ValueError("step_many_host needs contiguous CPU tensors: actions [T, N], obs [T, N, row], reward [T, N], "
+                             "done [T, N] uint8")
+        check(LIB.ballenv_step_many_host(self._h, C.c_void_p(actions.data_ptr()), kind, T, C.c_void_p(obs_out.data_ptr()),
+                                         C.c_void_p(reward_out.data_ptr()), C.c_void_p(done_out.data_ptr()),
+                                         self._stream()))
+        return obs_out, reward_out, done_out
+
     # ------------------------------------------------------------------ state injection / inspection
     def get_state(self) -> Dict[str, torch.Tensor]:
         """Copies of the SoA state.  Obstacles are [K, N]; ``dynamic_goal`` / ``dynamic_counter`` unpack dynamic_meta."""
@@ -314,7 +333,12 @@ class BallVecEnv:
         "lean" (thread per environment), "roles" (block of roles, production specialisation) or "generic"."""
         kind = {torch.int64: L.ACT_INDEX_I64, torch.int32: L.ACT_INDEX_I32, torch.uint8: L.ACT_INDEX_U8,
                 torch.float32: L.ACT_XY_F32, torch.float64: L.ACT_XY_F64}[action_dtype]
-        return ("generic", "roles", "lean")[check(LIB.ballenv_kernel_variant(self._h, kind, int(n_steps)))]
+        return ("generic", "roles", "lean", "lean")[check(LIB.ballenv_kernel_variant(self._h, kind, int(n_steps)))]
+
+    def kernel_lanes(self, n_steps: int = 1) -> int:
+        """Lanes per environment of the lean kernel step() / step_many() launches (1 or 2; 0: another kernel)."""
+        v = check(LIB.ballenv_kernel_variant(self._h, L.ACT_INDEX_I64, int(n_steps)))
+        return {L.KERNEL_LEAN: 1, L.KERNEL_LEAN2: 2}.get(v, 0)
 
     @property
     def launch_count(self) -> int:

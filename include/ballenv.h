@@ -223,6 +223,17 @@ int ballenv_step_host(BallenvHandle *h, const void *actions_host, int action_kin
                       void *reward_host, uint8_t *done_host, ballenv_stream_t stream);
 
 /*
+ * T consecutive ballenv_step_host calls as one pipelined call (open-loop host rollouts, or a host policy that acts on
+ * observations one step old): actions_host [T][n], obs_host [T][n][row] (or NULL), reward_host [T][n], done_host [T][n]
+ * (or NULL).  While the kernel of step t runs on `stream`, the actions of step t + 1 travel host -> device and the
+ * results of step t - 1 device -> host on two internal copy streams (two device staging sets).  Same results as T
+ * calls of ballenv_step_host; returns synchronised.  Pin the host buffers (and allocate them on the GPU's NUMA node)
+ * for speed.
+ */
+int ballenv_step_many_host(BallenvHandle *h, const void *actions_host, int action_kind, int32_t n_steps, void *obs_host,
+                           void *reward_host, uint8_t *done_host, ballenv_stream_t stream);
+
+/*
  * Parity mode: replace Philox words by injected ones (copied to the device; NULL clears a tape).
  * step_tape  : host uint32 [n_steps][n][dynamic_obstacles][2]; step s of the tape answers the s-th
  *              ballenv_step call after this call.
@@ -241,10 +252,12 @@ int ballenv_error_flags(BallenvHandle *h, uint32_t *out /* host */, ballenv_stre
 int64_t ballenv_launch_count(BallenvHandle *h);
 /* Which kernel a ballenv_step (n_steps = 1) or ballenv_step_many (n_steps > 1) call with this action kind and
  * observation rows requested launches (no reference counterpart; diagnostics, bench.py, tests):
- * BALLENV_KERNEL_GENERIC, _ROLES (block of roles, production specialisation) or _LEAN (thread per environment). */
+ * BALLENV_KERNEL_GENERIC, _ROLES (block of roles, production specialisation), _LEAN (one lane per environment) or
+ * _LEAN2 (a pair of lanes per environment). */
 #define BALLENV_KERNEL_GENERIC 0
 #define BALLENV_KERNEL_ROLES 1
 #define BALLENV_KERNEL_LEAN 2
+#define BALLENV_KERNEL_LEAN2 3
 int ballenv_kernel_variant(BallenvHandle *h, int action_kind, int32_t n_steps);
 /* Device self-tests of the arithmetic shortcuts the step kernel takes (no reference counterpart; run by the GPU
  * tests).  which = 0: the integer square root used for the distance to the goal when all coordinates are integral
