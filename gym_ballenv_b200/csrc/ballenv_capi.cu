@@ -141,6 +141,15 @@ int validate(const BallenvConfig* c) {
   return BALLENV_OK;
 }
 
+// The configuration a handle runs with.  The pygame ruleset always stores and computes in fp64: its coordinates are
+// non-integral (uniform doubles, raw float actions) and its progress reward is the difference of two nearby distances,
+// so fp32 positions cannot hold the 1e-5 relative reward tolerance; it is off the performance path anyway.
+BallenvConfig effective_config(const BallenvConfig& c) {
+  BallenvConfig e = c;
+  if (e.ruleset == BALLENV_RULESET_PYGAME) e.precision = BALLENV_F64;
+  return e;
+}
+
 struct Layout {
   size_t agent_x, agent_y, goal_x, goal_y, dist, total, acc, ep_len, episode, tick;
   size_t stat_x, stat_y, dyn_x, dyn_y, dyn_meta, flags, stats, errors, lean_tab, lean_tab_entries, bytes;
@@ -431,7 +440,7 @@ int64_t ballenv_state_bytes(const BallenvConfig* cfg, int64_t n_envs) {
   int rc = validate(cfg);
   if (rc != BALLENV_OK) return rc;
   if (n_envs <= 0) return fail(BALLENV_EINVAL, "n_envs must be positive");
-  return (int64_t)make_layout(*cfg, n_envs).bytes;
+  return (int64_t)make_layout(effective_config(*cfg), n_envs).bytes;
 }
 
 int ballenv_create(const BallenvConfig* cfg, int64_t n_envs, int64_t global_env_offset, int device, uint64_t seed,
@@ -457,12 +466,12 @@ int ballenv_create(const BallenvConfig* cfg, int64_t n_envs, int64_t global_env_
   DeviceGuard guard(device);
   BallenvHandle* h = new (std::nothrow) BallenvHandle();
   if (h == nullptr) return fail(BALLENV_ENOMEM, "out of host memory");
-  h->cfg = *cfg;
+  h->cfg = effective_config(*cfg);
   h->n = n_envs;
   h->g0 = global_env_offset;
   h->device = device;
   h->seed = seed;
-  h->L = make_layout(*cfg, n_envs);
+  h->L = make_layout(h->cfg, n_envs);
   const char* fg = getenv("BALLENV_FORCE_GENERIC");
   h->force_generic = fg != nullptr && fg[0] == '1';
   const char* nl = getenv("BALLENV_NO_LEAN");

@@ -73,7 +73,10 @@ class BallVecEnv:
         self._h = h
         self._ptrs = L.BallenvStatePtrs()
         check(LIB.ballenv_state_ptrs(self._h, C.byref(self._ptrs)))
-        self._real = torch.float64 if parity else torch.float32
+        # positions / rewards are float64 in parity mode - and always for the pygame ruleset (non-integral coordinates:
+        # fp32 storage cannot hold the 1e-5 reward tolerance there; the library promotes it, real_bytes tells)
+        self._real = torch.float64 if int(self._ptrs.real_bytes) == 8 else torch.float32
+        self.parity = self._real == torch.float64
         self._make_views()
         self.obs_row = int(self._ptrs.obs_row_elems)
         obs_t = torch.int32 if obs_dtype == "bits" else obs_dtype

@@ -49,7 +49,9 @@ extern "C" {
 #define BALLENV_RULESET_PYGAME 1  /* ballenv_pygame.py : createBoard (100x100, float coordinates) */
 
 /* BallenvConfig.precision : type the positions are stored and compared in */
-#define BALLENV_F32 0   /* production: fp32 positions, fp64 distance/reward arithmetic in registers */
+#define BALLENV_F32 0   /* production: fp32 positions, fp64 distance/reward arithmetic in registers (gym ruleset; the
+                           pygame ruleset, whose coordinates are non-integral, always runs as BALLENV_F64:
+                           BallenvStatePtrs.real_bytes tells) */
 #define BALLENV_F64 1   /* parity mode: everything fp64, operation order of the reference */
 
 /* BallenvConfig.obs_format : element type of the observation rows */

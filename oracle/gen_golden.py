@@ -51,6 +51,13 @@ CFG_BUSY = dict(static_obstacles=3, dynamic_obstacles=4, obstacle_speed=[1, 2, 1
                 time_step_for_change=7, rd_th_obs=45, static_penalty=[1, 1], dynamic_penalty=[4000, 8000])
 
 
+# repeated obstacle goals (indices 0 and 2 are the same point): the goal-change step draws among the goals whose
+# POSITION differs from the current one (ballenv_env.py:351-352), duplicates included as separate list entries
+CFG_DUPGOALS = dict(static_obstacles=2, dynamic_obstacles=3, obstacle_speed=[1, 2, 1],
+                    obs_goal_position=['40,30', '250,5', '40,30', '460,20'],
+                    time_step_for_change=5, rd_th_obs=50, static_penalty=[1, 1], dynamic_penalty=[4000, 8000])
+
+
 def _pack_rows(obs, window):
     """float obs [4 + W*W] -> (quadrant index, W row bitmasks)."""
     q = int(np.argmax(obs[:4]))
@@ -535,6 +542,7 @@ def main(argv):
         "edge_gym": lambda: edge_cases(),
         "rollout_philox_default": lambda: compress_rollout(rollout(CFG_DEFAULT, 24, 260, 7, "philox", 120, g0=1000)),
         "rollout_philox_busy": lambda: compress_rollout(rollout(CFG_BUSY, 16, 200, 11, "philox", 40, g0=5)),
+        "rollout_philox_dupgoals": lambda: compress_rollout(rollout(CFG_DUPGOALS, 16, 160, 13, "philox", 40, g0=3)),
         "rollout_philox_dense": lambda: compress_rollout(rollout(CFG_DENSE, 8, 120, 3, "philox", 1000, windows=(10,))),
         "rollout_mt_default": lambda: compress_rollout(rollout(CFG_DEFAULT, 8, 150, 0, "mt", 60)),
         "features_kat": lambda: features_kats(),

@@ -44,3 +44,10 @@ def tapes_from_golden(z, meta):
     ns[5::2] = 460
     reset = (((rv << np.uint64(32)) + ns - np.uint64(1)) // ns).astype(np.uint32)
     return step, reset
+
+
+def canonical_goal_index(cfg):
+    """index -> first index of a goal with the same position.  The reference holds an obstacle's goal as a position
+    (ballenv_env.py:351-353), so with repeated goals an index is only defined up to that mapping."""
+    goals = parse_goals(cfg)
+    return np.array([goals.index(g) for g in goals])

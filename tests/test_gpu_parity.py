@@ -54,11 +54,17 @@ def _check_state(env, z, prefix, idx, ks, kd, exact_dist=True):
 
 @pytest.mark.parametrize("parity", [False, True])
 @pytest.mark.parametrize("name", ["rollout_philox_default", "rollout_philox_busy", "rollout_philox_dense",
-                                  "rollout_mt_default"])
+                                  "rollout_mt_default", "rollout_philox_dupgoals"])
 def test_golden_rollout(name, parity):
+    """Rollouts recorded by running the reference itself (oracle/gen_golden.py through oracle/ref_shim.py).
+    rollout_philox_dupgoals has two equal obstacle goals: the goal-change step then takes the kernels' generic
+    branch (move_obstacle with goals_distinct == 0: candidates are the goals whose POSITION differs,
+    ballenv_env.py:351-352); a goal is compared by its canonical (first) index, as the reference only holds positions."""
     from gym_ballenv_b200 import BallVecEnv
+    from helpers import canonical_goal_index
     z, meta = load_golden(name)
     cfg = meta["cfg"]
+    canon = canonical_goal_index(cfg)
     ks, kd = cfg["static_obstacles"], cfg["dynamic_obstacles"]
     n, T, g0 = meta["n_envs"], meta["T"], meta["g0"]
     for w in meta["windows"]:
@@ -83,7 +89,7 @@ def test_golden_rollout(name, parity):
             s = _check_state(env, z, "rec_", t, ks, kd)
             assert np.array_equal(s["acc_reward"].cpu().numpy(), z["rec_acc"][t]), (t, w)
             assert np.array_equal(s["ep_len"].cpu().numpy(), z["rec_ep_len"][t])
-            assert np.array_equal(s["dynamic_goal"].cpu().numpy().T, z["rec_dyn_goal"][t])
+            assert np.array_equal(canon[s["dynamic_goal"].cpu().numpy().T], z["rec_dyn_goal"][t])
             assert np.array_equal(s["dynamic_counter"].cpu().numpy().T, z["rec_dyn_counter"][t])
             q, rows = _rows_from_obs(obs, w)
             assert np.array_equal(q, z["rec_quadrant"][t]), (t, w)
@@ -365,12 +371,13 @@ def test_rollout_kernel_matches_per_step_launches(w, cfgname, n, keep, no_lean, 
 @pytest.mark.gpu
 @pytest.mark.parametrize("parity", [True, False])
 def test_pygame_ruleset_against_the_reference_rollout(parity):
-    """createBoard (ballenv_pygame.py:650-706, 460-513) recorded through the shim, raw float actions, auto-reset.
-    fp64 parity mode: positions and done bit-exact; distances / rewards to 1e-12 relative - for non-integral
-    coordinates glibc's pow(x, 2) (what math.pow calls) is not guaranteed correctly rounded, the kernel's x * x is, so
-    a distance may differ in the last bit ("fp64 parity mode").  fp32 production mode: positions are stored
-    in fp32 (the coordinates are non-integral here), so rewards agree to 1e-4 relative / 1e-6 absolute and the
-    comparison stops at the first episode end (a discrete event may flip on a last-bit difference)."""
+    """createBoard (ballenv_pygame.py:650-706, 460-513) recorded through the shim, raw float actions, auto-reset, the
+    whole rollout including the resets.  Positions and done bit-exact; distances / rewards to 1e-12 relative - for
+    non-integral coordinates glibc's pow(x, 2) (what math.pow calls) is not guaranteed correctly rounded, the kernel's
+    x * x is, so a distance may differ in the last bit ("fp64 parity mode").  The pygame ruleset
+    stores fp64 whatever precision is asked for (its rewards are differences of nearby distances of non-integral
+    points: fp32 positions cannot hold the 1e-5 relative tolerance), so `parity=False` runs the same arithmetic: the
+    rewards are inside north_star's 1e-5 - by eleven orders of magnitude."""
     from gym_ballenv_b200 import BallVecEnv, EnvConfig
     z, meta = load_golden("rollout_pygame")
     n, T, g0 = meta["n_envs"], meta["T"], meta["g0"]
@@ -378,14 +385,15 @@ def test_pygame_ruleset_against_the_reference_rollout(parity):
                      seed=meta["seed"], parity=parity, global_env_offset=g0)
     env.reset()
     st = env.get_state()
-    real = np.float64 if parity else np.float32
+    real = np.float64
+    assert env.parity and st["agent_x"].dtype == torch.float64
+    parity = True
     assert np.array_equal(st["agent_x"].cpu().numpy(), z["init_agent"][:, 0].astype(real))
     assert np.array_equal(st["goal_y"].cpu().numpy(), z["init_goal"][:, 1].astype(real))
     assert np.array_equal(st["static_x"].cpu().numpy().T, z["init_obst"][:, :, 0].astype(real))
     if parity:
         np.testing.assert_allclose(st["dist"].cpu().numpy(), z["init_dist"], rtol=1e-14)
         np.testing.assert_allclose(st["total_distance"].cpu().numpy(), z["init_total_distance"], rtol=1e-14)
-    alive = np.ones(n, bool)
     for t in range(T):
         a = torch.from_numpy(z["rec_actions"][t].astype(real)).cuda()
         obs, rew, done, info = env.step(a)
@@ -400,10 +408,8 @@ def test_pygame_ruleset_against_the_reference_rollout(parity):
             assert np.array_equal(st["static_y"].cpu().numpy().T, z["rec_obst"][t, :, :, 1]), t
             nd = ~done
             np.testing.assert_allclose(st["acc_reward"].cpu().numpy()[nd], z["rec_acc"][t][nd], rtol=1e-11, atol=1e-14)
-        else:
-            np.testing.assert_allclose(rew[alive], z["rec_reward"][t][alive], rtol=1e-4, atol=1e-6)
-            assert np.array_equal(done[alive], z["rec_done"][t].astype(bool)[alive]), t
-            alive &= ~z["rec_done"][t].astype(bool)
+        # north_star: 1e-5 relative (the absolute floor only covers rewards that are zero up to rounding)
+        np.testing.assert_allclose(rew, z["rec_reward"][t], rtol=1e-5, atol=1e-12)
     if parity:
         assert env.stats()["episodes"] == meta["episodes"]
     assert env.error_flags() == 0

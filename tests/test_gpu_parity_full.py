@@ -161,3 +161,39 @@ def test_unusual_obstacle_counts_against_the_c_oracle(ks, kd, w, n):
     _check_state(env, c)
     assert env.stats()["episodes"] == c.stats["episodes"] > 0 and env.error_flags() == 0
     env.close()
+
+
+@pytest.mark.parametrize("parity", [False, True])
+def test_duplicate_obstacle_goals_against_the_c_oracle(parity):
+    """Repeated obstacle goals (4 goals, two of them the same point; change step 5): the kernels' generic goal-change
+    branch - candidates are the goals whose position differs from the current one (ballenv_env.py:351-352) - at 2048
+    environments x 150 steps against oracle/ballenv_oracle.c, every observation / done / flag, then the state (goal
+    indices through their canonical position: the reference only holds positions)."""
+    from gym_ballenv_b200 import BallVecEnv
+    from helpers import canonical_goal_index
+    from oracle.c_oracle import COracleVec
+    from oracle.gen_golden import CFG_DUPGOALS
+    n, T, seed = 2048, 150, 77
+    canon = canonical_goal_index(CFG_DUPGOALS)
+    env = BallVecEnv(n, window=5, config=_env_config(CFG_DUPGOALS), seed=seed, max_episode_steps=37, parity=parity)
+    assert env.kernel_variant(1) == "generic"        # repeated goals are outside the production specialisations
+    c = COracleVec(oracle_config(CFG_DUPGOALS, 5, 37), seed, n)
+    obs = env.reset()
+    c.reset()
+    assert np.array_equal(obs.cpu().numpy(), c.observe())
+    g = torch.Generator().manual_seed(4)
+    for t in range(T):
+        a = torch.randint(0, 9, (n,), generator=g)
+        obs, rew, done, info = env.step(a.cuda())
+        r, d, f = c.step(a.numpy())
+        assert np.array_equal(obs.cpu().numpy(), c.observe()), t
+        assert np.array_equal(done.cpu().numpy(), d), t
+        assert np.array_equal(info["flags"].cpu().numpy(), f), t
+        np.testing.assert_allclose(rew.cpu().numpy(), r, rtol=1e-5, atol=0)
+    st, ref = env.get_state(), c.state()
+    assert np.array_equal(st["dynamic_x"].cpu().numpy().T.astype(np.float64), ref["obstacles"][:, 2:, 0])
+    assert np.array_equal(st["dynamic_y"].cpu().numpy().T.astype(np.float64), ref["obstacles"][:, 2:, 1])
+    assert np.array_equal(canon[st["dynamic_goal"].cpu().numpy().T], canon[ref["dyn_goal"]])
+    assert np.array_equal(st["dynamic_counter"].cpu().numpy().T, ref["dyn_counter"])
+    assert env.stats()["episodes"] > n and env.error_flags() == 0
+    env.close()
