@@ -54,7 +54,13 @@ def rollout(env: BallVecEnv, policy: Policy, n_steps: int, obs: Optional[torch.T
         obs = env.observe()
     log_probs, values, rewards, dones, actions = [], [], [], [], []
     for _ in range(n_steps):
-        probs, value = policy(obs.float())
+        # The observation is a view of an env-owned double buffer that the kernel rewrites two steps later behind
+        # autograd's back (a raw launch does not bump the tensor's version counter): give the graph its own copy, or
+        # fc1's weight gradient would be computed from later observations.
+        x = obs.float()
+        if x.data_ptr() == obs.data_ptr():
+            x = x.clone()
+        probs, value = policy(x)
         if greedy:
             action = probs.argmax(dim=-1)
         else:
@@ -160,9 +166,26 @@ def discounted_returns(reward: torch.Tensor, done: torch.Tensor, gamma: float, b
     return out
 
 
+def finish_episode_loss(log_prob: torch.Tensor, value: torch.Tensor, rewards: torch.Tensor, gamma: float = 0.99):
+    """The loss of the reference's ``finish_episode`` (examples/ball_cnn_ac3.py:222-246) for ONE finished episode:
+    discounted returns from the end (:228-230), normalised by their mean and unbiased standard deviation + eps (:231-232),
+    sum of -log_prob * (R - V.item()) and of smooth_l1(V, R) (:233-241).  ``log_prob``, ``value``, ``rewards``: [T].
+    tests/golden/a2c_kat.npz holds what the reference's own function computes (loss and gradients).  ``a2c_loss`` below
+    is the same formula over a [T, N] batch; for N = 1, no episode end inside and no bootstrap it is this function."""
+    batch = dict(log_prob=log_prob.view(-1, 1), value=value.view(-1, 1), reward=rewards.view(-1, 1),
+                 done=torch.zeros(rewards.numel(), 1, dtype=torch.bool, device=rewards.device))
+    return a2c_loss(batch, gamma)
+
+
 def a2c_loss(batch: Dict[str, torch.Tensor], gamma: float = 0.99, bootstrap: Optional[torch.Tensor] = None):
     """Batched finish_episode (examples/ball_cnn_ac3.py:222-246): returns normalised over the batch,
-    policy loss -log_prob * (R - V.detach()), value loss smooth_l1(V, R), summed."""
+    policy loss -log_prob * (R - V.detach()), value loss smooth_l1(V, R), summed.
+
+    Intended differences from the reference, which updates once per finished episode of its single environment:
+    the batch is a fixed-length slice of N environments' trajectories, so (a) returns restart wherever an episode
+    ended inside the slice (``done``) and may be bootstrapped with V(s_T) where it did not, (b) mean / std are taken
+    over the whole [T, N] batch instead of one episode.  With N = 1, one whole episode and no bootstrap both
+    differences vanish (``finish_episode_loss``; pinned by tests/test_a2c_driver.py against the reference's function)."""
     returns = discounted_returns(batch["reward"].float(), batch["done"], gamma, bootstrap)
     returns = (returns - returns.mean()) / (returns.std() + EPS)
     advantage = returns - batch["value"].detach()

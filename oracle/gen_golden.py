@@ -68,6 +68,8 @@ def _pack_rows(obs, window):
 
 
 def _action_for(policy, src, g, t, ref):
+    if callable(policy):      # the reference's own network in the loop (greedy), fed by its own prep_state4
+        return policy(ref)
     w = src.action_word(g, t)
     if policy == "random":
         return D.mulhi(w, 9)
@@ -232,7 +234,8 @@ def rollout(cfg, n_envs, T, seed, mode, max_steps, windows=(5, 10), g0=0, polici
         out.update(tape_step_val=step_val, tape_step_n=step_n, tape_reset_val=reset_val)
     meta = dict(kind="rollout", ruleset="gym", mode=mode, seed=seed, n_envs=n_envs, T=T, g0=g0,
                 max_episode_steps=max_steps, auto_reset=True, windows=list(windows), cfg=cfg,
-                tape_attempts=A, stats=stats, action_seed=seed ^ 0x5EED, policies=list(policies),
+                tape_attempts=A, stats=stats, action_seed=seed ^ 0x5EED,
+                policies=[p if isinstance(p, str) else "checkpoint" for p in policies],
                 made_by="oracle/gen_golden.py running /root/reference unedited via oracle/ref_shim.py")
     out["meta"] = np.array(json.dumps(meta))
     return out
@@ -368,6 +371,69 @@ def pathlog_kat():
     n = 96
     return dict(states=np.asarray(X[:n], np.float64), actions=np.asarray(Y[:n], np.int64), labels=np.asarray(labels[:n], np.int64),
                 meta=json.dumps(dict(n=n, total=len(X), label_histogram=np.bincount(labels, minlength=9).tolist())))
+
+
+def a2c_kats():
+    """Known answers of the reference's actor-critic update and of its shipped WINDOW = 5 checkpoint.
+
+    * finish_episode (examples/ball_cnn_ac3.py:222-246), AST-lifted and run unedited on one recorded episode: the
+      observations, greedy actions and rewards that went in, the loss it printed and the gradients it left on every
+      parameter of ``Policy(5)`` (its optimizer stepping with lr = 0 so that they survive).
+    * the state_dict the reference ships (stored_models/ball_state3/2layer+dropout+randpos/episode_2500.pth, the
+      README's run) - 6 tensors, 21 KB: a data file of the reference, kept as a fixture so that the GPU box (which has
+      no reference tree) can load the same network.
+    """
+    import torch
+    ns = R.load_a2c(5, gamma=0.99)
+    policy = ns["policy"]
+    sd = torch.load(R.REFERENCE_CHECKPOINT_W5, map_location="cpu")
+    policy.load_state_dict(sd)
+    rng = np.random.RandomState(5)
+    T = 24
+    states = (rng.rand(T, 29) < 0.15).astype(np.float32)
+    states[:, :4] = 0
+    states[np.arange(T), rng.randint(0, 4, T)] = 1
+    rewards = (rng.randn(T) * 0.01).astype(np.float64)
+    rewards[-1] -= 1.0                                   # the episode ends on a static obstacle
+    actions = np.zeros(T, np.int64)
+    probs_rec = np.zeros((T, 9), np.float32)
+    values_rec = np.zeros(T, np.float32)
+    for t in range(T):
+        probs, value = policy(torch.from_numpy(states[t:t + 1]))          # select_action (:210-220), greedy
+        a = int(probs.argmax(-1))
+        actions[t] = a
+        probs_rec[t], values_rec[t] = probs.detach().numpy()[0], float(value)
+        policy.saved_actions.append(ns["SavedAction"](torch.log(probs[0, a]), value))
+        policy.rewards.append(float(rewards[t]))
+    ns["finish_episode"]()
+    loss = float(ns["printed"][-1][1])
+    out = {"ckpt_" + k.replace(".", "_"): v.numpy() for k, v in sd.items()}
+    out.update({"grad_" + k.replace(".", "_"): p.grad.numpy().copy() for k, p in policy.named_parameters()})
+    out.update(states=states, actions=actions, rewards=rewards, probs=probs_rec, values=values_rec,
+               loss=np.array(loss, np.float64))
+    out["meta"] = np.array(json.dumps(dict(kind="a2c_kat", gamma=0.99, T=T, window=5,
+                                           checkpoint="examples/stored_models/ball_state3/2layer+dropout+randpos/episode_2500.pth",
+                                           made_by="oracle/gen_golden.py: Policy and finish_episode AST-lifted from "
+                                                   "examples/ball_cnn_ac3.py, run unedited")))
+    return out
+
+
+def rollout_checkpoint():
+    """The shipped WINDOW = 5 checkpoint driving the reference environment in closed loop: the reference's own
+    ``Policy`` (AST-lifted) fed by its own ``prep_state4``, greedy actions, default obstacles, Philox-addressed draws
+    (so the CUDA path can replay the episodes), TimeLimit 60, auto-reset - examples/ball_cnn_ac3.py:553-613 without
+    the sampling noise."""
+    import torch
+    ns = R.load_a2c(5)
+    policy = ns["policy"]
+    policy.load_state_dict(torch.load(R.REFERENCE_CHECKPOINT_W5, map_location="cpu"))
+
+    def greedy(ref):
+        with torch.no_grad():
+            probs, _ = policy(ref.prep_state4(ref.env.state, 5).float())
+        return int(probs.argmax(-1))
+
+    return compress_rollout(rollout(CFG_DEFAULT, 12, 180, 29, "philox", 60, windows=(5,), g0=77, policies=(greedy,)))
 
 
 def compress_rollout(out):
@@ -545,6 +611,8 @@ def main(argv):
         "rollout_philox_dupgoals": lambda: compress_rollout(rollout(CFG_DUPGOALS, 16, 160, 13, "philox", 40, g0=3)),
         "rollout_philox_dense": lambda: compress_rollout(rollout(CFG_DENSE, 8, 120, 3, "philox", 1000, windows=(10,))),
         "rollout_mt_default": lambda: compress_rollout(rollout(CFG_DEFAULT, 8, 150, 0, "mt", 60)),
+        "a2c_kat": lambda: a2c_kats(),
+        "rollout_checkpoint": lambda: rollout_checkpoint(),
         "features_kat": lambda: features_kats(),
         "blocks_kat": lambda: blocks_kats(),
         "pathlog_kat": lambda: pathlog_kat(),

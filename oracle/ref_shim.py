@@ -255,6 +255,38 @@ def load_prep_state(env, names=("prep_state2", "prep_state4")):
     return tuple(ns[n] for n in names)
 
 
+def load_a2c(window, gamma=0.99):
+    """AST-lift ``Policy`` (examples/ball_cnn_ac3.py:109-146) and ``finish_episode`` (:222-246) of the reference's
+    actor-critic script (the module itself cannot be imported: argparse, gym.make, matplotlib and readchar at top level)
+    into a namespace that provides what they read as script globals.  -> namespace with ``policy`` (a fresh
+    ``Policy(window)`` on the CPU), ``finish_episode``, ``SavedAction``, ``printed`` (what finish_episode printed: the
+    loss) and an ``optimizer`` whose step changes nothing (lr = 0), so that the gradients of the call stay readable."""
+    import collections
+    import torch
+    import torch.nn as nn
+    import torch.nn.functional as F
+    path = os.path.join(REFERENCE_ROOT, "examples", "ball_cnn_ac3.py")
+    with open(path) as f:
+        tree = ast.parse(f.read(), path)
+    keep = [n for n in tree.body
+            if (isinstance(n, ast.ClassDef) and n.name == "Policy") or (isinstance(n, ast.FunctionDef) and n.name == "finish_episode")]
+    assert len(keep) == 2
+    printed = []
+    ns = {"np": _np, "torch": torch, "nn": nn, "F": F, "math": math, "device": torch.device("cpu"),
+          "eps": _np.finfo(_np.float32).eps.item(),                      # :76
+          "args": type("Args", (), {"gamma": gamma})(),
+          "SavedAction": collections.namedtuple("SavedAction", ["log_prob", "value"]),   # :78
+          "print": lambda *a, **k: printed.append(a), "printed": printed}
+    exec(compile(ast.Module(body=keep, type_ignores=[]), path, "exec"), ns)
+    ns["policy"] = ns["Policy"](window)
+    ns["optimizer"] = torch.optim.SGD(ns["policy"].parameters(), lr=0.0)
+    return ns
+
+
+REFERENCE_CHECKPOINT_W5 = os.path.join(REFERENCE_ROOT, "examples", "stored_models", "ball_state3",
+                                       "2layer+dropout+randpos", "episode_2500.pth")   # the README's WINDOW = 5 run
+
+
 def load_legacy_block_state():
     """AST-lift the legacy 29-float observation of examples/ball_env_reinforce.py:130-172 (prep_state2 + block_to_arrpos).
     The script is Python 2: with integer coordinates ``x_dist/abs(x_dist)`` is an integer there and the array index

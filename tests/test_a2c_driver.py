@@ -26,6 +26,127 @@ def test_discounted_returns_restart_at_episode_ends():
     assert torch.isfinite(a2c_loss(batch, 0.5))
 
 
+def _reference_policy():
+    """Policy(5) holding the state_dict the reference ships (episode_2500.pth of its README run), from the fixture."""
+    from gym_ballenv_b200.a2c import Policy
+    from helpers import load_golden
+    z, meta = load_golden("a2c_kat")
+    policy = Policy(5)
+    sd = {k: torch.from_numpy(z["ckpt_" + k.replace(".", "_")]) for k in policy.state_dict()}
+    policy.load_state_dict(sd)        # same parameter names and shapes as examples/ball_cnn_ac3.py:109-146
+    return policy, z, meta
+
+
+def test_finish_episode_loss_and_gradients_match_the_reference():
+    """tests/golden/a2c_kat.npz: the reference's own Policy + finish_episode (AST-lifted, run unedited by
+    oracle/gen_golden.py) on one recorded 24-step episode with the shipped checkpoint - forward pass, loss and the
+    gradient of every parameter."""
+    from gym_ballenv_b200.a2c import finish_episode_loss
+    policy, z, meta = _reference_policy()
+    x = torch.from_numpy(z["states"])
+    probs, value = policy(x)
+    np.testing.assert_allclose(probs.detach().numpy(), z["probs"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(value.detach().numpy()[:, 0], z["values"], rtol=1e-5, atol=1e-7)
+    actions = torch.from_numpy(z["actions"])
+    assert torch.equal(probs.argmax(-1), actions)                       # the recorded episode was greedy
+    logp = torch.log(probs.gather(-1, actions.view(-1, 1)).squeeze(-1))
+    loss = finish_episode_loss(logp, value.squeeze(-1), torch.from_numpy(z["rewards"]).float(), meta["gamma"])
+    assert float(loss.detach()) == pytest.approx(float(z["loss"]), rel=2e-5)
+    loss.backward()
+    for name, prm in policy.named_parameters():
+        ref = z["grad_" + name.replace(".", "_")]
+        np.testing.assert_allclose(prm.grad.numpy(), ref, rtol=2e-3, atol=2e-5 * float(np.abs(ref).max()))
+
+
+def test_shipped_checkpoint_drives_the_oracle_like_the_reference():
+    """tests/golden/rollout_checkpoint.npz: the reference environment driven in closed loop by the reference's own
+    network (shipped checkpoint, greedy) through its own prep_state4.  Here: the CPU oracle port observed through its
+    window raster, this package's Policy with the same weights - same actions at every step of every episode."""
+    from helpers import load_golden, oracle_config
+    from oracle import draws as D
+    from oracle.ballenv_oracle import OracleVec
+    policy, _, _ = _reference_policy()
+    z, meta = load_golden("rollout_checkpoint")
+    n, T = meta["n_envs"], meta["T"]
+    vec = OracleVec(oracle_config(meta["cfg"], 5, meta["max_episode_steps"]), D.PhiloxDraws(meta["seed"]), n, meta["g0"])
+    vec.reset()
+    with torch.no_grad():
+        for t in range(T):
+            obs = torch.tensor(vec.observe(), dtype=torch.float32)
+            a = policy(obs)[0].argmax(-1)
+            assert a.tolist() == list(z["rec_actions"][t]), t
+            rew, done, flags = vec.step(a.tolist())
+            assert rew == list(z["rec_reward"][t]) and [int(d) for d in done] == list(z["rec_done"][t]), t
+    assert vec.stats["episodes"] == meta["stats"]["episodes"]
+
+
+@pytest.mark.gpu
+def test_shipped_checkpoint_closed_loop_on_the_gpu():
+    """The same closed loop on the CUDA path: BallVecEnv observations -> Policy (shipped weights, on the device) ->
+    greedy action -> ballenv_step, against the reference's recorded episodes (actions, rewards, dones, quadrant bits and
+    window rows), auto-resets included."""
+    from gym_ballenv_b200 import BallVecEnv, EnvConfig
+    from helpers import load_golden
+    policy, _, _ = _reference_policy()
+    policy = policy.cuda()
+    z, meta = load_golden("rollout_checkpoint")
+    n, T = meta["n_envs"], meta["T"]
+    env = BallVecEnv(n, window=5, config=EnvConfig(), seed=meta["seed"], max_episode_steps=meta["max_episode_steps"],
+                     global_env_offset=meta["g0"])
+    obs = env.reset()
+    with torch.no_grad():
+        for t in range(T):
+            a = policy(obs.float())[0].argmax(-1)
+            assert a.cpu().tolist() == list(z["rec_actions"][t]), t
+            obs, rew, done, _ = env.step(a)
+            np.testing.assert_allclose(rew.cpu().numpy(), z["rec_reward"][t], rtol=1e-5, atol=0)
+            assert done.cpu().numpy().astype(np.uint8).tolist() == list(z["rec_done"][t]), t
+            o = obs.cpu().numpy()
+            assert np.array_equal(o[:, :4].argmax(1), z["rec_quadrant"][t]), t
+            rows = (o[:, 4:].reshape(n, 5, 5) * (1 << np.arange(5))).sum(-1).astype(np.uint32)
+            assert np.array_equal(rows, z["rec_rows5"][t]), t
+    assert env.stats()["episodes"] == meta["stats"]["episodes"] and env.error_flags() == 0
+    env.close()
+
+
+@pytest.mark.gpu
+def test_eager_rollout_gradients_do_not_alias_the_env_buffers():
+    """rollout() feeds the policy env-owned observation buffers that the kernel rewrites two steps later; the autograd
+    graph must hold its own copies.  The gradients of a rollout's loss equal those recomputed from cloned
+    (observation, action) pairs in one batched forward pass."""
+    from gym_ballenv_b200 import BallVecEnv
+    from gym_ballenv_b200.a2c import Policy, a2c_loss, rollout
+    torch.manual_seed(4)
+    n, T = 2048, 12
+    env = BallVecEnv(n, window=5, seed=6)
+    twin = BallVecEnv(n, window=5, seed=6)
+    policy = Policy(5).cuda()
+    obs = env.reset()
+    obs_t = twin.reset().clone()
+    batch = rollout(env, policy, T, obs=obs, greedy=True)
+    loss = a2c_loss(batch, 0.99)
+    policy.zero_grad()
+    loss.backward()
+    got = {k: p.grad.clone() for k, p in policy.named_parameters()}
+    # recompute: same trajectory on a twin env (greedy actions are deterministic), observations cloned per step
+    seen = []
+    with torch.no_grad():
+        for t in range(T):
+            seen.append(obs_t.clone())
+            obs_t, _, _, _ = twin.step(batch["action"][t])
+            obs_t = obs_t.clone()
+    probs, value = policy(torch.stack(seen).view(T * n, -1))
+    logp = torch.log(probs.gather(-1, batch["action"].reshape(-1, 1)).squeeze(-1)).view(T, n)
+    ref = a2c_loss(dict(log_prob=logp, value=value.view(T, n), reward=batch["reward"], done=batch["done"]), 0.99)
+    policy.zero_grad()
+    ref.backward()
+    assert float(loss.detach()) == pytest.approx(float(ref.detach()), rel=1e-5)
+    for k, p in policy.named_parameters():
+        torch.testing.assert_close(got[k], p.grad, rtol=1e-3, atol=1e-4 * float(p.grad.abs().max()))
+    env.close()
+    twin.close()
+
+
 @pytest.mark.gpu
 def test_closed_loop_16k_envs_against_the_c_oracle():
     """16384 environments, the policy in the loop (greedy actions so both sides see the same indices): every

@@ -54,7 +54,7 @@ def _check_state(env, z, prefix, idx, ks, kd, exact_dist=True):
 
 @pytest.mark.parametrize("parity", [False, True])
 @pytest.mark.parametrize("name", ["rollout_philox_default", "rollout_philox_busy", "rollout_philox_dense",
-                                  "rollout_mt_default", "rollout_philox_dupgoals"])
+                                  "rollout_mt_default", "rollout_philox_dupgoals", "rollout_checkpoint"])
 def test_golden_rollout(name, parity):
     """Rollouts recorded by running the reference itself (oracle/gen_golden.py through oracle/ref_shim.py).
     rollout_philox_dupgoals has two equal obstacle goals: the goal-change step then takes the kernels' generic

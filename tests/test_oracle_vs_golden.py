@@ -108,7 +108,7 @@ def _check_rollout(name):
 
 
 @pytest.mark.parametrize("name", ["rollout_philox_default", "rollout_philox_busy", "rollout_philox_dense",
-                                  "rollout_mt_default", "rollout_philox_dupgoals"])
+                                  "rollout_mt_default", "rollout_philox_dupgoals", "rollout_checkpoint"])
 def test_rollout(name):
     meta = _check_rollout(name)
     assert meta["stats"]["episodes"] > 0
