@@ -23,14 +23,25 @@ __all__ = ["legacy", "pathlogs", "BallVecEnv", "BallEnv", "createBoard", "TimeLi
 
 
 def _register_with_gym():
-    """If a real ``gym`` is importable, register the same id the reference registers
-    (gym_ballenv/__init__.py:4-11) pointing at this implementation."""
+    """If a real ``gym`` is importable, register the id the reference registers - ``gymball-v0``
+    (gym_ballenv/__init__.py:4-11: entry point, max_episode_steps=1000, reward_threshold=100.0) - pointing at this
+    implementation, so that a script calling ``gym.make('gymball-v0')`` is served unchanged.  Skipped when the reference
+    package has registered the id already, or when BALLENV_NO_GYM_REGISTER=1.  (Without gym, ``gym_ballenv_b200.make``
+    takes the same id.)"""
+    import os
+    if os.environ.get("BALLENV_NO_GYM_REGISTER", "0") == "1":
+        return False
     try:
+        import gym
         from gym.envs.registration import register
-        register(id='gymball-b200-v0', entry_point='gym_ballenv_b200.env:BallEnv', max_episode_steps=1000,
+    except ImportError:
+        return False
+    try:
+        register(id='gymball-v0', entry_point='gym_ballenv_b200.env:BallEnv', max_episode_steps=1000,
                  reward_threshold=100.0, nondeterministic=False)
-    except Exception:
-        pass
+    except gym.error.Error:      # the id is taken (the reference package was imported first): leave it alone
+        return False
+    return True
 
 
 _register_with_gym()

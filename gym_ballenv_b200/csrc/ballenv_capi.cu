@@ -11,6 +11,7 @@
 #include "ballenv_kernels.cuh"
 #include "ballenv_features.cuh"
 #include "ballenv_lean.cuh"
+#include "ballenv_reset_fixed.cuh"
 
 using namespace ballenv;
 
@@ -624,6 +625,19 @@ int ballenv_reset(BallenvHandle* h, const uint8_t* mask, void* obs_out, ballenv_
   p.obs = obs_out;
   p.reset_tape = h->reset_tape;
   return launch(h, p, (cudaStream_t)stream);
+}
+
+int ballenv_reset_fixed(BallenvHandle* h, const uint8_t* mask, double goal_x, double goal_y, void* obs_out,
+                        ballenv_stream_t stream) {
+  if (h == nullptr) return fail(BALLENV_EINVAL, "handle is NULL");
+  if (h->cfg.ruleset != BALLENV_RULESET_PYGAME)
+    return fail(BALLENV_EINVAL, "resetFixedstate belongs to the pygame ruleset (ballenv_pygame.py:589-624)");
+  DeviceGuard guard(h->device);
+  const unsigned grid = (unsigned)((h->n + 127) / 128);
+  ballenv_reset_fixed_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(h->base, mask, goal_x, goal_y);
+  h->launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  return obs_out != nullptr ? ballenv_observe(h, obs_out, stream) : BALLENV_OK;
 }
 
 int ballenv_observe(BallenvHandle* h, void* obs_out, ballenv_stream_t stream) {

@@ -132,19 +132,22 @@ class BallEnv(object):
 
     def _pull_state(self):
         v = self._vec
-        hv = v._views_of(v._arena.cpu())          # one small device->host copy of the whole SoA arena (N = 1)
-        ax, ay = hv["agent_x"][0].item(), hv["agent_y"][0].item()
-        gx, gy = hv["goal_x"][0].item(), hv["goal_y"][0].item()
-        dist = float(hv["dist"][0].item())
-        self.total_distance = float(hv["total_distance"][0].item())
-        self.total_reward_accumulated = float(hv["acc_reward"][0].item())
+        sv = v.state_views      # fp64 (parity mode): the one environment's slice, gathered on the device, one small copy
         ks, kd = self._cfg.static_obstacles, self._cfg.dynamic_obstacles
+        flat = torch.cat([sv[k][0:1] for k in ("agent_x", "agent_y", "goal_x", "goal_y", "dist", "total_distance",
+                                               "acc_reward")] +
+                         [sv[k][:, 0] for k in ("static_x", "static_y", "dynamic_x", "dynamic_y")]).cpu().tolist()
+        ax, ay, gx, gy, dist = flat[0], flat[1], flat[2], flat[3], float(flat[4])
+        self.total_distance = float(flat[5])
+        self.total_reward_accumulated = float(flat[6])
         state = [(_num(ax), _num(ay)), (_num(gx), _num(gy)), dist]
+        o = 7
         if ks:
-            sx, sy = hv["static_x"][:, 0].tolist(), hv["static_y"][:, 0].tolist()
+            sx, sy = flat[o:o + ks], flat[o + ks:o + 2 * ks]
             state += [(_num(x), _num(y)) for x, y in zip(sx, sy)]
+        o += 2 * ks
         if kd:
-            dx, dy = hv["dynamic_x"][:, 0].tolist(), hv["dynamic_y"][:, 0].tolist()
+            dx, dy = flat[o:o + kd], flat[o + kd:o + 2 * kd]
             state += [(float(x), float(y)) for x, y in zip(dx, dy)]
         self.goal_x, self.goal_y = state[1]
         self.old_dist = dist
@@ -295,16 +298,18 @@ class createBoard(object):
 
     def _pull(self):
         v = self._vec
-        hv = v._views_of(v._arena.cpu())
-        agent = (hv["agent_x"][0].item(), hv["agent_y"][0].item())
-        goal = (hv["goal_x"][0].item(), hv["goal_y"][0].item())
+        sv = v.state_views      # fp64: the one environment's slice, gathered on the device, one small copy
+        ks = self.no_static_obstacles
+        flat = torch.cat([sv[k][0:1] for k in ("agent_x", "agent_y", "goal_x", "goal_y", "dist", "total_distance",
+                                               "acc_reward")] + [sv["static_x"][:, 0], sv["static_y"][:, 0]]).cpu().tolist()
+        agent, goal = (flat[0], flat[1]), (flat[2], flat[3])
         self.agent_x, self.agent_y = agent
         self.goal_x, self.goal_y = goal
-        self.total_distance = hv["total_distance"][0].item()
-        self.total_reward_accumulated = hv["acc_reward"][0].item()
-        state = [agent, goal, hv["dist"][0].item()]
+        self.total_distance = flat[5]
+        self.total_reward_accumulated = flat[6]
+        state = [agent, goal, flat[4]]
         # obstacle tuples carry the Obstacle.rad default 20 (ballenv_pygame.py:33-36, 496)
-        state += [(int(x), int(y), 20) for x, y in zip(hv["static_x"][:, 0].tolist(), hv["static_y"][:, 0].tolist())]
+        state += [(int(x), int(y), 20) for x, y in zip(flat[7:7 + ks], flat[7 + ks:7 + 2 * ks])]
         self.state = state
         self.sensor_readings = v.sensor_readings()
         out = np.empty(len(state), dtype=object)
@@ -315,6 +320,16 @@ class createBoard(object):
     def reset(self):
         """ballenv_pygame.py:460-513."""
         self._vec.reset()
+        out = self._pull()
+        self.old_dist = self.state[2]
+        return out
+
+    def resetFixedstate(self):
+        """ballenv_pygame.py:589-624: goal at (145, 120), the obstacles of the last reset() kept, the agent redrawn until
+        it is clear of them."""
+        if self.state is None:
+            raise RuntimeError("call reset() before resetFixedstate() (it keeps the obstacles of the last reset)")
+        self._vec.reset_fixed((145, 120))
         out = self._pull()
         self.old_dist = self.state[2]
         return out

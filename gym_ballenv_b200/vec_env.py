@@ -151,6 +151,19 @@ class BallVecEnv:
         check(LIB.ballenv_reset(self._h, mptr, C.c_void_p(buf["obs"].data_ptr()), self._stream()))
         return buf["obs"]
 
+    def reset_fixed(self, goal=(145.0, 120.0), mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """createBoard.resetFixedstate (ballenv_pygame.py:589-624; pygame ruleset): new episodes with the goal at
+        ``goal`` and the obstacles kept -> observation [N, 4 + W*W]."""
+        buf = self._next_buf()
+        mptr = None
+        if mask is not None:
+            mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+            assert mask.shape == (self.num_envs,)
+            mptr = C.c_void_p(mask.data_ptr())
+        check(LIB.ballenv_reset_fixed(self._h, mptr, float(goal[0]), float(goal[1]), C.c_void_p(buf["obs"].data_ptr()),
+                                      self._stream()))
+        return buf["obs"]
+
     def observe(self) -> torch.Tensor:
         """prep_state4 of the current state, without stepping."""
         buf = self._next_buf()

@@ -173,6 +173,15 @@ int ballenv_state_ptrs(BallenvHandle *h, BallenvStatePtrs *out);
 int ballenv_reset(BallenvHandle *h, const uint8_t *mask, void *obs_out, ballenv_stream_t stream);
 
 /*
+ * Replaces: createBoard.resetFixedstate() (ballenv_pygame.py:589-624; pygame ruleset only): a new episode with the
+ * goal at a fixed point ((145, 120) in the reference) and the OBSTACLES KEPT - the agent is redrawn until it is at least
+ * 50 from the goal and touches no obstacle; state[2] is the distance of the accepted attempt's first draw; the
+ * accumulated reward restarts at 0.  mask / obs_out as for ballenv_reset.
+ */
+int ballenv_reset_fixed(BallenvHandle *h, const uint8_t *mask, double goal_x, double goal_y, void *obs_out,
+                        ballenv_stream_t stream);
+
+/*
  * Replaces: BallEnv.step(action) (ballenv_env.py:232-289) incl. move_obstacles (:323-353) and
  * calculate_reward (:200-229) / createBoard.step (ballenv_pygame.py:650-706), the TimeLimit wrapper,
  * and the prep_state4 call of the training loop (examples/ball_cnn_ac3.py:560) - one fused launch.

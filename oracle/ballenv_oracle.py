@@ -161,6 +161,34 @@ class OracleEnv:
             self._reset_pygame()
         return self.state()
 
+    def reset_fixed(self, goal=(145, 120)):
+        """createBoard.resetFixedstate (ballenv_pygame.py:589-624): goal fixed, obstacles kept, the agent redrawn until it
+        is >= 50 from the goal (:607-612) and touches no obstacle (:613-616, calc_reward :680-688)."""
+        assert self.cfg.ruleset != RULESET_GYM
+        src, g = self.src, self.g
+        self.episode += 1
+        self.ep_len = 0
+        ep = self.episode
+        outer = 0
+        while True:
+            w = src.reset_words(g, ep, D.RK_FIXED_AGENT, item=outer, attempt=0, count=4)
+            agent = (0 + D.ranf_from_words(w[0], w[1]) * (100 - 0),        # :601-602, 454-457
+                     0 + D.ranf_from_words(w[2], w[3]) * (100 - 0))
+            dist = _dist(goal, agent)                                      # :605 (kept even if redrawn)
+            inner = 1
+            while _dist(goal, agent) < 50:                                 # :607-612
+                w = src.reset_words(g, ep, D.RK_FIXED_AGENT, item=outer, attempt=inner, count=4)
+                agent = (0 + D.ranf_from_words(w[0], w[1]) * (100 - 0),
+                         0 + D.ranf_from_words(w[2], w[3]) * (100 - 0))
+                inner += 1
+            if not any(not (_dist(agent, o) > self.radius_sum) for o in self.obst):   # :613-616 -> check_overlap :381-387
+                break
+            outer += 1
+        self.agent, self.goal, self.dist = agent, tuple(goal), dist
+        self.acc = 0.0                                                     # :621
+        self.total_distance = _dist(agent, goal)                           # :622
+        return self.state()
+
     def _reset_gym(self):
         cfg, src, g, ep = self.cfg, self.src, self.g, self.episode
         w = src.reset_words(g, ep, D.RK_HEAD, count=4)
@@ -349,6 +377,10 @@ class OracleVec:
     def reset(self):
         for e in self.envs:
             e.reset()
+
+    def reset_fixed(self, goal=(145, 120)):
+        for e in self.envs:
+            e.reset_fixed(goal)
 
     def step(self, actions):
         """actions: per env an index into AGENT_MOVES or a (dx, dy) pair.

@@ -43,6 +43,7 @@ RK_HEAD = 0      # block 0: goal_x, goal_y, agent_x, agent_y   (gym ruleset)
 RK_STATIC = 1    # | i << 16 | attempt >> 1 ; words (attempt & 1) * 2 + {0, 1}
 RK_DYNAMIC = 2   # | j >> 1                 ; words (j & 1) * 2 + {0, 1}
 RK_AGENT_REDRAW = 3   # | attempt            ; words 0..3 (two ranf)
+RK_FIXED_AGENT = 4    # resetFixedstate (pygame): | outer << 12 | inner ; words 0..3 (two ranf); inner 0 = first draw
 
 
 def philox4x32_10(c0, c1, c2, c3, k0, k1):
@@ -124,6 +125,8 @@ def reset_block(kind, item=0, attempt=0):
         return (RK_DYNAMIC << 28) | (item >> 1), (item & 1) * 2
     if kind == RK_AGENT_REDRAW:
         return (RK_AGENT_REDRAW << 28) | attempt, 0
+    if kind == RK_FIXED_AGENT:
+        return (RK_FIXED_AGENT << 28) | (item << 12) | attempt, 0
     raise ValueError(kind)
 
 

@@ -292,6 +292,57 @@ def rollout_pygame(n_static, n_envs, T, seed, g0=0):
     return out
 
 
+def reset_fixed_kat(n_static=9, n_envs=48, seed=33, g0=9, rounds=3, steps=6):
+    """createBoard.resetFixedstate (ballenv_pygame.py:589-624) on the running reference: reset(), a few raw-action steps,
+    then per round resetFixedstate() and a few more steps.  Recorded after every resetFixedstate: agent, goal, state[2],
+    total_distance, accumulated reward, the (kept) obstacles, the number of agent draws it took; and the rewards / dones
+    of the steps that follow (they depend on old_dist and total_distance)."""
+    src = D.PhiloxDraws(seed)
+    act_src = D.PhiloxDraws(seed ^ 0x5EED)
+    refs = [R.ReferencePygameEnv(n_static, R.PygameRouter(src, g0 + i)) for i in range(n_envs)]
+    rec = dict(agent=np.zeros((rounds, n_envs, 2)), goal=np.zeros((rounds, n_envs, 2)), dist=np.zeros((rounds, n_envs)),
+               total_distance=np.zeros((rounds, n_envs)), acc=np.zeros((rounds, n_envs)),
+               obst=np.zeros((rounds, n_envs, n_static, 2)), draws=np.zeros((rounds, n_envs), np.int32),
+               actions=np.zeros((rounds, steps, n_envs, 2)), reward=np.zeros((rounds, steps, n_envs)),
+               done=np.zeros((rounds, steps, n_envs), np.uint8))
+    pre_actions = np.zeros((steps, n_envs, 2))
+    t = 0
+    for i, ref in enumerate(refs):
+        ref.reset()
+    for k in range(steps):                       # episodes under way, accumulated reward non-zero, before the first call
+        for i, ref in enumerate(refs):
+            a = pygame_action(act_src, g0 + i, t)
+            pre_actions[k, i] = a
+            _, _, done, _ = ref.step(a)
+            assert not done or True
+        t += 1
+    for r in range(rounds):
+        for i, ref in enumerate(refs):
+            n0 = len(ref.router.trace)
+            ref.reset_fixed()
+            st = ref.env.state
+            rec["agent"][r, i], rec["goal"][r, i], rec["dist"][r, i] = st[0], st[1], st[2]
+            rec["total_distance"][r, i] = ref.env.total_distance
+            rec["acc"][r, i] = ref.env.total_reward_accumulated
+            rec["draws"][r, i] = (len(ref.router.trace) - n0) // 2
+            for j in range(n_static):
+                rec["obst"][r, i, j] = st[3 + j][:2]
+        for k in range(steps):
+            for i, ref in enumerate(refs):
+                a = pygame_action(act_src, g0 + i, t)
+                rec["actions"][r, k, i] = a
+                _, reward, done, _ = ref.step(a)
+                rec["reward"][r, k, i], rec["done"][r, k, i] = reward, done
+            t += 1
+    out = {"rec_" + k: v for k, v in rec.items()}
+    out["pre_actions"] = pre_actions
+    out["meta"] = np.array(json.dumps(dict(kind="reset_fixed_kat", ruleset="pygame", n_static=n_static, n_envs=n_envs,
+                                           seed=seed, g0=g0, rounds=rounds, steps=steps, goal=[145, 120],
+                                           made_by="oracle/gen_golden.py running createBoard.resetFixedstate of "
+                                                   "/root/reference/ballenv_pygame.py unedited via oracle/ref_shim.py")))
+    return out
+
+
 def features_kats():
     """States -> the 20 floats of the reference's featureExtractor helpers (numpy part, featureExtractor.py:36-257)."""
     rng = np.random.RandomState(12)
@@ -617,6 +668,7 @@ def main(argv):
         "blocks_kat": lambda: blocks_kats(),
         "pathlog_kat": lambda: pathlog_kat(),
         "rollout_pygame": lambda: rollout_pygame(9, 12, 200, 21, g0=40),
+        "reset_fixed_kat": lambda: reset_fixed_kat(),
     }
     only = set(argv[1:])
     for name, fn in jobs.items():

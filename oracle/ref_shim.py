@@ -403,7 +403,38 @@ class PygameRouter(object):
         self._last_len = -1
         self._attempt = 0
 
+    def begin_reset_fixed(self, goal=(145, 120)):
+        """resetFixedstate (ballenv_pygame.py:589-624) draws nothing but agent positions, two ranf each: the first of an
+        outer attempt, then a redraw while the agent is closer than 50 to the (fixed) goal.  Which of the two the next
+        pair is follows from the pair just handed out, so the router can address it as (outer, inner)."""
+        self.context = "reset_fixed"
+        self.episode += 1
+        self._fixed_goal = goal
+        self._outer, self._inner = -1, 0
+        self._half = None          # words of the current pair while its second ranf is pending
+        self._last = None          # the agent position handed out last
+
+    def _ranf_fixed(self):
+        if self._half is None:
+            if self._last is not None and math.sqrt(math.pow(self._fixed_goal[0] - self._last[0], 2) +
+                                                    math.pow(self._fixed_goal[1] - self._last[1], 2)) < 50:
+                self._inner += 1
+            else:
+                self._outer, self._inner = self._outer + 1, 0
+            self._half = self.src.reset_words(self.g, self.episode, D.RK_FIXED_AGENT, item=self._outer,
+                                              attempt=self._inner, count=4)
+            v = D.ranf_from_words(self._half[0], self._half[1])
+            self._x = 0 + v * (100 - 0)
+        else:
+            v = D.ranf_from_words(self._half[2], self._half[3])
+            self._last = (self._x, 0 + v * (100 - 0))
+            self._half = None
+        self.trace.append((self.context, 0.0, 1.0, v))
+        return v
+
     def ranf(self):
+        if self.context == "reset_fixed":
+            return self._ranf_fixed()
         assert self.context == "reset"
         k = self._nf
         self._nf += 1
@@ -483,6 +514,11 @@ class ReferencePygameEnv(object):
         self.env.static_obstacle_list = []
         self.router.begin_reset()
         return self.env.reset()
+
+    def reset_fixed(self):
+        self.pg.np = _NumpyProxy(self.router)
+        self.router.begin_reset_fixed()
+        return self.env.resetFixedstate()
 
     def step(self, action):
         self.pg.np = _NumpyProxy(self.router)

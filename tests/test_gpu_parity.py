@@ -417,6 +417,74 @@ def test_pygame_ruleset_against_the_reference_rollout(parity):
 
 
 @pytest.mark.gpu
+def test_reset_fixed_against_the_reference_and_the_oracle():
+    """ballenv_reset_fixed == createBoard.resetFixedstate (ballenv_pygame.py:589-624): the reference-recorded fixture
+    (goal (145, 120): agent, state[2], total_distance, zeroed accumulated reward, obstacles kept, the rewards of the
+    steps that follow), then a goal in the middle of the world, where the inner redraw-while-closer-than-50 loop fires
+    for most environments, against the oracle's restatement; the facade method on top."""
+    from gym_ballenv_b200 import BallVecEnv, EnvConfig, createBoard
+    from oracle import draws as D
+    from oracle.ballenv_oracle import RULESET_PYGAME, OracleConfig, OracleVec
+    z, meta = load_golden("reset_fixed_kat")
+    n, g0, ks = meta["n_envs"], meta["g0"], meta["n_static"]
+    env = BallVecEnv(n, window=5, config=EnvConfig.pygame_default(static_obstacles=ks), ruleset="pygame", seed=meta["seed"],
+                     global_env_offset=g0, auto_reset=False, max_episode_steps=0)
+    env.reset()
+    for k in range(meta["steps"]):
+        env.step(torch.from_numpy(z["pre_actions"][k]).cuda())
+    for r in range(meta["rounds"]):
+        obs = env.reset_fixed(tuple(meta["goal"]))
+        st = env.get_state()
+        assert np.array_equal(st["agent_x"].cpu().numpy(), z["rec_agent"][r, :, 0])
+        assert np.array_equal(st["agent_y"].cpu().numpy(), z["rec_agent"][r, :, 1])
+        assert np.array_equal(st["goal_x"].cpu().numpy(), z["rec_goal"][r, :, 0])
+        np.testing.assert_allclose(st["dist"].cpu().numpy(), z["rec_dist"][r], rtol=1e-14)
+        np.testing.assert_allclose(st["total_distance"].cpu().numpy(), z["rec_total_distance"][r], rtol=1e-14)
+        assert np.array_equal(st["acc_reward"].cpu().numpy(), z["rec_acc"][r]) and int(st["ep_len"].max()) == 0
+        assert np.array_equal(st["static_x"].cpu().numpy().T, z["rec_obst"][r, :, :, 0])
+        assert torch.equal(obs, env.observe()) and torch.all(obs[:, :4].sum(1) == 1)
+        for k in range(meta["steps"]):
+            _, rew, done, _ = env.step(torch.from_numpy(z["rec_actions"][r, k]).cuda())
+            np.testing.assert_allclose(rew.cpu().numpy(), z["rec_reward"][r, k], rtol=1e-10, atol=1e-15)
+            assert np.array_equal(done.cpu().numpy(), z["rec_done"][r, k].astype(bool)), (r, k)
+    # a goal inside the world: most first draws are closer than 50 -> the inner loop; masked: only the even environments
+    cfg = OracleConfig(ruleset=RULESET_PYGAME, window=5, n_static=ks, n_dynamic=0, speeds=(), goals=(), max_episode_steps=0,
+                       auto_reset=False)
+    vec = OracleVec(cfg, D.PhiloxDraws(5), n, 0)
+    env2 = BallVecEnv(n, window=5, config=EnvConfig.pygame_default(static_obstacles=ks), ruleset="pygame", seed=5,
+                      auto_reset=False, max_episode_steps=0)
+    env2.reset()
+    vec.reset()
+    before = env2.get_state()
+    mask = torch.arange(n) % 2 == 0
+    env2.reset_fixed((60.0, 40.0), mask=mask)
+    st = env2.get_state()
+    redrawn = 0
+    for i, e in enumerate(vec.envs):
+        if i % 2 == 0:
+            e.reset_fixed((60.0, 40.0))
+            assert (st["agent_x"][i].item(), st["agent_y"][i].item()) == tuple(e.agent), i
+            assert st["dist"][i].item() == pytest.approx(e.dist, rel=1e-14)
+            assert st["total_distance"][i].item() == pytest.approx(e.total_distance, rel=1e-14)
+            assert st["episode"][i].item() == e.episode == 1
+            redrawn += e.dist != e.total_distance
+        else:
+            assert st["agent_x"][i].item() == before["agent_x"][i].item() and st["episode"][i].item() == 0
+    assert redrawn > n // 8
+    assert env.error_flags() == 0 and env2.error_flags() == 0
+    env.close()
+    env2.close()
+    board = createBoard(static_obstacles=ks, seed=meta["seed"] + 1)
+    with pytest.raises(RuntimeError):
+        board.resetFixedstate()
+    board.reset()
+    s = board.resetFixedstate()
+    assert s[1] == (145, 120) and board.total_reward_accumulated == 0 and len(s) == 3 + ks
+    assert board.total_distance == pytest.approx(board.calculate_distance(s[0], s[1]), rel=1e-14)
+    board.close()
+
+
+@pytest.mark.gpu
 def test_rollout_buffer_with_unaligned_steps():
     """[T][n][row] rollout rows of step t start at t * n * row elements: with n = 777 and W = 5 (row = 29) that is
     not a multiple of 4 elements, so the 128-bit store path must fall back to element stores for those steps."""

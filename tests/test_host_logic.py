@@ -135,3 +135,37 @@ def test_legacy_block_policy_supervised_fit_and_reference_checkpoint():
         xs, ys = P.load_path_log("/root/reference/examples/State_info_trail_no2", "/root/reference/examples/Trial_no_2")
         acc = (ref(xs).argmax(-1) == ys).float().mean().item()
         assert acc > 0.3, acc          # nine classes; the net was trained on logs like this one
+
+
+def test_registers_the_reference_id_when_gym_is_present(monkeypatch):
+    """gym_ballenv/__init__.py:4-11 registers 'gymball-v0'; with a gym importable this package registers the same id
+    (entry point BallEnv, TimeLimit 1000) unless the id is taken or BALLENV_NO_GYM_REGISTER=1."""
+    import types
+    import gym_ballenv_b200 as pkg
+    calls = []
+
+    class GymError(Exception):
+        pass
+
+    gym = types.ModuleType("gym")
+    gym.error = types.SimpleNamespace(Error=GymError)
+    envs = types.ModuleType("gym.envs")
+    reg = types.ModuleType("gym.envs.registration")
+
+    def register(**kw):
+        if any(c["id"] == kw["id"] for c in calls):
+            raise GymError("Cannot re-register id")
+        calls.append(kw)
+
+    reg.register = register
+    gym.envs, envs.registration = envs, reg
+    monkeypatch.setitem(sys.modules, "gym", gym)
+    monkeypatch.setitem(sys.modules, "gym.envs", envs)
+    monkeypatch.setitem(sys.modules, "gym.envs.registration", reg)
+    assert pkg._register_with_gym() is True
+    assert calls == [dict(id='gymball-v0', entry_point='gym_ballenv_b200.env:BallEnv', max_episode_steps=1000,
+                          reward_threshold=100.0, nondeterministic=False)]
+    assert pkg._register_with_gym() is False        # taken: left alone, no exception
+    monkeypatch.setenv("BALLENV_NO_GYM_REGISTER", "1")
+    calls.clear()
+    assert pkg._register_with_gym() is False and calls == []

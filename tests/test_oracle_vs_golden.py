@@ -142,6 +142,34 @@ def test_rollout_pygame_ruleset():
     assert vec.stats["episodes"] == meta["episodes"] > 0
 
 
+def test_reset_fixed_against_the_reference():
+    """createBoard.resetFixedstate (ballenv_pygame.py:589-624) run on the reference through the shim
+    (tests/golden/reset_fixed_kat.npz): goal (145, 120), obstacles kept, the agent redrawn until it is clear of them
+    (up to 10 draws in the fixture); the oracle's restatement reproduces agent, state[2], total_distance, the zeroed
+    accumulated reward and the rewards of the steps that follow, exactly."""
+    from oracle.ballenv_oracle import RULESET_PYGAME, OracleConfig
+    z, meta = load_golden("reset_fixed_kat")
+    n, g0 = meta["n_envs"], meta["g0"]
+    cfg = OracleConfig(ruleset=RULESET_PYGAME, window=5, n_static=meta["n_static"], n_dynamic=0, speeds=(), goals=(),
+                       max_episode_steps=0, auto_reset=False)
+    vec = OracleVec(cfg, D.PhiloxDraws(meta["seed"]), n, g0)
+    vec.reset()
+    for k in range(meta["steps"]):
+        vec.step([tuple(a) for a in z["pre_actions"][k]])
+    assert z["rec_draws"].max() >= 5            # the redraw-while-touching loop is exercised
+    for r in range(meta["rounds"]):
+        vec.reset_fixed(tuple(meta["goal"]))
+        for i, e in enumerate(vec.envs):
+            assert tuple(e.agent) == tuple(z["rec_agent"][r, i]) and tuple(e.goal) == tuple(z["rec_goal"][r, i]), (r, i)
+            assert e.dist == z["rec_dist"][r, i] and e.total_distance == z["rec_total_distance"][r, i]
+            assert e.acc == z["rec_acc"][r, i] == 0.0
+            assert np.array_equal(np.array(e.obst, dtype=np.float64), z["rec_obst"][r, i])
+        for k in range(meta["steps"]):
+            rew, done, _ = vec.step([tuple(a) for a in z["rec_actions"][r, k]])
+            assert [float(x) for x in rew] == list(z["rec_reward"][r, k]), (r, k)
+            assert [int(d) for d in done] == list(z["rec_done"][r, k]), (r, k)
+
+
 def test_features20_against_the_reference_helpers():
     """featureExtractor.py's numpy helpers (run through the shim) vs the oracle's restatement, 160 states."""
     from oracle.ballenv_oracle import features20
