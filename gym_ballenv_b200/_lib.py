@@ -57,7 +57,7 @@ EXPORTS = (
     "ballenv_create", "ballenv_destroy", "ballenv_state_ptrs", "ballenv_reset", "ballenv_step",
     "ballenv_step_many", "ballenv_observe", "ballenv_observe_features", "ballenv_observe_blocks", "ballenv_step_host", "ballenv_set_draw_tape", "ballenv_stats",
     "ballenv_stats_reset", "ballenv_error_flags", "ballenv_launch_count", "ballenv_selftest", "ballenv_kernel_variant",
-    "ballenv_step_many_host", "ballenv_reset_fixed",
+    "ballenv_step_many_host", "ballenv_reset_fixed", "ballenv_state_written",
 )
 
 
@@ -72,6 +72,7 @@ def _bind(lib):
     lib.ballenv_create.argtypes = [cfgp, i64, i64, C.c_int, u64, vp, C.POINTER(vp)]
     lib.ballenv_destroy.argtypes = [vp]
     lib.ballenv_state_ptrs.argtypes = [vp, C.POINTER(BallenvStatePtrs)]
+    lib.ballenv_state_written.argtypes = [vp, vp]
     lib.ballenv_reset.argtypes = [vp, vp, vp, vp]
     lib.ballenv_reset_fixed.argtypes = [vp, vp, C.c_double, C.c_double, vp, vp]
     lib.ballenv_step.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp]

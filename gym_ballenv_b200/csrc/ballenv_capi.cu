@@ -37,6 +37,26 @@ BALLENV_LEAN_DECL(5, 8, 24)
 #undef BALLENV_LEAN_DECL
 }  // namespace ballenv
 
+// ballenv_state_written: is every coordinate of the (fp32) state integral and inside the ranges the lean kernels'
+// exact shortcuts assume (ballenv_lean.cuh: small_integral for obstacles, small_int for agent and goal)?
+__global__ void __launch_bounds__(128) validate_state_kernel(const __grid_constant__ ballenv::Params p, uint32_t* dirty) {
+  using namespace ballenv;
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= p.n) return;
+  const float* ax = reinterpret_cast<const float*>(p.agent_x);
+  const float* ay = reinterpret_cast<const float*>(p.agent_y);
+  const float* gx = reinterpret_cast<const float*>(p.goal_x);
+  const float* gy = reinterpret_cast<const float*>(p.goal_y);
+  bool ok = small_int(ax[e]) && small_int(ay[e]) && small_int(gx[e]) && small_int(gy[e]);
+  const float* sx = reinterpret_cast<const float*>(p.stat_x) + e * p.stat_stride;
+  const float* sy = reinterpret_cast<const float*>(p.stat_y) + e * p.stat_stride;
+  for (int k = 0; k < p.cfg.ks; ++k) ok = ok && lean::small_integral(sx[k]) && lean::small_integral(sy[k]);
+  const float* dx = reinterpret_cast<const float*>(p.dyn_x) + e * p.dyn_stride;
+  const float* dy = reinterpret_cast<const float*>(p.dyn_y) + e * p.dyn_stride;
+  for (int k = 0; k < p.cfg.kd; ++k) ok = ok && lean::small_integral(dx[k]) && lean::small_integral(dy[k]);
+  if (!ok) atomicOr(dirty, 1u);
+}
+
 __global__ void selftest_sqrt_kernel(long long n, unsigned long long* bad) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -231,10 +251,11 @@ struct BallenvHandle {
 namespace {
 
 // production specialisation (see ballenv_kernel<.., kFast>): everything the generic kernel tests per launch
-bool fast_eligible(const BallenvHandle* h, const Params& p) {
+// any_rows: the observation rows may have any format (the lean kernels); otherwise float32 rows (block of roles)
+bool fast_eligible(const BallenvHandle* h, const Params& p, bool any_rows = false) {
   return h->cfg.precision == BALLENV_F32 && p.mode == kModeStep && p.cfg.ruleset == BALLENV_RULESET_GYM &&
          p.step_tape == nullptr && p.reset_tape == nullptr && (p.cfg.goals_distinct || p.cfg.kd == 0) &&
-         p.obs != nullptr && p.cfg.obs_format == BALLENV_OBS_F32 &&
+         p.obs != nullptr && (any_rows || p.cfg.obs_format == BALLENV_OBS_F32) &&
          (p.action_kind == BALLENV_ACT_INDEX_I64 || p.action_kind == BALLENV_ACT_INDEX_I32 ||
           p.action_kind == BALLENV_ACT_INDEX_U8) &&
          !h->force_generic;
@@ -244,7 +265,7 @@ bool fast_eligible(const BallenvHandle* h, const Params& p) {
 // obstacle counts, integral geometry and a change step that fits a byte
 typedef void (*LeanLauncher)(const Params&, unsigned, cudaStream_t);
 LeanLauncher lean_launcher(const BallenvHandle* h, const Params& p, int* lanes = nullptr) {
-  if (!fast_eligible(h, p) || h->no_lean || p.lean_tab == nullptr) return nullptr;
+  if (!fast_eligible(h, p, true) || h->no_lean || p.lean_tab == nullptr) return nullptr;
   const DevConfig& c = p.cfg;
   if (c.change_step > 254 || c.n_goals < 2 || c.step_x != 1.0 || c.step_y != 1.0 || c.radius_sum != 25.0) return nullptr;
   if (c.margin != (double)(25 + c.window / 2 + 2)) return nullptr;
@@ -289,7 +310,7 @@ int launch(BallenvHandle* h, const Params& p_in, cudaStream_t s) {
   const unsigned grid = (unsigned)((p.n + kEnvsPerBlock - 1) / kEnvsPerBlock);
   const bool f64 = h->cfg.precision == BALLENV_F64;
   const bool fast = fast_eligible(h, p);
-  if (!fast && p.n_steps != 1) return fail(BALLENV_EINVAL, "internal: multi-step launch needs the fast kernel");
+  if (!fast && p.n_steps != 1) return fail(BALLENV_EINVAL, "internal: multi-step launch needs a rollout kernel");
   if (fast) {
     switch (h->cfg.window) {
       case 5: launch_f32_w5_fast(p, grid, s); break;
@@ -516,6 +537,7 @@ int ballenv_create(const BallenvConfig* cfg, int64_t n_envs, int64_t global_env_
       free(tab);
     }
   }
+  if (e == cudaSuccess) e = cudaMemset(h->arena + h->L.errors + 4, 1, 4);   // state_dirty: nothing is known yet
   // everything above ran on the legacy stream: a caller that launches on a non-blocking stream next must see it done
   if (e == cudaSuccess) e = cudaStreamSynchronize(0);
   if (e != cudaSuccess) {
@@ -556,6 +578,7 @@ int ballenv_create(const BallenvConfig* cfg, int64_t n_envs, int64_t global_env_
   p.stats = (double*)(a + L.stats);
   p.errors = (uint32_t*)(a + L.errors);
   p.lean_tab = L.lean_tab_entries > 0 ? (const uint16_t*)(a + L.lean_tab) : nullptr;
+  p.state_dirty = p.errors + 1;   // second word of the error block: "coordinates not known to be integral"
   for (int r = 0; r < 10; ++r) {   // Philox4x32 key schedule (ballenv_rng.cuh)
     p.rk[2 * r] = p.k0 + (uint32_t)r * kPhiloxW0;
     p.rk[2 * r + 1] = p.k1 + (uint32_t)r * kPhiloxW1;
@@ -624,7 +647,26 @@ int ballenv_reset(BallenvHandle* h, const uint8_t* mask, void* obs_out, ballenv_
   p.reset_mask = mask;
   p.obs = obs_out;
   p.reset_tape = h->reset_tape;
-  return launch(h, p, (cudaStream_t)stream);
+  int rc = launch(h, p, (cudaStream_t)stream);
+  // a full reset of the gym ruleset leaves nothing but integer draws in the state: the lean kernels may skip their test
+  if (rc == BALLENV_OK && mask == nullptr && h->cfg.ruleset == BALLENV_RULESET_GYM && h->cfg.precision == BALLENV_F32)
+    CUDA_TRY(cudaMemsetAsync(const_cast<uint32_t*>(h->base.state_dirty), 0, 4, (cudaStream_t)stream));
+  return rc;
+}
+
+int ballenv_state_written(BallenvHandle* h, ballenv_stream_t stream) {
+  if (h == nullptr) return fail(BALLENV_EINVAL, "handle is NULL");
+  DeviceGuard guard(h->device);
+  uint32_t* dirty = const_cast<uint32_t*>(h->base.state_dirty);
+  if (h->cfg.precision != BALLENV_F32 || h->cfg.ruleset != BALLENV_RULESET_GYM) {   // no lean kernels there: stays unknown
+    CUDA_TRY(cudaMemsetAsync(dirty, 1, 4, (cudaStream_t)stream));
+    return BALLENV_OK;
+  }
+  CUDA_TRY(cudaMemsetAsync(dirty, 0, 4, (cudaStream_t)stream));
+  validate_state_kernel<<<(unsigned)((h->n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(h->base, dirty);
+  h->launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  return BALLENV_OK;
 }
 
 int ballenv_reset_fixed(BallenvHandle* h, const uint8_t* mask, double goal_x, double goal_y, void* obs_out,
@@ -690,6 +732,8 @@ int ballenv_step(BallenvHandle* h, const void* actions, int action_kind, void* o
   p.reward = reward_out;
   p.done = done_out;
   p.reset_tape = h->reset_tape;
+  if (action_kind == BALLENV_ACT_XY_F32 || action_kind == BALLENV_ACT_XY_F64)   // raw (dx, dy): the agent may leave the integers
+    CUDA_TRY(cudaMemsetAsync(const_cast<uint32_t*>(h->base.state_dirty), 1, 4, (cudaStream_t)stream));
   if (h->step_tape != nullptr) {
     if (h->step_tape_pos >= h->step_tape_steps)
       return fail(BALLENV_ESTATE, "step tape exhausted after %lld steps", h->step_tape_steps);
@@ -723,7 +767,7 @@ int ballenv_step_many(BallenvHandle* h, const void* actions, int action_kind, in
     p.done = done_out;
     p.reset_tape = h->reset_tape;
     p.step_tape = h->step_tape;
-    if (!h->no_rollout && fast_eligible(h, p)) {
+    if (!h->no_rollout && (fast_eligible(h, p) || lean_launcher(h, p) != nullptr)) {
       // the kernel indexes the [T][n] arrays with 32 bits: at most (2^31 - 1) / n steps per launch
       const int64_t max_t = n > 0 ? (int64_t)0x7fffffff / (int64_t)n : n_steps;
       if (max_t < 1) return fail(BALLENV_EINVAL, "too many environments for one launch");

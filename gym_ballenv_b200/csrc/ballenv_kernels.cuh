@@ -139,6 +139,10 @@ struct Params {
   // of window column masks (LeanTab<W>, in the arena)
   uint32_t rk[20];
   const uint16_t* lean_tab;
+  // 0: every coordinate of the handle is known to be integral and inside the exact ranges (the lean kernels then skip
+  // their per-launch test); non-zero: unknown.  Maintained by the host (ballenv_capi.cu: full resets clear it, float
+  // actions and ballenv_state_written's validation set it)
+  const uint32_t* state_dirty;
 };
 
 // ---- arithmetic that must not be contracted into FMAs (the reference squares, then adds) -------------------

@@ -35,6 +35,8 @@ class BallVecEnv:
       * float32 / float64 ``[N, 2]`` raw ``(dx, dy)`` (what ``BallEnv.step`` indexes, ballenv_env.py:247-248)
     and returns ``(obs [N, 4 + W*W], reward [N], done [N] bool, info)``.  The returned tensors are views of
     env-owned double buffers: they stay valid until the step after next (``clone()`` to keep them).
+    ``info["state"]`` / ``state_views`` are live views of the state arrays: edit them through ``set_state`` or call
+    ``state_written()`` afterwards.
     """
 
     def __init__(self, num_envs: int, window: int = 5, config: Optional[EnvConfig] = None, ruleset: str = "gym",
@@ -307,6 +309,12 @@ class BallVecEnv:
         for k, val in fields.items():
             dst = self.state_views[k]
             dst.copy_(torch.as_tensor(val, device=self.device).to(dst.dtype))
+        self.state_written()
+
+    def state_written(self):
+        """Call after writing into ``state_views`` / ``info["state"]`` directly (set_state does it itself): the library
+        re-validates what its production kernels assume about the coordinates (ballenv_state_written)."""
+        check(LIB.ballenv_state_written(self._h, self._stream()))
 
     def set_draw_tape(self, step_tape=None, reset_tape=None, attempts: int = 1):
         """Parity mode: inject the random words (uint32, held as int64/uint32 CPU tensors or numpy arrays).

@@ -164,6 +164,14 @@ int ballenv_create(const BallenvConfig *cfg, int64_t n_envs, int64_t global_env_
                    uint64_t seed, void *arena, BallenvHandle **out);
 int ballenv_destroy(BallenvHandle *h);
 int ballenv_state_ptrs(BallenvHandle *h, BallenvStatePtrs *out);
+/*
+ * Tell the library that the caller has written state through the pointers of ballenv_state_ptrs (state injection:
+ * no reference counterpart - the reference's scripts assign env.state directly).  The production kernels take exact
+ * shortcuts that hold for the integral coordinates the gym ruleset produces and skip the test for it while nothing
+ * but resets and index-action steps has touched the state; this call re-validates the whole state on `stream` (one
+ * small kernel, no synchronisation).  Writing non-integral coordinates WITHOUT calling it gives wrong observations.
+ */
+int ballenv_state_written(BallenvHandle *h, ballenv_stream_t stream);
 
 /*
  * Replaces: BallEnv.reset() (ballenv_env.py:113-167) / createBoard.reset() (ballenv_pygame.py:460-513),

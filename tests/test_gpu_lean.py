@@ -245,3 +245,66 @@ def test_lean_is_not_selected_outside_its_domain():
     env = BallVecEnv(64, window=5)
     assert env.kernel_variant(1) == "lean" and env.kernel_variant(1, torch.float32) == "generic"
     env.close()
+
+
+def test_direct_state_writes_need_state_written(monkeypatch):
+    """The lean kernels skip their integrality test while the library knows the state to be integral (full reset, index
+    actions only).  A caller that edits the live state views directly announces it with state_written(): the state is
+    re-validated on the device and fractional coordinates take the general path again - same results as the
+    block-of-roles kernel, which shares that arithmetic."""
+    n, w = 256, 10
+    lean, ref = _pair(monkeypatch, n, w, "dense", "roles", seed=2, max_episode_steps=0, auto_reset=False)
+    lean.reset()
+    ref.reset()
+    for e in (lean, ref):
+        e.state_views["agent_x"][: n // 2] += 0.25        # a direct write into the arena ...
+        e.state_views["static_x"][:, ::3] += 0.5
+        e.state_written()                                  # ... announced
+    g = torch.Generator().manual_seed(9)
+    a = torch.randint(0, 9, (40, n), generator=g).cuda()
+    o1, r1, d1 = lean.step_many(a, keep_all_obs=True)
+    o2, r2, d2 = ref.step_many(a, keep_all_obs=True)
+    assert torch.equal(o1, o2) and torch.equal(r1, r2) and torch.equal(d1, d2)
+    # integral again (a full reset): the shortcut path, still identical
+    assert torch.equal(lean.reset(), ref.reset())
+    for t in range(20):
+        ol, rl, dl, _ = lean.step(a[t])
+        orf, rr, dr, _ = ref.step(a[t])
+        assert torch.equal(ol, orf) and torch.equal(rl, rr) and torch.equal(dl, dr), t
+    _same_state(lean, ref)
+    lean.close()
+    ref.close()
+
+
+@pytest.mark.parametrize("fmt", ["u8", "bits"])
+@pytest.mark.parametrize("w,cfgname,n", [(10, "dense", 1000), (5, "default", 777), (5, "dense", 64)])
+def test_lean_row_formats(w, cfgname, n, fmt):
+    """uint8 and bit-packed observation rows out of the lean kernels (single-step and rollout, ragged last warp) hold
+    the same 0 / 1 values as the float32 rows, every step."""
+    from gym_ballenv_b200 import BallVecEnv
+    cfg = _env_config(_cfg(cfgname))
+    dt = {"u8": torch.uint8, "bits": "bits"}[fmt]
+    ref = BallVecEnv(n, window=w, config=cfg, seed=5, max_episode_steps=19)
+    env = BallVecEnv(n, window=w, config=cfg, seed=5, max_episode_steps=19, obs_dtype=dt)
+    assert env.kernel_variant(1) == "lean" and env.kernel_variant(16) == "lean"
+    nb = 4 + w * w
+
+    def as01(o):
+        o = o.cpu().numpy()
+        if fmt == "bits":
+            words = o.astype(np.int64) & 0xffffffff
+            return ((words[..., None] >> np.arange(32)) & 1).reshape(o.shape[:-1] + (-1,))[..., :nb].astype(np.float32)
+        return o.astype(np.float32)
+
+    assert np.array_equal(as01(env.reset()), ref.reset().cpu().numpy())
+    g = torch.Generator().manual_seed(0)
+    for t in range(25):
+        a = torch.randint(0, 9, (n,), generator=g).cuda()
+        assert np.array_equal(as01(env.step(a)[0]), ref.step(a)[0].cpu().numpy()), t
+    a = torch.randint(0, 9, (33, n), generator=g).cuda()
+    o, r, d = env.step_many(a, keep_all_obs=True)
+    o2, r2, d2 = ref.step_many(a, keep_all_obs=True)
+    assert np.array_equal(as01(o), o2.cpu().numpy()) and torch.equal(r, r2) and torch.equal(d, d2)
+    assert env.error_flags() == 0
+    env.close()
+    ref.close()
