@@ -64,6 +64,24 @@ __global__ void selftest_sqrt_kernel(long long n, unsigned long long* bad) {
   if (__double_as_longlong(ballenv::sqrt_int22(s)) != __double_as_longlong(sqrt((double)s))) atomicAdd(bad, 1ull);
 }
 
+// the lean kernels' inline division (ballenv_lean.cuh: div64_fast_path) against the compiler's `/` on pairs shaped like
+// the reward's: num = difference of two distances of integral points (|num| <= 1.5, often tiny), den = a distance in
+// [471, 708] (total_distance of a gym-ruleset episode)
+__global__ void selftest_div_kernel(long long n, unsigned long long* bad) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint4 w = ballenv::philox4x32_10((uint32_t)i, (uint32_t)(i >> 32), 0u, 77u, 0x1234u, 0x5678u);
+  // two integral points at most one step apart, a goal and a start point: num = |p0 - g| - |p1 - g|, den = |s - g|
+  const double gx = (double)(w.x % 500u), gy = 480.0 + (double)(w.y % 20u);
+  const double px = (double)(w.z % 501u), py = (double)((w.z >> 16) % 501u);
+  const double qx = px + (double)((int)(w.w % 3u) - 1), qy = py + (double)((int)((w.w >> 8) % 3u) - 1);
+  const double sx = (double)((w.w >> 16) % 500u), sy = (double)((w.y >> 16) % 10u);
+  const double num = ballenv::dist64(gx, gy, px, py) - ballenv::dist64(gx, gy, qx, qy);
+  const double den = ballenv::dist64(gx, gy, sx, sy);
+  if (num == 0.0) return;
+  if (__double_as_longlong(ballenv::lean::div64_fast_path(num, den)) != __double_as_longlong(num / den)) atomicAdd(bad, 1ull);
+}
+
 namespace {
 
 thread_local char g_err[512] = "";
@@ -960,13 +978,15 @@ int ballenv_kernel_variant(BallenvHandle* h, int action_kind, int32_t n_steps) {
 
 int ballenv_selftest(int which, int64_t arg, int device, int64_t* mismatches) {
   if (mismatches == nullptr) return fail(BALLENV_EINVAL, "mismatches is null");
-  if (which != 0) return fail(BALLENV_EINVAL, "unknown self-test %d", which);
-  if (arg < 0 || arg > (1ll << 22)) return fail(BALLENV_EINVAL, "sqrt_int22 is defined for 0 <= s < 2^22");
+  if (which != 0 && which != 1) return fail(BALLENV_EINVAL, "unknown self-test %d", which);
+  if (which == 0 && (arg < 0 || arg > (1ll << 22))) return fail(BALLENV_EINVAL, "sqrt_int22 is defined for 0 <= s < 2^22");
+  if (which == 1 && (arg < 0 || arg > (1ll << 34))) return fail(BALLENV_EINVAL, "at most 2^34 pairs");
   DeviceGuard guard(device);
   unsigned long long* d_bad = nullptr;
   CUDA_TRY(cudaMalloc(&d_bad, sizeof(*d_bad)));
   cudaMemset(d_bad, 0, sizeof(*d_bad));
-  selftest_sqrt_kernel<<<(unsigned)((arg + 255) / 256), 256>>>(arg, d_bad);
+  if (which == 0) selftest_sqrt_kernel<<<(unsigned)((arg + 255) / 256), 256>>>(arg, d_bad);
+  else selftest_div_kernel<<<(unsigned)((arg + 255) / 256), 256>>>(arg, d_bad);
   unsigned long long bad = 0;
   cudaError_t e = cudaMemcpy(&bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost);
   cudaFree(d_bad);

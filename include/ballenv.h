@@ -280,8 +280,9 @@ int64_t ballenv_launch_count(BallenvHandle *h);
 int ballenv_kernel_variant(BallenvHandle *h, int action_kind, int32_t n_steps);
 /* Device self-tests of the arithmetic shortcuts the step kernel takes (no reference counterpart; run by the GPU
  * tests).  which = 0: the integer square root used for the distance to the goal when all coordinates are integral
- * (sqrt_int22) against sqrt() for every integer 0 <= s < arg; *mismatches receives the number of differing
- * results (synchronises the device). */
+ * (sqrt_int22) against sqrt() for every integer 0 <= s < arg; which = 1: the inline fp64 division of the progress
+ * reward (the division's fast path without its out-of-line slow path) against `/` on arg pseudo-random pairs shaped
+ * like the reward's operands.  *mismatches receives the number of differing results (synchronises the device). */
 int ballenv_selftest(int which, int64_t arg, int device, int64_t *mismatches /* host */);
 
 #ifdef __cplusplus
