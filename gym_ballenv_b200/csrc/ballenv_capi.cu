@@ -253,10 +253,12 @@ struct BallenvHandle {
   long long step_tape_steps = 0, step_tape_pos = 0;
   uint32_t* reset_tape = nullptr;
   // device staging for ballenv_step_host
-  char* stage = nullptr;        // two staging sets (ballenv_step_many_host alternates between them)
-  size_t stage_bytes = 0, stage_set = 0;
+  char* stage = nullptr;
+  size_t stage_bytes = 0;
   size_t stage_act = 0, stage_obs = 0, stage_rew = 0, stage_done = 0;
   // ballenv_step_many_host: copy streams either way and the events that order them against the compute stream
+  char* many = nullptr;         // chunk staging of ballenv_step_many_host (two sets)
+  size_t many_bytes = 0;
   cudaStream_t s_in = nullptr, s_out = nullptr;
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_k[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr}, ev_start = nullptr;
   long long launches = 0;
@@ -416,7 +418,7 @@ int ensure_stage(BallenvHandle* h, int action_kind) {
   const size_t o = align_up(n * (size_t)obs_row_elems(h->cfg) * obs_elem_bytes(h->cfg), 256);
   const size_t r = align_up(n * 8, 256);
   const size_t d = align_up(n, 256);
-  const size_t need = 2 * (a + o + r + d);
+  const size_t need = a + o + r + d;
   (void)action_kind;
   if (h->stage_bytes < need) {
     if (h->stage) cudaFree(h->stage);
@@ -424,7 +426,6 @@ int ensure_stage(BallenvHandle* h, int action_kind) {
     h->stage_bytes = 0;
     CUDA_TRY(cudaMalloc(&h->stage, need));
     h->stage_bytes = need;
-    h->stage_set = a + o + r + d;
     h->stage_act = 0;
     h->stage_obs = a;
     h->stage_rew = a + o;
@@ -613,6 +614,7 @@ int ballenv_destroy(BallenvHandle* h) {
   if (h->step_tape) cudaFree(h->step_tape);
   if (h->reset_tape) cudaFree(h->reset_tape);
   if (h->stage) cudaFree(h->stage);
+  if (h->many) cudaFree(h->many);
   if (h->s_in) cudaStreamDestroy(h->s_in);
   if (h->s_out) cudaStreamDestroy(h->s_out);
   for (int i = 0; i < 2; ++i) {
@@ -851,8 +853,28 @@ int ballenv_step_many_host(BallenvHandle* h, const void* actions_host, int actio
   if (n_steps < 0) return fail(BALLENV_EINVAL, "n_steps < 0");
   if (n_steps == 0) return BALLENV_OK;
   DeviceGuard guard(h->device);
-  int rc = ensure_stage(h, action_kind);
-  if (rc != BALLENV_OK) return rc;
+  const size_t n = (size_t)h->n;
+  const size_t act_b = n * (size_t)ab;
+  const size_t obs_b = n * (size_t)obs_row_elems(h->cfg) * obs_elem_bytes(h->cfg);
+  const size_t rew_b = n * (h->cfg.precision == BALLENV_F64 ? 8 : 4);
+  const size_t done_b = n;
+  // The actions of all steps are known up front: the rollout proceeds in chunks of `tc` steps - one copy in, ONE launch
+  // of the rollout kernel (ballenv_step_many), three copies out per chunk - with two device staging sets, so that the
+  // copies out of chunk c overlap the kernel of chunk c + 1 and the copy in of chunk c + 2.  Every step's actions and
+  // every step's rows / rewards / dones cross the bus; the state never leaves the device.
+  const size_t per_step = align_up(act_b, 256) + align_up(obs_b, 256) + align_up(rew_b, 256) + align_up(done_b, 256);
+  int tc = (int)((size_t)(192u << 20) / per_step);   // staging budget per set
+  tc = tc < 1 ? 1 : (tc > 64 ? 64 : tc);
+  if (tc > (n_steps + 5) / 6) tc = (n_steps + 5) / 6;   // at least six chunks per call: something to overlap
+  const size_t o_act = 0, o_obs = align_up(act_b * tc, 256), o_rew = o_obs + align_up(obs_b * tc, 256),
+               o_done = o_rew + align_up(rew_b * tc, 256), set_b = o_done + align_up(done_b * tc, 256);
+  if (h->many_bytes < 2 * set_b) {
+    if (h->many) cudaFree(h->many);
+    h->many = nullptr;
+    h->many_bytes = 0;
+    CUDA_TRY(cudaMalloc(&h->many, 2 * set_b));
+    h->many_bytes = 2 * set_b;
+  }
   if (h->s_in == nullptr) {
     CUDA_TRY(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
@@ -864,36 +886,32 @@ int ballenv_step_many_host(BallenvHandle* h, const void* actions_host, int actio
     CUDA_TRY(cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming));
   }
   cudaStream_t s = (cudaStream_t)stream;
-  const size_t n = (size_t)h->n;
-  const size_t obs_b = n * (size_t)obs_row_elems(h->cfg) * obs_elem_bytes(h->cfg);
-  const size_t rew_b = n * (h->cfg.precision == BALLENV_F64 ? 8 : 4);
-  // Three streams, two staging sets: while the kernel of step t runs on `stream`, the actions of step t + 1 travel
-  // host -> device and the rows / rewards / dones of step t - 1 device -> host.  A set is reused two steps later: its
-  // actions once the kernel that read them has run, its outputs once they have been copied out.
   CUDA_TRY(cudaEventRecord(h->ev_start, s));          // the copy streams start behind whatever the caller had enqueued
   CUDA_TRY(cudaStreamWaitEvent(h->s_in, h->ev_start, 0));
   CUDA_TRY(cudaStreamWaitEvent(h->s_out, h->ev_start, 0));
-  for (int t = 0; t < n_steps; ++t) {
-    const int b = t & 1;
-    char* st = h->stage + (size_t)b * h->stage_set;
-    if (t >= 2) CUDA_TRY(cudaStreamWaitEvent(h->s_in, h->ev_k[b], 0));      // kernel t - 2 has read this set's actions
-    CUDA_TRY(cudaMemcpyAsync(st + h->stage_act, (const char*)actions_host + (size_t)t * n * ab, n * ab,
-                             cudaMemcpyHostToDevice, h->s_in));
+  int c = 0;
+  for (int t0 = 0; t0 < n_steps; t0 += tc, ++c) {
+    const int tn = n_steps - t0 < tc ? n_steps - t0 : tc;
+    const int b = c & 1;
+    char* st = h->many + (size_t)b * set_b;
+    if (c >= 2) CUDA_TRY(cudaStreamWaitEvent(h->s_in, h->ev_k[b], 0));      // the kernel of chunk c - 2 has read this set's actions
+    CUDA_TRY(cudaMemcpyAsync(st + o_act, (const char*)actions_host + (size_t)t0 * act_b, act_b * tn, cudaMemcpyHostToDevice,
+                             h->s_in));
     CUDA_TRY(cudaEventRecord(h->ev_in[b], h->s_in));
     CUDA_TRY(cudaStreamWaitEvent(s, h->ev_in[b], 0));
-    if (t >= 2) CUDA_TRY(cudaStreamWaitEvent(s, h->ev_out[b], 0));          // outputs of step t - 2 have left this set
-    rc = ballenv_step(h, st + h->stage_act, action_kind, obs_host ? st + h->stage_obs : nullptr,
-                      reward_host ? st + h->stage_rew : nullptr, done_host ? (uint8_t*)(st + h->stage_done) : nullptr, stream);
+    if (c >= 2) CUDA_TRY(cudaStreamWaitEvent(s, h->ev_out[b], 0));          // the outputs of chunk c - 2 have left this set
+    int rc = ballenv_step_many(h, st + o_act, action_kind, tn, obs_host ? st + o_obs : nullptr, 1,
+                               reward_host ? st + o_rew : nullptr, done_host ? (uint8_t*)(st + o_done) : nullptr, stream);
     if (rc != BALLENV_OK) return rc;
     CUDA_TRY(cudaEventRecord(h->ev_k[b], s));
     CUDA_TRY(cudaStreamWaitEvent(h->s_out, h->ev_k[b], 0));
     if (obs_host)
-      CUDA_TRY(cudaMemcpyAsync((char*)obs_host + (size_t)t * obs_b, st + h->stage_obs, obs_b, cudaMemcpyDeviceToHost, h->s_out));
+      CUDA_TRY(cudaMemcpyAsync((char*)obs_host + (size_t)t0 * obs_b, st + o_obs, obs_b * tn, cudaMemcpyDeviceToHost, h->s_out));
     if (reward_host)
-      CUDA_TRY(cudaMemcpyAsync((char*)reward_host + (size_t)t * rew_b, st + h->stage_rew, rew_b, cudaMemcpyDeviceToHost,
+      CUDA_TRY(cudaMemcpyAsync((char*)reward_host + (size_t)t0 * rew_b, st + o_rew, rew_b * tn, cudaMemcpyDeviceToHost,
                                h->s_out));
     if (done_host)
-      CUDA_TRY(cudaMemcpyAsync(done_host + (size_t)t * n, st + h->stage_done, n, cudaMemcpyDeviceToHost, h->s_out));
+      CUDA_TRY(cudaMemcpyAsync(done_host + (size_t)t0 * done_b, st + o_done, done_b * tn, cudaMemcpyDeviceToHost, h->s_out));
     CUDA_TRY(cudaEventRecord(h->ev_out[b], h->s_out));
   }
   CUDA_TRY(cudaStreamSynchronize(h->s_out));

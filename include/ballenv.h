@@ -242,12 +242,13 @@ int ballenv_step_host(BallenvHandle *h, const void *actions_host, int action_kin
                       void *reward_host, uint8_t *done_host, ballenv_stream_t stream);
 
 /*
- * T consecutive ballenv_step_host calls as one pipelined call (open-loop host rollouts, or a host policy that acts on
- * observations one step old): actions_host [T][n], obs_host [T][n][row] (or NULL), reward_host [T][n], done_host [T][n]
- * (or NULL).  While the kernel of step t runs on `stream`, the actions of step t + 1 travel host -> device and the
- * results of step t - 1 device -> host on two internal copy streams (two device staging sets).  Same results as T
- * calls of ballenv_step_host; returns synchronised.  Pin the host buffers (and allocate them on the GPU's NUMA node)
- * for speed.
+ * T consecutive ballenv_step_host calls as one call, for rollouts whose actions are known up front (open loop, or a
+ * host policy that acts on observations a chunk old): actions_host [T][n], obs_host [T][n][row] (or NULL), reward_host
+ * [T][n], done_host [T][n] (or NULL).  The steps run in chunks: per chunk one copy in, ONE launch of the rollout kernel
+ * (as ballenv_step_many) and the copies out, on two internal copy streams with two device staging sets, so that the
+ * copies of consecutive chunks overlap the kernels.  Every step's actions and results cross the bus; the state never
+ * leaves the device.  Same results as T calls of ballenv_step_host; returns synchronised.  Pin the host buffers (and
+ * allocate them on the GPU's NUMA node) for speed.
  */
 int ballenv_step_many_host(BallenvHandle *h, const void *actions_host, int action_kind, int32_t n_steps, void *obs_host,
                            void *reward_host, uint8_t *done_host, ballenv_stream_t stream);

@@ -591,6 +591,36 @@ def test_step_host_equals_step(obs_dtype):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("obs_dtype,parity,w", [(torch.float32, False, 10), (torch.uint8, False, 5), ("bits", False, 10),
+                                                (torch.float32, True, 5)])
+def test_step_many_host_equals_step_many(obs_dtype, parity, w):
+    """ballenv_step_many_host (host buffers; chunks of steps, one rollout launch per chunk, copies overlapped on two
+    internal streams and two staging sets) returns what the same steps return on the device - several chunks, so that
+    a staging set is reused; production (lean rollout kernel) and fp64 parity (one generic launch per step) handles."""
+    from gym_ballenv_b200 import BallVecEnv
+    n, T = 333, 150
+    kw = dict(window=w, seed=8, max_episode_steps=11, obs_dtype=obs_dtype, parity=parity)
+    dev_env, host_env = BallVecEnv(n, **kw), BallVecEnv(n, **kw)
+    dev_env.reset()
+    host_env.reset()
+    g = torch.Generator().manual_seed(6)
+    for rep in range(2):
+        a = torch.randint(0, 9, (T, n), generator=g)
+        o, r, d = dev_env.step_many(a.cuda(), keep_all_obs=True)
+        obs = torch.empty(tuple(o.shape), dtype=o.dtype).pin_memory()
+        rew = torch.empty((T, n), dtype=r.dtype).pin_memory()
+        done = torch.empty((T, n), dtype=torch.uint8).pin_memory()
+        host_env.step_many_host(a.pin_memory(), obs, rew, done)
+        assert torch.equal(o.cpu(), obs) and torch.equal(r.cpu(), rew) and torch.equal(d.cpu(), done.bool()), rep
+    sa, sb = dev_env.get_state(), host_env.get_state()
+    for k in sa:
+        assert torch.equal(sa[k], sb[k]), k
+    assert host_env.error_flags() == 0
+    dev_env.close()
+    host_env.close()
+
+
+@pytest.mark.gpu
 def test_state_snapshot_resumes_identically():
     """Checkpoint / resume of the environment state: get_state() of a running env loaded into a
     fresh env of the same seed with set_state() continues bit-identically, resets included."""
@@ -653,6 +683,18 @@ def test_integer_sqrt_shortcut_is_exact():
     rc = L.LIB.ballenv_selftest(0, 1 << 22, 0, C.byref(bad))
     assert rc == 0, L.LIB.ballenv_last_error()
     assert bad.value == 0, "%d of 2^22 arguments differ from sqrt()" % bad.value
+
+
+@pytest.mark.gpu
+def test_inline_reward_division_is_exact():
+    """The lean kernels divide the progress reward with the fp64 division's fast path written out (no out-of-line
+    slow path in the step loop): bit-identical to `/` on 2^28 operand pairs shaped like the reward's."""
+    import ctypes as C
+    from gym_ballenv_b200 import _lib as L
+    bad = C.c_int64(-1)
+    rc = L.LIB.ballenv_selftest(1, 1 << 28, 0, C.byref(bad))
+    assert rc == 0, L.LIB.ballenv_last_error()
+    assert bad.value == 0, "%d of 2^28 quotients differ from /" % bad.value
 
 
 @pytest.mark.gpu
