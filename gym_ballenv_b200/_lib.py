@@ -57,7 +57,7 @@ EXPORTS = (
     "ballenv_create", "ballenv_destroy", "ballenv_state_ptrs", "ballenv_reset", "ballenv_step",
     "ballenv_step_many", "ballenv_observe", "ballenv_observe_features", "ballenv_observe_blocks", "ballenv_step_host", "ballenv_set_draw_tape", "ballenv_stats",
     "ballenv_stats_reset", "ballenv_error_flags", "ballenv_launch_count", "ballenv_selftest", "ballenv_kernel_variant",
-    "ballenv_step_many_host", "ballenv_reset_fixed", "ballenv_state_written",
+    "ballenv_step_many_host", "ballenv_reset_fixed", "ballenv_state_written", "ballenv_observe_patches",
 )
 
 
@@ -80,6 +80,7 @@ def _bind(lib):
     lib.ballenv_observe.argtypes = [vp, vp, vp]
     lib.ballenv_observe_features.argtypes = [vp, vp, vp]
     lib.ballenv_observe_blocks.argtypes = [vp, vp, vp]
+    lib.ballenv_observe_patches.argtypes = [vp, vp, i32, i32, i32, i32, vp]
     lib.ballenv_step_host.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp]
     lib.ballenv_step_many_host.argtypes = [vp, vp, C.c_int, i32, vp, vp, vp, vp]
     lib.ballenv_set_draw_tape.argtypes = [vp, vp, i64, vp, i64, i32]

@@ -44,6 +44,30 @@ class Policy(nn.Module):
         return F.softmax(self.action_head(x), dim=-1), self.value_head(x)
 
 
+class PolicyCNN(nn.Module):
+    """examples/ball_cnn_ac3.py:80-106 (the same class in ball_cnn_reinforce.py): three 5 x 5 stride-2 convolutions with
+    batch norm over the 3 x 40 x 40 patch (``BallVecEnv.rgb_patches``), the 128 features joined with the 4 goal-quadrant
+    floats (``obs[:, :4]``), then the 9-way action head and the value head.  Parameter names as in the reference."""
+
+    def __init__(self):
+        super().__init__()
+        self.conv1 = nn.Conv2d(3, 16, kernel_size=5, stride=2)
+        self.bn1 = nn.BatchNorm2d(16)
+        self.conv2 = nn.Conv2d(16, 32, kernel_size=5, stride=2)
+        self.bn2 = nn.BatchNorm2d(32)
+        self.conv3 = nn.Conv2d(32, 32, kernel_size=5, stride=2)
+        self.bn3 = nn.BatchNorm2d(32)
+        self.action_head = nn.Linear(132, 9)
+        self.value_head = nn.Linear(132, 1)
+
+    def forward(self, x, y):
+        x = F.relu(self.bn1(self.conv1(x)))
+        x = F.relu(self.bn2(self.conv2(x)))
+        x = F.relu(self.bn3(self.conv3(x)))
+        x = torch.cat((x.view(x.size(0), -1), y), 1)
+        return F.softmax(self.action_head(x), dim=-1), self.value_head(x)
+
+
 def rollout(env: BallVecEnv, policy: Policy, n_steps: int, obs: Optional[torch.Tensor] = None, greedy: bool = False,
             generator: Optional[torch.Generator] = None) -> Dict[str, torch.Tensor]:
     """n_steps of policy-in-the-loop stepping for all environments; no host synchronisation inside the loop.

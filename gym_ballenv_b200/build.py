@@ -38,7 +38,7 @@ LEAN_INSTANCES = [(5, 13, 5), (10, 13, 5), (10, 8, 24), (5, 8, 24)]
 
 def _sources():
     deps = [os.path.join(CSRC, f) for f in ("ballenv_kernels.cuh", "ballenv_rng.cuh", "ballenv_lean.cuh",
-                                            "ballenv_features.cuh")]
+                                            "ballenv_features.cuh", "ballenv_patches.cuh", "ballenv_reset_fixed.cuh")]
     deps.append(os.path.join(os.path.dirname(HERE), "include", "ballenv.h"))
     jobs = [(os.path.join(CSRC, "ballenv_capi.cu"), os.path.join(OBJ, "ballenv_capi.o"), [])]
     for t, w, fast, name in INSTANCES:

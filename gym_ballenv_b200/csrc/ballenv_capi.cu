@@ -11,6 +11,7 @@
 #include "ballenv_kernels.cuh"
 #include "ballenv_features.cuh"
 #include "ballenv_lean.cuh"
+#include "ballenv_patches.cuh"
 #include "ballenv_reset_fixed.cuh"
 
 using namespace ballenv;
@@ -261,6 +262,10 @@ struct BallenvHandle {
   size_t many_bytes = 0;
   cudaStream_t s_in = nullptr, s_out = nullptr;
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_k[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr}, ev_start = nullptr;
+  // ballenv_observe_patches: device tables of the last (width, out_size, interp) asked for
+  char* patch_tab = nullptr;
+  int patch_key[3] = {0, 0, -1};
+  int patch_ksize = 0;
   long long launches = 0;
   bool no_rollout = false;      // BALLENV_NO_ROLLOUT=1: ballenv_step_many launches one kernel per step (tests, profiling)
   int lean_g = 0;               // BALLENV_LEAN_G=1|2: lanes per environment of the lean kernels (0: the measured best)
@@ -615,6 +620,7 @@ int ballenv_destroy(BallenvHandle* h) {
   if (h->reset_tape) cudaFree(h->reset_tape);
   if (h->stage) cudaFree(h->stage);
   if (h->many) cudaFree(h->many);
+  if (h->patch_tab) cudaFree(h->patch_tab);
   if (h->s_in) cudaStreamDestroy(h->s_in);
   if (h->s_out) cudaStreamDestroy(h->s_out);
   for (int i = 0; i < 2; ++i) {
@@ -732,6 +738,63 @@ int ballenv_observe_blocks(BallenvHandle* h, float* out, ballenv_stream_t stream
   const unsigned grid = (unsigned)((h->n + 127) / 128);
   if (h->cfg.precision == BALLENV_F64) ballenv_blocks_kernel<double><<<grid, 128, 0, (cudaStream_t)stream>>>(h->base, out);
   else ballenv_blocks_kernel<float><<<grid, 128, 0, (cudaStream_t)stream>>>(h->base, out);
+  h->launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  return BALLENV_OK;
+}
+
+int ballenv_observe_patches(BallenvHandle* h, void* out, int32_t width, int32_t out_size, int32_t interp,
+                            int32_t out_format, ballenv_stream_t stream) {
+  if (h == nullptr || out == nullptr) return fail(BALLENV_EINVAL, "NULL argument");
+  if (h->cfg.ruleset != BALLENV_RULESET_GYM) return fail(BALLENV_EINVAL, "rgb patches render the gym ruleset's viewer");
+  if (width < 2 || width > kPatchMaxWidth || (width & 1) != 0) return fail(BALLENV_EINVAL, "width must be even, 2..%d", kPatchMaxWidth);
+  if (out_size < 1 || out_size > kPatchMaxOut) return fail(BALLENV_EINVAL, "out_size must be 1..%d", kPatchMaxOut);
+  if (interp != BALLENV_INTERP_BILINEAR && interp != BALLENV_INTERP_BICUBIC) return fail(BALLENV_EINVAL, "unknown interp %d", interp);
+  if (out_format != BALLENV_OBS_F32 && out_format != BALLENV_OBS_U8) return fail(BALLENV_EINVAL, "patches are float32 or uint8");
+  DeviceGuard guard(h->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  // device tables: [bounds 2 * 64][coef 64 * kmax][agent 10][goal 10][obstacle 40] - rebuilt when the geometry changes
+  constexpr int kMaxK = 64;   // taps of the resampling kernel: ceil(support * width / out_size) * 2 + 1 must fit
+  const size_t off_coef = 4 * 2 * kPatchMaxOut, off_masks = (off_coef + 4 * (size_t)kPatchMaxOut * kMaxK + 7) / 8 * 8;
+  const size_t tab_bytes = off_masks + 8 * (2 * kPatchAgentR + 10 + 2 * kPatchObstacleR);
+  if (h->patch_tab == nullptr) CUDA_TRY(cudaMalloc(&h->patch_tab, tab_bytes));
+  if (h->patch_key[0] != width || h->patch_key[1] != out_size || h->patch_key[2] != interp) {
+    std::vector<int> bounds, kk;
+    const int ksize = patch_host::coefficients(width, out_size, interp == BALLENV_INTERP_BICUBIC, &bounds, &kk);
+    if (ksize > kMaxK) return fail(BALLENV_EINVAL, "width / out_size too large: the resampling kernel has %d taps (max %d)", ksize, kMaxK);
+    unsigned long long masks[2 * kPatchAgentR + 10 + 2 * kPatchObstacleR];
+    patch_host::sprite_rows(patch_host::circle_polygon(kPatchAgentR), kPatchAgentR, masks);                       // ballenv_env.py:367
+    patch_host::sprite_rows(std::vector<double>{5, 5, 5, -5, -5, 5, -5, -5}, 5, masks + 2 * kPatchAgentR);           // :371
+    patch_host::sprite_rows(patch_host::circle_polygon(kPatchObstacleR), kPatchObstacleR, masks + 2 * kPatchAgentR + 10);   // :299, :305
+    // (pageable sources: the copies are staged before these calls return)
+    CUDA_TRY(cudaMemcpyAsync(h->patch_tab, bounds.data(), 4 * bounds.size(), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(h->patch_tab + off_coef, kk.data(), 4 * kk.size(), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(h->patch_tab + off_masks, masks, sizeof(masks), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaStreamSynchronize(s));   // the host vectors go away
+    h->patch_key[0] = width;
+    h->patch_key[1] = out_size;
+    h->patch_key[2] = interp;
+    h->patch_ksize = ksize;
+  }
+  PatchTables tb;
+  tb.width = width;
+  tb.out = out_size;
+  tb.ksize = h->patch_ksize;
+  tb.bounds = reinterpret_cast<const int*>(h->patch_tab);
+  tb.coef = reinterpret_cast<const int*>(h->patch_tab + off_coef);
+  tb.agent = reinterpret_cast<const unsigned long long*>(h->patch_tab + off_masks);
+  tb.goal = tb.agent + 2 * kPatchAgentR;
+  tb.obstacle = tb.goal + 10;
+  const int n_obj = 2 + h->cfg.static_obstacles + h->cfg.dynamic_obstacles;
+  const size_t smem = patch_smem_bytes(width, out_size, tb.ksize, n_obj);
+  if (smem > 200 * 1024) return fail(BALLENV_EINVAL, "patch geometry needs %zu bytes of shared memory", smem);
+  if (h->cfg.precision == BALLENV_F64) {
+    CUDA_TRY(cudaFuncSetAttribute(ballenv_patch_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ballenv_patch_kernel<double><<<(unsigned)h->n, kPatchThreads, smem, s>>>(h->base, tb, out, out_format == BALLENV_OBS_U8);
+  } else {
+    CUDA_TRY(cudaFuncSetAttribute(ballenv_patch_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ballenv_patch_kernel<float><<<(unsigned)h->n, kPatchThreads, smem, s>>>(h->base, tb, out, out_format == BALLENV_OBS_U8);
+  }
   h->launches += 1;
   CUDA_TRY(cudaGetLastError());
   return BALLENV_OK;

@@ -207,6 +207,36 @@ class BallEnv(object):
         return v.observe()
 
 
+    def extract_patch(self, state=None, width=100, interp="bicubic"):
+        """``extract_patch(state, width)`` of the pixel-policy scripts (examples/ball_cnn_reinforce.py:120-163): the
+        viewer's frame around the agent, resized to 40 x 40 - float32 [1, 3, 40, 40] in [0, 1] on the device, rendered
+        by the GPU (BallVecEnv.rgb_patches) instead of pyglet + PIL.  ``state``: a reference-style state list, or None
+        for the current state."""
+        if state is None or (self.state is not None and len(state) == len(self.state)
+                             and all(a == b for a, b in zip(state, self.state))):
+            self._ensure()
+            return self._vec.rgb_patches(width=width, interp=interp)
+        k = len(state) - 3
+        ks = self._cfg.static_obstacles if k == self._cfg.static_obstacles + self._cfg.dynamic_obstacles else k
+        key = ("patch", ks, k - ks)
+        v = self._scratch.get(key)
+        if v is None:
+            cfg = EnvConfig(static_obstacles=ks, dynamic_obstacles=k - ks,
+                            obstacle_speed=tuple(self._cfg.obstacle_speed)[:k - ks] if k > ks else (),
+                            obs_goal_position=self._cfg.obs_goal_position if k > ks else ())
+            v = BallVecEnv(1, window=5, config=cfg, device=self._device, parity=True, auto_reset=False, max_episode_steps=0)
+            self._scratch[key] = v
+        fields = dict(agent_x=[state[0][0]], agent_y=[state[0][1]], goal_x=[state[1][0]], goal_y=[state[1][1]])
+        if ks:
+            fields["static_x"] = [[float(p[0])] for p in state[3:3 + ks]]
+            fields["static_y"] = [[float(p[1])] for p in state[3:3 + ks]]
+        if k > ks:
+            fields["dynamic_x"] = [[float(p[0])] for p in state[3 + ks:]]
+            fields["dynamic_y"] = [[float(p[1])] for p in state[3 + ks:]]
+        v.set_state(**fields)
+        return v.rgb_patches(width=width, interp=interp)
+
+
 class TimeLimit(object):
     """The wrapper gym.make() puts around the env for ``timestep_limit = 1000`` (gym_ballenv/__init__.py:7;
     gym 0.10.9 ``TimeLimit``: done once elapsed steps >= max_episode_steps)."""

@@ -187,6 +187,26 @@ class BallVecEnv:
         check(LIB.ballenv_observe_blocks(self._h, C.c_void_p(out.data_ptr()), self._stream()))
         return out
 
+    def rgb_patches(self, width: int = 100, size: int = 40, interp: str = "bicubic", dtype=torch.float32,
+                    out: torch.Tensor = None) -> torch.Tensor:
+        """The pixel policies' observation (``extract_patch`` of examples/ball_cnn_reinforce.py:120-163 and
+        examples/ball_cnn_ac3.py:248-307): the viewer's frame (ballenv_env.py:357-386) cropped to ``width`` x ``width``
+        around the agent and resized to ``size`` x ``size`` as PIL does (``interp`` "bicubic" or "bilinear"), for every
+        environment at once: float32 [N, 3, size, size] in [0, 1] (ToTensor) or uint8, on the device, of the current
+        state.  Rendered on the GPU - no pyglet, no host round trip."""
+        if interp not in ("bilinear", "bicubic"):
+            raise ValueError("interp must be 'bilinear' or 'bicubic'")
+        if dtype not in (torch.float32, torch.uint8):
+            raise ValueError("patches are float32 or uint8")
+        if out is None:
+            out = torch.empty((self.num_envs, 3, size, size), dtype=dtype, device=self.device)
+        elif out.shape != (self.num_envs, 3, size, size) or out.dtype != dtype or not out.is_contiguous() or out.device != self.device:
+            raise ValueError("out must be a contiguous [N, 3, size, size] tensor of the requested dtype on the env's device")
+        check(LIB.ballenv_observe_patches(self._h, C.c_void_p(out.data_ptr()), int(width), int(size),
+                                          1 if interp == "bicubic" else 0,
+                                          L.OBS_F32 if dtype == torch.float32 else L.OBS_U8, self._stream()))
+        return out
+
     def _next_buf(self):
         self._flip ^= 1
         return self._bufs[self._flip]

@@ -234,6 +234,22 @@ int ballenv_observe_features(BallenvHandle *h, float *out, ballenv_stream_t stre
 int ballenv_observe_blocks(BallenvHandle *h, float *out, ballenv_stream_t stream);
 
 /*
+ * Replaces: extract_patch(state, width=100) of the pixel-policy scripts (examples/ball_cnn_reinforce.py:120-163; the
+ * copy at examples/ball_cnn_ac3.py:248-307) - env.render(mode='rgb_array') (ballenv_env.py:357-386: white 500 x 500
+ * frame, agent = black 30-gon of radius 5, goal = black quad, obstacles = 30-gons of radius 20, red if speed == 0
+ * else green, drawn in that order), the frame padded with white, cropped to width x width around the agent, resized
+ * with PIL (BICUBIC in ball_cnn_reinforce.py:124, BILINEAR in ball_cnn_ac3.py:255) to 40 x 40 and scaled to [0, 1].
+ * out : device float32 (BALLENV_OBS_F32, value / 255) or uint8 (BALLENV_OBS_U8) [n][3][out_size][out_size] of the
+ * CURRENT state.  gym ruleset only; width even, <= 128; out_size <= 64.  The resize is Pillow's 8-bit two-pass
+ * resampling bit for bit; the frame restates the gym 0.10.9 viewer (pixel centre inside the polygon, no
+ * anti-aliasing, coordinates rounded to integers) - parity for that half is unpinned: pyglet / OpenGL cannot run here.
+ */
+#define BALLENV_INTERP_BILINEAR 0
+#define BALLENV_INTERP_BICUBIC 1
+int ballenv_observe_patches(BallenvHandle *h, void *out, int32_t width, int32_t out_size, int32_t interp,
+                            int32_t out_format, ballenv_stream_t stream);
+
+/*
  * Same as ballenv_step but with HOST buffers (pinned or pageable): copies actions host->device, steps,
  * copies obs/reward/done device->host and synchronises `stream` before returning.  This is the call the
  * end-to-end number of bench.py is measured through.

@@ -20,6 +20,9 @@ Fixture families
   edge_gym.npz          hand-built single-step cases on injected states.
   window_kat.npz        RNG-free window-observation known answers (W=5,10,21).
   blocks_kat.npz        legacy 29-float block-count observation of the REINFORCE scripts, 200 states.
+  patches_kat.npz       40 x 40 rgb patches of the pixel policies: the reference's patch path cannot run (pyglet /
+                        OpenGL viewer, Python-2 slicing), so the frame is the restatement of oracle/patches.py and
+                        the pad / crop / resize is done here with the installed Pillow itself (BICUBIC and BILINEAR).
 """
 from __future__ import annotations
 
@@ -399,6 +402,46 @@ def blocks_kats():
                 made_by="oracle/gen_golden.py: prep_state2 of examples/ball_env_reinforce.py:130-172, AST-lifted")))
 
 
+def patches_kats():
+    """States -> uint8 [3, 40, 40] patches: restated frame (oracle/patches.py), then the steps of extract_patch
+    (examples/ball_cnn_reinforce.py:130-147) with numpy padding and Pillow's own resize."""
+    from PIL import Image
+    from . import patches as P
+    rng = np.random.RandomState(40)
+    KS, KD = 4, 4
+    agents, goals, stat, dyn, out_c, out_l = [], [], [], [], [], []
+    for i in range(48):
+        agent = tuple(int(v) for v in rng.randint(0, 501, 2))
+        goal = tuple(int(v) for v in (np.array(agent) + rng.randint(-60, 61, 2))) if i % 3 == 0 else tuple(int(v) for v in rng.randint(0, 500, 2))
+        st = [tuple(int(v) for v in (np.array(agent) + rng.randint(-75, 76, 2))) for _ in range(KS)]
+        dy = [tuple(int(v) for v in (np.array(agent) + rng.randint(-75, 76, 2))) for _ in range(KD)]
+        if i == 0:
+            agent = (0, 0)                      # the padding fills three quarters of the patch
+        if i == 1:
+            agent = (500, 500)
+        if i == 2:
+            st[0] = (agent[0] + 10, agent[1]); dy[0] = (agent[0] + 20, agent[1] + 5)   # overlapping discs: draw order
+            goal = (agent[0] - 12, agent[1] + 9)
+        if i == 3:
+            agent = (250, 3); st[1] = (260, -15); dy[1] = (230, -30)                   # obstacles outside the world
+        agents.append(agent); goals.append(goal); stat.append(st); dyn.append(dy)
+        span = 50
+        frame = P.codes_to_rgb(P.render_frame(agent, goal, st, dy))
+        padded = np.pad(frame, ((span, span), (span, span), (0, 0)), mode="constant", constant_values=255)   # :137
+        ax, ay = agent[0] + span, frame.shape[0] - agent[1] + span                                           # :133-135
+        patch = padded[max(ay - span, 0):ay + span, ax - span:ax + span, :]                                  # :144
+        full = np.full((100, 100, 3), 255, np.uint8)       # (agent_y = 500: the slice starts above the padded frame)
+        full[100 - patch.shape[0]:, :patch.shape[1]] = patch
+        img = Image.fromarray(full, "RGB")
+        out_c.append(np.asarray(img.resize((40, 40), Image.BICUBIC)).transpose(2, 0, 1))
+        out_l.append(np.asarray(img.resize((40, 40), Image.BILINEAR)).transpose(2, 0, 1))
+    import PIL
+    return dict(agent=np.array(agents, np.float64), goal=np.array(goals, np.float64), stat=np.array(stat, np.float64),
+                dyn=np.array(dyn, np.float64), bicubic=np.array(out_c, np.uint8), bilinear=np.array(out_l, np.uint8),
+                meta=json.dumps(dict(KS=KS, KD=KD, n=len(agents), pillow=PIL.__version__,
+                made_by="oracle/gen_golden.py: oracle/patches.py frame + Pillow resize (see the module header)")))
+
+
 def pathlog_kat():
     """The head of the shipped demonstration log (examples/State_info_trail_no2 + Trial_no_2, Python 2 pickles) and
     the labels examples/train_supervise.py:43-59 derives from its actions (restated here: that script is Python 2
@@ -669,6 +712,7 @@ def main(argv):
         "pathlog_kat": lambda: pathlog_kat(),
         "rollout_pygame": lambda: rollout_pygame(9, 12, 200, 21, g0=40),
         "reset_fixed_kat": lambda: reset_fixed_kat(),
+        "patches_kat": lambda: patches_kats(),
     }
     only = set(argv[1:])
     for name, fn in jobs.items():
