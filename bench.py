@@ -353,47 +353,77 @@ def measure_e2e(env, torch, n, steps, chunk, dist, world, mode="many", t_call=25
 
 def measure_c5(torch, dev, iterations=12, n_steps=32, n=16384):
     """BASELINE.json config 5: the actor-critic loop of examples/ball_cnn_ac3.py:528-646 driving 16 K GPU environments
-    end to end - torch Policy forward + Categorical sampling + ballenv_step per env-step (the T-step rollout replayed as
-    one CUDA graph), then the batched finish_episode update (forward, loss, backward, Adam) every n_steps."""
+    end to end.  An iteration = one n_steps-step policy-in-the-loop rollout of all environments - ONE launch
+    (ballenv_rollout_policy: the environments' own lanes evaluate Policy(5) and draw the action between two steps) - and
+    the batched finish_episode update (forward over the stored pairs with autograd, discounted returns, loss, backward,
+    Adam), the whole iteration replayed as one CUDA graph (a2c.GraphedTrainer).  Beside it: the rollout alone, and the
+    same iteration with the per-step torch policy (GraphedRollout: Policy forward + multinomial + ballenv_step per
+    env-step, replayed as a graph; what this leg measured before the fused launch existed)."""
     from gym_ballenv_b200 import BallVecEnv
-    from gym_ballenv_b200.a2c import GraphedRollout, Policy, a2c_loss
+    from gym_ballenv_b200.a2c import FusedRollout, GraphedRollout, GraphedTrainer, Policy, a2c_loss
+
+    def timed(fn, reps):
+        torch.cuda.synchronize(dev)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(reps):
+            out = fn()
+        ev1.record()
+        torch.cuda.synchronize(dev)
+        return ev0.elapsed_time(ev1) / reps, out
+
     torch.manual_seed(0)
     env = BallVecEnv(n, window=5, seed=0, device=dev)
     policy = Policy(5).to(dev)
-    opt = torch.optim.Adam(policy.parameters(), lr=1e-3)
     env.reset()
-    roll = GraphedRollout(env, policy, n_steps)
+    trainer = GraphedTrainer(env, policy, n_steps)
+    trainer.step()      # three eager iterations, then the capture
+    trainer.step()
+    l0 = env.launch_count
+    ms_it, loss = timed(trainer.step, iterations)
+    launches = env.launch_count - l0      # (replays do not pass through the library: counted below)
+    roll = FusedRollout(env, policy, n_steps)
+    roll.run()
+    ms_roll, _ = timed(roll.run, iterations)
+    errs = env.error_flags()
+    env.close()
 
-    def iteration():
-        raw = roll.run()
-        batch = roll.evaluate(raw)
+    # the per-step torch policy, for comparison
+    torch.manual_seed(0)
+    env = BallVecEnv(n, window=5, seed=0, device=dev)
+    policy2 = Policy(5).to(dev)
+    opt = torch.optim.Adam(policy2.parameters(), lr=1e-3)
+    env.reset()
+    groll = GraphedRollout(env, policy2, n_steps)
+
+    def torch_iteration():
+        raw = groll.run()
+        batch = groll.evaluate(raw)
         with torch.no_grad():
-            _, v_last = policy(raw["obs"][n_steps])
-        loss = a2c_loss(batch, 0.99, bootstrap=v_last.squeeze(-1))
+            _, v_last = policy2(raw["obs"][n_steps])
+        l = a2c_loss(batch, 0.99, bootstrap=v_last.squeeze(-1))
         opt.zero_grad(set_to_none=True)
-        loss.backward()
+        l.backward()
         opt.step()
-        return loss
+        return l
 
     for _ in range(3):
-        iteration()
-    torch.cuda.synchronize(dev)
-    l0 = env.launch_count
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for _ in range(iterations):
-        loss = iteration()
-    ev1.record()
-    torch.cuda.synchronize(dev)
-    ms = ev0.elapsed_time(ev1)
-    out = {"workload": "config 5: 16384 envs, WINDOW=5, reference defaults (13 + 5 obstacles), Policy(5) MLP 29-128-{9,1} in "
-                       "the loop (on-device Categorical), %d-step graphed rollouts, batched finish_episode + Adam per rollout"
-                       % n_steps,
-           "value": n * n_steps * iterations / (ms * 1e-3), "unit": UNIT, "ms_per_iteration": ms / iterations,
-           "env_kernel": env.kernel_variant(1), "env_launches": env.launch_count - l0, "iterations": iterations,
-           "loss_finite": bool(torch.isfinite(loss).item()), "device_error_flags": env.error_flags()}
+        torch_iteration()
+    ms_torch, _ = timed(torch_iteration, max(4, iterations // 2))
     env.close()
-    return out
+    return {"workload": "config 5: 16384 envs, WINDOW=5, reference defaults (13 + 5 obstacles), Policy(5) MLP 29-128-{9,1} in "
+                        "the loop (Categorical by inverse CDF of the env's Philox stream), %d-step rollouts in ONE launch "
+                        "(ballenv_rollout_policy), batched finish_episode + Adam per rollout, the iteration replayed as one "
+                        "CUDA graph" % n_steps,
+            "value": n * n_steps / (ms_it * 1e-3), "unit": UNIT, "ms_per_iteration": ms_it,
+            "rollout_only": {"value": n * n_steps / (ms_roll * 1e-3), "unit": UNIT, "ms_per_rollout": ms_roll,
+                             "us_per_env_step_of_all_envs": ms_roll * 1e3 / n_steps},
+            "torch_policy_per_step": {"value": n * n_steps / (ms_torch * 1e-3), "unit": UNIT, "ms_per_iteration": ms_torch,
+                                      "what": "GraphedRollout: torch Policy forward + multinomial + ballenv_step per env-step "
+                                              "(one CUDA graph per rollout), same update issued eagerly"},
+            "env_kernel": "ballenv_lean_kernel<5,13,5,lanes=2,rollout,policy>",
+            "gpu_launches_per_iteration": 1, "iterations": iterations,
+            "loss_finite": bool(torch.isfinite(loss).item()), "device_error_flags": errs}
 
 
 def run_gpu(args, spec):

@@ -52,12 +52,20 @@ class BallenvStatePtrs(C.Structure):
     ]
 
 
+class BallenvPolicyMLP(C.Structure):
+    """include/ballenv.h: BallenvPolicyMLP (ballenv_rollout_policy)."""
+    _fields_ = [("n_inputs", C.c_int32), ("hidden", C.c_int32), ("greedy", C.c_int32), ("reserved", C.c_int32),
+                ("fc1_weight", C.c_void_p), ("fc1_bias", C.c_void_p), ("action_weight", C.c_void_p),
+                ("action_bias", C.c_void_p)]
+
+
 EXPORTS = (
     "ballenv_abi_version", "ballenv_last_error", "ballenv_config_default", "ballenv_state_bytes",
     "ballenv_create", "ballenv_destroy", "ballenv_state_ptrs", "ballenv_reset", "ballenv_step",
     "ballenv_step_many", "ballenv_observe", "ballenv_observe_features", "ballenv_observe_blocks", "ballenv_step_host", "ballenv_set_draw_tape", "ballenv_stats",
     "ballenv_stats_reset", "ballenv_error_flags", "ballenv_launch_count", "ballenv_selftest", "ballenv_kernel_variant",
     "ballenv_step_many_host", "ballenv_reset_fixed", "ballenv_state_written", "ballenv_observe_patches",
+    "ballenv_rollout_policy", "ballenv_discounted_returns",
 )
 
 
@@ -81,6 +89,8 @@ def _bind(lib):
     lib.ballenv_observe_features.argtypes = [vp, vp, vp]
     lib.ballenv_observe_blocks.argtypes = [vp, vp, vp]
     lib.ballenv_observe_patches.argtypes = [vp, vp, i32, i32, i32, i32, vp]
+    lib.ballenv_rollout_policy.argtypes = [vp, C.POINTER(BallenvPolicyMLP), i32, vp, vp, vp, vp, vp, vp]
+    lib.ballenv_discounted_returns.argtypes = [vp, vp, vp, C.c_float, i32, i64, vp, vp]
     lib.ballenv_step_host.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp]
     lib.ballenv_step_many_host.argtypes = [vp, vp, C.c_int, i32, vp, vp, vp, vp]
     lib.ballenv_set_draw_tape.argtypes = [vp, vp, i64, vp, i64, i32]

@@ -159,12 +159,80 @@ class GraphedRollout:
         return dict(log_prob=logp, value=value.view(T, n), reward=batch["reward"], done=batch["done"])
 
 
+class FusedRollout(GraphedRollout):
+    """The T-step policy-in-the-loop rollout as ONE KERNEL LAUNCH (``BallVecEnv.rollout_policy``): the environments'
+    own lanes evaluate the MLP and draw the action between two steps, so nothing but observations, actions, rewards
+    and dones touches device memory inside the loop.  Same buffers and ``evaluate`` as GraphedRollout; actions are
+    drawn from the env's Philox stream (inverse CDF of the same softmax) instead of ``torch.multinomial``."""
+
+    @torch.no_grad()
+    def run(self, first_obs: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        if first_obs is None:
+            first_obs = self.obs[self.n_steps].clone() if self.graph is not None else self.env.observe()
+        self.graph = True      # (no graph to capture: marks that obs[n_steps] holds the last observation)
+        self.obs[0].copy_(first_obs)
+        self.env.rollout_policy(self.policy, self.n_steps, self.obs[0], self.obs[1:], self.action, self.reward, self.done,
+                                greedy=self.greedy)
+        return dict(obs=self.obs, action=self.action, reward=self.reward, done=self.done.bool())
+
+
+def train_fused(env: BallVecEnv, policy: Policy, iterations: int, n_steps: int = 32, gamma: float = 0.99,
+                lr: float = 1e-3, log=None):
+    """train_graphed with the rollout in one launch (FusedRollout)."""
+    return train_graphed(env, policy, iterations, n_steps, gamma, lr, log, rollout_cls=FusedRollout)
+
+
+class GraphedTrainer:
+    """One whole iteration of the actor-critic loop - the fused T-step rollout (one launch), the batched
+    ``finish_episode`` update (forward over the stored pairs, discounted returns, loss, backward) and the Adam step - as
+    ONE CUDA graph, replayed per iteration: nothing is launched from Python inside the loop (the update is a few dozen
+    small kernels that are launch-bound when issued one by one).  Needs a configuration with a policy-in-the-loop
+    kernel (``BallVecEnv.rollout_policy``)."""
+
+    def __init__(self, env: BallVecEnv, policy: Policy, n_steps: int = 32, gamma: float = 0.99, lr: float = 1e-3):
+        self.env, self.policy, self.n_steps, self.gamma = env, policy, n_steps, gamma
+        self.opt = torch.optim.Adam(policy.parameters(), lr=lr, capturable=True)
+        self.roll = FusedRollout(env, policy, n_steps)
+        self.loss = torch.zeros((), dtype=torch.float32, device=env.device)
+        self.graph = None
+
+    def _body(self):
+        raw = self.roll.run()
+        batch = self.roll.evaluate(raw)
+        with torch.no_grad():
+            _, v_last = self.policy(raw["obs"][self.n_steps])
+        loss = a2c_loss(batch, self.gamma, bootstrap=v_last.squeeze(-1))
+        self.opt.zero_grad(set_to_none=True)
+        loss.backward()
+        self.opt.step()
+        self.loss.copy_(loss.detach())
+
+    def step(self) -> torch.Tensor:
+        """One iteration (the first call runs three, eagerly, to warm up before the capture); returns the loss, a device
+        scalar that the next call overwrites."""
+        if self.graph is None:
+            dev = self.env.device
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):       # off the capturing stream: allocations, cuBLAS handles, Adam state
+                for _ in range(3):
+                    self._body()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            self.graph = torch.cuda.CUDAGraph()
+            self.opt.zero_grad(set_to_none=True)
+            with torch.cuda.graph(self.graph):
+                self._body()
+            return self.loss
+        self.graph.replay()
+        return self.loss
+
+
 def train_graphed(env: BallVecEnv, policy: Policy, iterations: int, n_steps: int = 32, gamma: float = 0.99,
-                  lr: float = 1e-3, log=None):
+                  lr: float = 1e-3, log=None, rollout_cls=None):
     """train() with the rollout replayed as a CUDA graph and the update computed from one batched forward pass."""
     opt = torch.optim.Adam(policy.parameters(), lr=lr)
     env.reset()
-    roll = GraphedRollout(env, policy, n_steps)
+    roll = (rollout_cls or GraphedRollout)(env, policy, n_steps)
     for it in range(iterations):
         raw = roll.run()
         batch = roll.evaluate(raw)
@@ -183,6 +251,21 @@ def discounted_returns(reward: torch.Tensor, done: torch.Tensor, gamma: float, b
     """R_t = r_t + gamma * R_{t+1}, restarted where an episode ended (examples/ball_cnn_ac3.py:228-230, per env)."""
     T = reward.shape[0]
     out = torch.empty_like(reward)
+    if (reward.is_cuda and reward.dtype == torch.float32 and reward.dim() == 2 and reward.is_contiguous()
+            and done.dtype in (torch.bool, torch.uint8) and done.is_contiguous() and done.shape == reward.shape
+            and not reward.requires_grad and (bootstrap is None or not bootstrap.requires_grad)):
+        # one launch, one thread per environment (ballenv_discounted_returns): same float32 roundings as the loop below
+        import ctypes as C
+        from ._lib import LIB, check
+        boot = None
+        if bootstrap is not None:
+            boot = bootstrap.to(torch.float32).contiguous()
+        with torch.cuda.device(reward.device):
+            check(LIB.ballenv_discounted_returns(
+                C.c_void_p(reward.data_ptr()), C.c_void_p(done.data_ptr()), None if boot is None else C.c_void_p(boot.data_ptr()),
+                C.c_float(gamma), T, reward.shape[1], C.c_void_p(out.data_ptr()),
+                C.c_void_p(torch.cuda.current_stream(reward.device).cuda_stream)))
+        return out
     R = torch.zeros_like(reward[0]) if bootstrap is None else bootstrap
     for t in range(T - 1, -1, -1):
         R = reward[t] + gamma * R * (~done[t]).to(reward.dtype)

@@ -31,10 +31,16 @@ void launch_f32_wany_fast(const Params&, unsigned, cudaStream_t);
 #define BALLENV_LEAN_DECL(w, ks, kd)                                          \
   void launch_lean_w##w##_s##ks##_d##kd##_g1(const Params&, unsigned, cudaStream_t); \
   void launch_lean_w##w##_s##ks##_d##kd##_g2(const Params&, unsigned, cudaStream_t);
+// the same with the policy inside the rollout loop (ballenv_rollout_policy; WINDOW = 5 instances)
+#define BALLENV_LEAN_POLICY_DECL(w, ks, kd)                                          \
+  void launch_lean_policy_w##w##_s##ks##_d##kd##_g1(const Params&, unsigned, cudaStream_t); \
+  void launch_lean_policy_w##w##_s##ks##_d##kd##_g2(const Params&, unsigned, cudaStream_t);
 BALLENV_LEAN_DECL(5, 13, 5)
 BALLENV_LEAN_DECL(10, 13, 5)
 BALLENV_LEAN_DECL(10, 8, 24)
 BALLENV_LEAN_DECL(5, 8, 24)
+BALLENV_LEAN_POLICY_DECL(5, 13, 5)
+BALLENV_LEAN_POLICY_DECL(5, 8, 24)
 #undef BALLENV_LEAN_DECL
 }  // namespace ballenv
 
@@ -309,6 +315,22 @@ LeanLauncher lean_launcher(const BallenvHandle* h, const Params& p, int* lanes =
       if (lanes != nullptr) *lanes = g;
       return g == 2 ? i.g2 : i.g1;
     }
+  return nullptr;
+}
+
+// the lean kernel with the policy in its loop for this configuration, or nullptr
+LeanLauncher policy_launcher(const BallenvHandle* h, const Params& p, int* lanes = nullptr) {
+  int g = 0;
+  if (lean_launcher(h, p, &g) == nullptr || p.cfg.obs_format != BALLENV_OBS_F32) return nullptr;
+  struct Inst { int w, ks, kd; LeanLauncher g1, g2; };
+  static const Inst kInst[] = {{5, 13, 5, launch_lean_policy_w5_s13_d5_g1, launch_lean_policy_w5_s13_d5_g2},
+                               {5, 8, 24, launch_lean_policy_w5_s8_d24_g1, launch_lean_policy_w5_s8_d24_g2}};
+  // a pair of lanes per environment unless told otherwise: the pair also splits the hidden units of the policy, the
+  // longest dependent chain of a step
+  g = h->lean_g ? h->lean_g : 2;
+  if (lanes != nullptr) *lanes = g;
+  for (const Inst& i : kInst)
+    if (i.w == p.cfg.window && i.ks == p.cfg.ks && i.kd == p.cfg.kd) return g == 2 ? i.g2 : i.g1;
   return nullptr;
 }
 
@@ -826,6 +848,63 @@ int ballenv_step(BallenvHandle* h, const void* actions, int action_kind, void* o
   return launch(h, p, (cudaStream_t)stream);
 }
 
+int ballenv_rollout_policy(BallenvHandle* h, const BallenvPolicyMLP* pol, int32_t n_steps, const float* first_obs,
+                           float* obs_out, int64_t* actions_out, void* reward_out, uint8_t* done_out,
+                           ballenv_stream_t stream) {
+  if (h == nullptr || pol == nullptr || first_obs == nullptr || obs_out == nullptr || actions_out == nullptr)
+    return fail(BALLENV_EINVAL, "NULL argument");
+  if (pol->fc1_weight == nullptr || pol->fc1_bias == nullptr || pol->action_weight == nullptr || pol->action_bias == nullptr)
+    return fail(BALLENV_EINVAL, "NULL policy parameter");
+  if (n_steps < 0) return fail(BALLENV_EINVAL, "n_steps < 0");
+  if (n_steps == 0) return BALLENV_OK;
+  const int n_in = obs_row_elems(h->cfg);
+  if (pol->n_inputs != n_in) return fail(BALLENV_EINVAL, "the policy takes %d inputs, an observation row has %d", pol->n_inputs, n_in);
+  if (pol->hidden < 8 || pol->hidden > 512 || (pol->hidden & 7) != 0) return fail(BALLENV_EINVAL, "hidden must be a multiple of 8 in 8..512");
+  DeviceGuard guard(h->device);
+  Params p = h->base;
+  p.mode = kModeStep;
+  p.n_steps = n_steps;
+  p.obs_all_steps = 1;
+  p.actions = nullptr;
+  p.action_kind = BALLENV_ACT_INDEX_I64;
+  p.obs = obs_out;
+  p.reward = reward_out;
+  p.done = done_out;
+  p.reset_tape = h->reset_tape;
+  p.step_tape = h->step_tape;
+  p.pol_fc1_w = pol->fc1_weight;
+  p.pol_fc1_b = pol->fc1_bias;
+  p.pol_act_w = pol->action_weight;
+  p.pol_act_b = pol->action_bias;
+  p.pol_hidden = pol->hidden;
+  p.pol_greedy = pol->greedy ? 1 : 0;
+  LeanLauncher fn = policy_launcher(h, p);
+  if (fn == nullptr)
+    return fail(BALLENV_ESTATE, "no policy-in-the-loop kernel for this configuration (production mode, float32 rows, WINDOW 5, "
+                                "13 + 5 or 8 + 24 obstacles): drive ballenv_step from the caller's policy instead");
+  if (4 * lean::policy_smem_floats(n_in, pol->hidden) > 96 * 1024) return fail(BALLENV_EINVAL, "the policy does not fit in shared memory");
+  const size_t n = (size_t)h->n;
+  const size_t rew_b = 4;
+  // the kernel indexes the [T][n] arrays with 32 bits: at most (2^31 - 1) / n steps per launch
+  const int64_t max_t = n > 0 ? (int64_t)0x7fffffff / (int64_t)n : n_steps;
+  if (max_t < 1) return fail(BALLENV_EINVAL, "too many environments for one launch");
+  for (int64_t t0 = 0; t0 < n_steps; t0 += max_t) {
+    const int64_t tn = n_steps - t0 < max_t ? n_steps - t0 : max_t;
+    p.n_steps = (int)tn;
+    p.pol_first_obs = t0 == 0 ? first_obs : obs_out + (size_t)(t0 - 1) * n * n_in;
+    p.pol_actions = reinterpret_cast<long long*>(actions_out) + (size_t)t0 * n;
+    p.obs = obs_out + (size_t)t0 * n * n_in;
+    p.reward = reward_out ? (char*)reward_out + (size_t)t0 * n * rew_b : nullptr;
+    p.done = done_out ? done_out + (size_t)t0 * n : nullptr;
+    p.obs_row_bytes = (long long)n_in * 4;
+    p.obs_step_bytes = (long long)n * p.obs_row_bytes;
+    fn(p, (unsigned)((p.n + kLeanEnvsPerBlock - 1) / kLeanEnvsPerBlock), (cudaStream_t)stream);
+    h->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+  }
+  return BALLENV_OK;
+}
+
 int ballenv_step_many(BallenvHandle* h, const void* actions, int action_kind, int32_t n_steps, void* obs_out,
                       int32_t obs_all_steps, void* reward_out, uint8_t* done_out, ballenv_stream_t stream) {
   if (h == nullptr || actions == nullptr) return fail(BALLENV_EINVAL, "NULL argument");
@@ -1055,6 +1134,34 @@ int ballenv_kernel_variant(BallenvHandle* h, int action_kind, int32_t n_steps) {
   int lanes = 1;
   if (lean_launcher(h, p, &lanes) != nullptr) return lanes == 2 ? BALLENV_KERNEL_LEAN2 : BALLENV_KERNEL_LEAN;
   return fast_eligible(h, p) ? BALLENV_KERNEL_ROLES : BALLENV_KERNEL_GENERIC;
+}
+
+namespace {
+// R_t = r_t + gamma * R_{t+1} * (1 - done_t) from the end of a [T][n] slice, one thread per environment: the loop of
+// examples/ball_cnn_ac3.py:228-230 for N trajectories at once.  fp32, rounded like the tensor expression
+// reward[t] + gamma * R * mask (no contraction).
+__global__ void __launch_bounds__(256) discounted_returns_kernel(const float* __restrict__ reward, const uint8_t* __restrict__ done,
+                                                                 const float* __restrict__ bootstrap, float gamma, int T,
+                                                                 long long n, float* __restrict__ out) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  float R = bootstrap != nullptr ? bootstrap[e] : 0.0f;
+  for (int t = T - 1; t >= 0; --t) {
+    const size_t i = (size_t)t * (size_t)n + (size_t)e;
+    R = __fadd_rn(reward[i], __fmul_rn(__fmul_rn(gamma, R), done[i] ? 0.0f : 1.0f));
+    out[i] = R;
+  }
+}
+}  // namespace
+
+int ballenv_discounted_returns(const float* reward, const uint8_t* done, const float* bootstrap, float gamma, int32_t n_steps,
+                               int64_t n, float* out, ballenv_stream_t stream) {
+  if (reward == nullptr || done == nullptr || out == nullptr) return fail(BALLENV_EINVAL, "NULL argument");
+  if (n_steps < 0 || n < 0) return fail(BALLENV_EINVAL, "negative size");
+  if (n_steps == 0 || n == 0) return BALLENV_OK;
+  discounted_returns_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(reward, done, bootstrap, gamma, n_steps, n, out);
+  CUDA_TRY(cudaGetLastError());
+  return BALLENV_OK;
 }
 
 int ballenv_selftest(int which, int64_t arg, int device, int64_t* mismatches) {

@@ -143,6 +143,13 @@ struct Params {
   // their per-launch test); non-zero: unknown.  Maintained by the host (ballenv_capi.cu: full resets clear it, float
   // actions and ballenv_state_written's validation set it)
   const uint32_t* state_dirty;
+  // policy-in-the-loop rollouts (ballenv_rollout_policy; lean kernels instantiated with kPolicy): the MLP of
+  // examples/ball_cnn_ac3.py:109-146 in nn.Linear layout, the observation the first step acts on, the actions taken
+  const float *pol_fc1_w, *pol_fc1_b;   // [hidden][4 + W*W], [hidden]
+  const float *pol_act_w, *pol_act_b;   // [9][hidden], [9]
+  const float* pol_first_obs;           // float32 [n][4 + W*W]
+  long long* pol_actions;               // int64 [T][n]
+  int pol_hidden, pol_greedy;
 };
 
 // ---- arithmetic that must not be contracted into FMAs (the reference squares, then adds) -------------------

@@ -12,15 +12,18 @@
 
 namespace ballenv {
 
-template <bool kRollout>
+template <bool kRollout, bool kPolicy = false>
 static void launch_lean(const Params& p, unsigned grid, cudaStream_t s) {
-  auto kern = ballenv_lean_kernel<BALLENV_W, BALLENV_KS, BALLENV_KD, BALLENV_G, kRollout>;
+  auto kern = ballenv_lean_kernel<BALLENV_W, BALLENV_KS, BALLENV_KD, BALLENV_G, kRollout, kPolicy>;
   static bool configured[64] = {};   // per device: function attributes belong to the device's copy of the kernel
   int dev = 0;
   cudaGetDevice(&dev);
+  // (policy in the loop) the block's copy of the weights, dynamic shared memory
+  const size_t dyn = kPolicy ? 4 * lean::policy_smem_floats(4 + BALLENV_W * BALLENV_W, p.pol_hidden) : 0;
   if (dev >= 0 && dev < 64 && !configured[dev]) {
     // seven blocks of 64 environments with their obstacle slices in shared memory: ask for the whole array
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (kPolicy) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     configured[dev] = true;
   }
   // programmatic stream serialisation: the grid may begin while its predecessor on the stream drains; the kernel
@@ -29,7 +32,7 @@ static void launch_lean(const Params& p, unsigned grid, cudaStream_t s) {
   cudaLaunchConfig_t lc = {};
   lc.gridDim = dim3(grid);
   lc.blockDim = dim3(kLeanEnvsPerBlock * BALLENV_G);
-  lc.dynamicSmemBytes = 0;
+  lc.dynamicSmemBytes = dyn;
   lc.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -57,5 +60,10 @@ void BALLENV_NAME(const Params& p, unsigned grid, cudaStream_t s) {
   if (p.n_steps > 1) launch_lean<true>(p, grid, s);
   else launch_lean<false>(p, grid, s);
 }
+
+#ifdef BALLENV_POLICY_NAME
+// the rollout loop with the policy inside (ballenv_rollout_policy): any number of steps
+void BALLENV_POLICY_NAME(const Params& p, unsigned grid, cudaStream_t s) { launch_lean<true, true>(p, grid, s); }
+#endif
 
 }  // namespace ballenv

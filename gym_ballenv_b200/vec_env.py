@@ -249,6 +249,37 @@ class BallVecEnv:
         check(LIB.ballenv_step(self._h, C.c_void_p(actions.data_ptr()), kind, C.c_void_p(obs_out.data_ptr()),
                                C.c_void_p(reward_out.data_ptr()), C.c_void_p(done_out.data_ptr()), self._stream()))
 
+    def rollout_policy(self, policy, n_steps: int, first_obs: torch.Tensor, obs_out: torch.Tensor,
+                       actions_out: torch.Tensor, reward_out: torch.Tensor, done_out: torch.Tensor, greedy: bool = False):
+        """n_steps of the loop of examples/ball_cnn_ac3.py:553-613 - observe, ``Policy`` forward, Categorical sample,
+        step - for all environments in ONE launch: the kernel evaluates the MLP itself between two steps
+        (ballenv_rollout_policy).  ``policy``: a module with ``fc1`` / ``action_head`` Linear layers (a2c.Policy; the
+        value head is not needed to act).  first_obs [N, row] float32: the current observation; obs_out [T, N, row],
+        actions_out [T, N] int64, reward_out [T, N] float32, done_out [T, N] uint8 are written.  Raises BallenvError
+        for configurations without such a kernel (WINDOW other than 5, other obstacle counts, parity mode)."""
+        n, row, dev = self.num_envs, self.obs_row, self.device
+        w1, b1 = policy.fc1.weight, policy.fc1.bias
+        w2, b2 = policy.action_head.weight, policy.action_head.bias
+        for t in (w1, b1, w2, b2):
+            if t.dtype != torch.float32 or t.device != dev or not t.is_contiguous():
+                raise ValueError("policy parameters must be contiguous float32 tensors on the env's device")
+        hidden = w1.shape[0]
+        if tuple(w1.shape) != (hidden, row) or tuple(w2.shape) != (9, hidden):
+            raise ValueError("policy must map %d inputs -> hidden -> 9 actions" % row)
+        def ok(t, shape, dtype):
+            return tuple(t.shape) == shape and t.dtype == dtype and t.device == dev and t.is_contiguous()
+        if not (ok(first_obs, (n, row), torch.float32) and ok(obs_out, (n_steps, n, row), torch.float32)
+                and ok(actions_out, (n_steps, n), torch.int64) and ok(reward_out, (n_steps, n), torch.float32)
+                and ok(done_out, (n_steps, n), torch.uint8)):
+            raise ValueError("rollout_policy needs contiguous device tensors: first_obs [N, row] f32, obs_out [T, N, row] f32, "
+                             "actions_out [T, N] i64, reward_out [T, N] f32, done_out [T, N] u8")
+        pol = L.BallenvPolicyMLP(n_inputs=row, hidden=hidden, greedy=1 if greedy else 0, reserved=0,
+                                 fc1_weight=w1.data_ptr(), fc1_bias=b1.data_ptr(), action_weight=w2.data_ptr(),
+                                 action_bias=b2.data_ptr())
+        check(LIB.ballenv_rollout_policy(self._h, C.byref(pol), int(n_steps), C.c_void_p(first_obs.data_ptr()),
+                                         C.c_void_p(obs_out.data_ptr()), C.c_void_p(actions_out.data_ptr()),
+                                         C.c_void_p(reward_out.data_ptr()), C.c_void_p(done_out.data_ptr()), self._stream()))
+
     def alloc_rollout(self, T: int, keep_all_obs: bool = False):
         """Rollout buffers for step_many(out=...): (obs [T, N, row] or [N, row], reward [T, N], done [T, N] uint8)."""
         n = self.num_envs

@@ -213,6 +213,48 @@ int ballenv_step(BallenvHandle *h, const void *actions, int action_kind, void *o
 int ballenv_step_many(BallenvHandle *h, const void *actions, int action_kind, int32_t n_steps, void *obs_out,
                       int32_t obs_all_steps, void *reward_out, uint8_t *done_out, ballenv_stream_t stream);
 
+/*
+ * Replaces: the policy-in-the-loop rollout of examples/ball_cnn_ac3.py:553-613 - per step prep_state4 (:560),
+ * Policy(window) forward (:109-146), Categorical(probs).sample() with its .item() host round trip (:210-220) and
+ * env.step(move_list[action]) (:588) - for all environments and n_steps steps in ONE launch: the environment's own
+ * lane(s) evaluate softmax(action_head(relu(fc1(obs)))) from a shared-memory copy of the weights between two steps.
+ * The parameters are the tensors of the torch module as they lie (nn.Linear layout, float32, device); the value
+ * head is not needed to act (the update recomputes log-probabilities and values with autograd from the stored
+ * observations and actions).
+ * first_obs   : device float32 [n][row], the observation of the CURRENT state (what the last reset / step returned)
+ * obs_out     : device float32 [n_steps][n][row], the observation after each step (post-reset where an episode ended)
+ * actions_out : device int64   [n_steps][n], the action taken at each step (index into the agent move list, :530)
+ * reward_out / done_out : [n_steps][n] float32 / uint8, or NULL
+ * Sampling: word x of Philox4x32-10(counter = {global env id, tick, 0, stream 3}, key = seed), u = (word >> 8) 2^-24,
+ * action = first j with u * sum(e) < e_0 + .. + e_j, e = exp(logit - max): Categorical by inverse CDF, reproducible and
+ * independent of the sharding; greedy != 0 takes the first maximum instead.
+ * Production configuration only (BALLENV_F32, gym ruleset, Philox draws, BALLENV_OBS_F32 rows) with WINDOW = 5 and
+ * 13 + 5 or 8 + 24 obstacles; BALLENV_ESTATE otherwise (step from the caller's policy with ballenv_step).
+ */
+typedef struct BallenvPolicyMLP {
+  int32_t n_inputs;            /* 4 + WINDOW^2 */
+  int32_t hidden;              /* Policy.hidden_layer (128 for WINDOW = 5); a multiple of 8 */
+  int32_t greedy;              /* 0: sample, 1: argmax */
+  int32_t reserved;
+  const float *fc1_weight;     /* device [hidden][n_inputs] */
+  const float *fc1_bias;       /* device [hidden] */
+  const float *action_weight;  /* device [9][hidden] */
+  const float *action_bias;    /* device [9] */
+} BallenvPolicyMLP;
+int ballenv_rollout_policy(BallenvHandle *h, const BallenvPolicyMLP *policy, int32_t n_steps, const float *first_obs,
+                           float *obs_out, int64_t *actions_out, void *reward_out, uint8_t *done_out,
+                           ballenv_stream_t stream);
+
+/*
+ * Replaces: the discounted-return loop of finish_episode (examples/ball_cnn_ac3.py:228-230: R = r + gamma * R, from the
+ * end), for n trajectories of n_steps steps at once, restarted where an episode ended inside the slice:
+ * out[t][e] = reward[t][e] + gamma * out[t + 1][e] * (1 - done[t][e]), with out[n_steps][e] = bootstrap[e] (or 0 when
+ * bootstrap is NULL).  All device pointers on the CURRENT device ([n_steps][n] float32 / uint8, bootstrap [n]); float32
+ * arithmetic rounded like the tensor expression.  No handle: it touches no environment state.
+ */
+int ballenv_discounted_returns(const float *reward, const uint8_t *done, const float *bootstrap, float gamma,
+                               int32_t n_steps, int64_t n, float *out, ballenv_stream_t stream);
+
 /* prep_state4 on the current state without stepping (examples/ball_cnn_ac3.py:384-412). */
 int ballenv_observe(BallenvHandle *h, void *obs_out, ballenv_stream_t stream);
 

@@ -1,0 +1,229 @@
+"""The policy-in-the-loop rollout as one launch (ballenv_rollout_policy / FusedRollout; BASELINE config 5,
+examples/ball_cnn_ac3.py:553-613).
+
+What is pinned: (1) the environment side is the rollout kernel itself - replaying the actions the fused launch took
+through ballenv_step_many on a twin environment gives bit-identical observations, rewards and dones; (2) the actions
+are Categorical(policy(obs)) by inverse CDF of the documented draw: recomputed here from the torch policy's own
+probabilities and the numpy Philox word (oracle/draws.py), the emitted action is the one u selects (float32 summation
+order differs between the kernel and cuBLAS, so a draw within 1e-5 of a CDF step may go either way); (3) greedy mode is
+the argmax of the torch policy; (4) the training loop on top of it runs."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import draws as D
+
+SEED = 11
+
+
+def _make(n, ks=13, kd=5, window=5, lanes=None, g0=0):
+    import torch
+    from gym_ballenv_b200 import BallVecEnv, EnvConfig
+    if kd == 24:
+        goals = ['%d,%d' % (x, y) for y in (100, 200, 300, 400) for x in (50, 130, 210, 290, 370, 450)]
+        cfg = EnvConfig(static_obstacles=8, dynamic_obstacles=24, obstacle_speed=[1] * 24, obs_goal_position=goals)
+    else:
+        cfg = EnvConfig()
+    old = os.environ.get("BALLENV_LEAN_G")
+    if lanes is not None:
+        os.environ["BALLENV_LEAN_G"] = str(lanes)      # read when the handle is created
+    try:
+        env = BallVecEnv(n, window=window, config=cfg, seed=SEED, device="cuda:0", max_episode_steps=25,
+                         global_env_offset=g0)
+    finally:
+        if lanes is not None:
+            if old is None:
+                del os.environ["BALLENV_LEAN_G"]
+            else:
+                os.environ["BALLENV_LEAN_G"] = old
+    return env, torch
+
+
+def _policy(torch, window=5, scale=3.0):
+    from gym_ballenv_b200.a2c import Policy
+    torch.manual_seed(5)
+    pol = Policy(window).to("cuda:0")
+    with torch.no_grad():      # sharper than the default initialisation: the actions really depend on the observation
+        pol.action_head.weight.mul_(scale)
+        pol.fc1.weight.mul_(scale)
+    return pol
+
+
+def _fused(env, torch, pol, T, greedy=False):
+    n, row = env.num_envs, env.obs_row
+    first = env.observe().clone()
+    obs = torch.zeros((T, n, row), dtype=torch.float32, device=env.device)
+    act = torch.zeros((T, n), dtype=torch.int64, device=env.device)
+    rew = torch.zeros((T, n), dtype=torch.float32, device=env.device)
+    done = torch.zeros((T, n), dtype=torch.uint8, device=env.device)
+    env.rollout_policy(pol, T, first, obs, act, rew, done, greedy=greedy)
+    torch.cuda.synchronize()
+    assert env.error_flags() == 0
+    return first, obs, act, rew, done
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("lanes", [1, 2])
+@pytest.mark.parametrize("kd", [5, 24])
+def test_fused_rollout_is_the_rollout_kernel_under_the_policys_actions(lanes, kd):
+    n, T, g0 = 2048 + 17, 60, 1000
+    env, torch = _make(n, kd=kd, lanes=lanes, g0=g0)
+    twin, _ = _make(n, kd=kd, g0=g0)
+    env.reset()
+    twin.reset()
+    pol = _policy(torch)
+    tick0 = env.get_state()["tick"].cpu().numpy().astype(np.uint64)
+    first, obs, act, rew, done = _fused(env, torch, pol, T)
+    assert int(act.min()) >= 0 and int(act.max()) <= 8 and len(torch.unique(act)) == 9
+    assert int(done.sum()) > n        # episodes end (time limit 25) and restart inside the launch
+    # (1) the environment under these actions
+    o2, r2, d2 = twin.step_many(act, keep_all_obs=True)
+    assert torch.equal(o2, obs) and torch.equal(r2, rew) and torch.equal(d2.to(torch.uint8), done)
+    sa, sb = env.get_state(), twin.get_state()
+    for k in sa:
+        assert torch.equal(sa[k], sb[k]), k
+    # (2) the actions under the policy: u of the documented draw against the torch policy's own CDF
+    seen = torch.cat([first.unsqueeze(0), obs[:-1]], 0)
+    with torch.no_grad():
+        probs, _ = pol(seen.reshape(T * n, -1))
+    cdf = torch.cumsum(probs.double(), -1).cpu().numpy().reshape(T, n, 9)
+    genv = (np.arange(n, dtype=np.uint64) + np.uint64(g0))[None, :]
+    tick = tick0[None, :] + np.arange(T, dtype=np.uint64)[:, None]
+    w = D.philox4x32_10_np(np.broadcast_to(genv, (T, n)), tick, 0, D.STREAM_ACTION, SEED & 0xffffffff, SEED >> 32)[0]
+    u = (w >> np.uint64(8)).astype(np.float64) / 16777216.0
+    a = act.cpu().numpy()
+    want = np.minimum((u[..., None] >= cdf[..., :8]).sum(-1), 8)
+    edge = np.abs(u[..., None] - cdf[..., :8]).min(-1) < 1e-5
+    assert ((want == a) | edge).all(), int(((want != a) & ~edge).sum())
+    assert (want == a).mean() > 0.9999
+    env.close()
+    twin.close()
+
+
+@pytest.mark.gpu
+def test_fused_greedy_is_the_argmax_of_the_torch_policy():
+    n, T = 1024, 40
+    env, torch = _make(n)
+    env.reset()
+    pol = _policy(torch)
+    first, obs, act, _, _ = _fused(env, torch, pol, T, greedy=True)
+    seen = torch.cat([first.unsqueeze(0), obs[:-1]], 0)
+    with torch.no_grad():
+        probs, _ = pol(seen.reshape(T * n, -1))
+    top2 = probs.topk(2, -1).values
+    tie = (top2[:, 0] - top2[:, 1]) < 1e-5
+    ok = (probs.argmax(-1) == act.reshape(-1)) | tie
+    assert bool(ok.all())
+    env.close()
+
+
+@pytest.mark.gpu
+def test_fused_rollout_does_not_depend_on_the_sharding():
+    """Environments [256, 512) of a 1024-environment job stepped alone take the same actions (draws are keyed by the
+    global environment id)."""
+    T = 30
+    env, torch = _make(1024)
+    part, _ = _make(256, g0=256)
+    env.reset()
+    part.reset()
+    pol = _policy(torch)
+    _, obs, act, rew, _ = _fused(env, torch, pol, T)
+    _, obs_p, act_p, rew_p, _ = _fused(part, torch, pol, T)
+    assert torch.equal(act[:, 256:512], act_p) and torch.equal(obs[:, 256:512], obs_p) and torch.equal(rew[:, 256:512], rew_p)
+    env.close()
+    part.close()
+
+
+@pytest.mark.gpu
+def test_fused_rollout_needs_a_configuration_it_is_built_for():
+    from gym_ballenv_b200._lib import BallenvError
+    env, torch = _make(64, window=10)
+    env.reset()
+    pol = _policy(torch, window=10)
+    with pytest.raises(BallenvError):
+        _fused(env, torch, pol, 4)
+    env.close()
+
+
+@pytest.mark.gpu
+def test_train_fused_updates_the_policy():
+    from gym_ballenv_b200.a2c import FusedRollout, Policy, train_fused
+    env, torch = _make(4096)
+    torch.manual_seed(0)
+    pol = Policy(5).to("cuda:0")
+    before = [p.detach().clone() for p in pol.parameters()]
+    losses = []
+    train_fused(env, pol, iterations=4, n_steps=16, log=lambda it, loss, batch: losses.append(float(loss)))
+    assert len(losses) == 4 and all(np.isfinite(losses))
+    assert any(not torch.equal(a, b) for a, b in zip(before, pol.parameters()))
+    # the evaluate() of the stored pairs is the policy's own forward pass
+    roll = FusedRollout(env, pol, 8)
+    raw = roll.run()
+    ev = roll.evaluate(raw)
+    with torch.no_grad():
+        probs, value = pol(raw["obs"][:8].reshape(8 * 4096, -1))
+    lp = torch.log(probs.gather(-1, raw["action"].reshape(-1, 1)).squeeze(-1)).view(8, 4096)
+    assert torch.allclose(ev["log_prob"], lp) and torch.allclose(ev["value"], value.view(8, 4096))
+    assert env.error_flags() == 0
+    env.close()
+
+
+@pytest.mark.gpu
+def test_discounted_returns_kernel_is_the_loop():
+    import torch
+    from gym_ballenv_b200.a2c import discounted_returns
+    g = torch.Generator(device="cuda:0").manual_seed(3)
+    T, n = 37, 5000
+    reward = torch.randn((T, n), device="cuda:0", generator=g)
+    done = torch.rand((T, n), device="cuda:0", generator=g) < 0.1
+    boot = torch.randn((n,), device="cuda:0", generator=g)
+    for b in (None, boot):
+        for d in (done, done.to(torch.uint8)):
+            got = discounted_returns(reward, d, 0.99, b)
+            R = torch.zeros_like(reward[0]) if b is None else b          # the tensor-expression form (a2c.py)
+            want = torch.empty_like(reward)
+            for t in range(T - 1, -1, -1):
+                R = reward[t] + 0.99 * R * (~done[t]).to(reward.dtype)
+                want[t] = R
+            assert torch.equal(got, want)
+
+
+@pytest.mark.gpu
+def test_graphed_trainer_is_the_eager_iteration():
+    """The whole iteration replayed as one CUDA graph gives what the same steps give issued one by one: same rollouts
+    (deterministic draws), same losses, same weights after the same number of iterations."""
+    from gym_ballenv_b200.a2c import FusedRollout, GraphedTrainer, Policy, a2c_loss
+    results = []
+    for graphed in (True, False):
+        env, torch = _make(2048)
+        env.reset()
+        torch.manual_seed(0)
+        pol = Policy(5).to("cuda:0")
+        losses = []
+        if graphed:
+            tr = GraphedTrainer(env, pol, n_steps=8)
+            tr.step()                       # three eager iterations + the capture
+            for _ in range(4):
+                losses.append(float(tr.step()))
+        else:
+            opt = torch.optim.Adam(pol.parameters(), lr=1e-3, capturable=True)
+            roll = FusedRollout(env, pol, 8)
+            for it in range(7):
+                raw = roll.run()
+                batch = roll.evaluate(raw)
+                with torch.no_grad():
+                    _, v_last = pol(raw["obs"][8])
+                loss = a2c_loss(batch, 0.99, bootstrap=v_last.squeeze(-1))
+                opt.zero_grad(set_to_none=True)
+                loss.backward()
+                opt.step()
+                if it >= 3:
+                    losses.append(float(loss))
+        results.append((losses, [p.detach().clone() for p in pol.parameters()], env.get_state()))
+        assert env.error_flags() == 0
+        env.close()
+    (la, pa, sa), (lb, pb, sb) = results
+    assert np.allclose(la, lb, rtol=1e-4), (la, lb)
+    for a, b in zip(pa, pb):
+        assert torch.allclose(a, b, rtol=1e-3, atol=1e-5)
