@@ -49,8 +49,8 @@ def _sources():
             name = "launch_lean_w%d_s%d_d%d_g%d" % (w, ks, kd, g)
             defs = ["-DBALLENV_W=%d" % w, "-DBALLENV_KS=%d" % ks, "-DBALLENV_KD=%d" % kd, "-DBALLENV_G=%d" % g,
                     "-DBALLENV_NAME=" + name]
-            if w == 5:   # the policy-in-the-loop rollout (ballenv_rollout_policy): the reference's W = 5 policies
-                defs.append("-DBALLENV_POLICY_NAME=" + name.replace("launch_lean_", "launch_lean_policy_"))
+            # the policy-in-the-loop rollout (ballenv_rollout_policy) of the same configuration
+            defs.append("-DBALLENV_POLICY_NAME=" + name.replace("launch_lean_", "launch_lean_policy_"))
             jobs.append((os.path.join(CSRC, "ballenv_lean_inst.cu"), os.path.join(OBJ, name + ".o"), defs))
     return deps, jobs
 

@@ -31,7 +31,7 @@ void launch_f32_wany_fast(const Params&, unsigned, cudaStream_t);
 #define BALLENV_LEAN_DECL(w, ks, kd)                                          \
   void launch_lean_w##w##_s##ks##_d##kd##_g1(const Params&, unsigned, cudaStream_t); \
   void launch_lean_w##w##_s##ks##_d##kd##_g2(const Params&, unsigned, cudaStream_t);
-// the same with the policy inside the rollout loop (ballenv_rollout_policy; WINDOW = 5 instances)
+// the same with the policy inside the rollout loop (ballenv_rollout_policy)
 #define BALLENV_LEAN_POLICY_DECL(w, ks, kd)                                          \
   void launch_lean_policy_w##w##_s##ks##_d##kd##_g1(const Params&, unsigned, cudaStream_t); \
   void launch_lean_policy_w##w##_s##ks##_d##kd##_g2(const Params&, unsigned, cudaStream_t);
@@ -40,6 +40,8 @@ BALLENV_LEAN_DECL(10, 13, 5)
 BALLENV_LEAN_DECL(10, 8, 24)
 BALLENV_LEAN_DECL(5, 8, 24)
 BALLENV_LEAN_POLICY_DECL(5, 13, 5)
+BALLENV_LEAN_POLICY_DECL(10, 13, 5)
+BALLENV_LEAN_POLICY_DECL(10, 8, 24)
 BALLENV_LEAN_POLICY_DECL(5, 8, 24)
 #undef BALLENV_LEAN_DECL
 }  // namespace ballenv
@@ -324,6 +326,8 @@ LeanLauncher policy_launcher(const BallenvHandle* h, const Params& p, int* lanes
   if (lean_launcher(h, p, &g) == nullptr || p.cfg.obs_format != BALLENV_OBS_F32) return nullptr;
   struct Inst { int w, ks, kd; LeanLauncher g1, g2; };
   static const Inst kInst[] = {{5, 13, 5, launch_lean_policy_w5_s13_d5_g1, launch_lean_policy_w5_s13_d5_g2},
+                               {10, 13, 5, launch_lean_policy_w10_s13_d5_g1, launch_lean_policy_w10_s13_d5_g2},
+                               {10, 8, 24, launch_lean_policy_w10_s8_d24_g1, launch_lean_policy_w10_s8_d24_g2},
                                {5, 8, 24, launch_lean_policy_w5_s8_d24_g1, launch_lean_policy_w5_s8_d24_g2}};
   // a pair of lanes per environment unless told otherwise: the pair also splits the hidden units of the policy, the
   // longest dependent chain of a step
@@ -880,9 +884,9 @@ int ballenv_rollout_policy(BallenvHandle* h, const BallenvPolicyMLP* pol, int32_
   p.pol_greedy = pol->greedy ? 1 : 0;
   LeanLauncher fn = policy_launcher(h, p);
   if (fn == nullptr)
-    return fail(BALLENV_ESTATE, "no policy-in-the-loop kernel for this configuration (production mode, float32 rows, WINDOW 5, "
-                                "13 + 5 or 8 + 24 obstacles): drive ballenv_step from the caller's policy instead");
-  if (4 * lean::policy_smem_floats(n_in, pol->hidden) > 96 * 1024) return fail(BALLENV_EINVAL, "the policy does not fit in shared memory");
+    return fail(BALLENV_ESTATE, "no policy-in-the-loop kernel for this configuration (production mode, float32 rows, WINDOW 5 "
+                                "or 10, 13 + 5 or 8 + 24 obstacles): drive ballenv_step from the caller's policy instead");
+  if (4 * lean::policy_smem_floats(n_in, pol->hidden) > 160 * 1024) return fail(BALLENV_EINVAL, "the policy does not fit in shared memory");
   const size_t n = (size_t)h->n;
   const size_t rew_b = 4;
   // the kernel indexes the [T][n] arrays with 32 bits: at most (2^31 - 1) / n steps per launch

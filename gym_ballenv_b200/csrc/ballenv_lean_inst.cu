@@ -23,7 +23,7 @@ static void launch_lean(const Params& p, unsigned grid, cudaStream_t s) {
   if (dev >= 0 && dev < 64 && !configured[dev]) {
     // seven blocks of 64 environments with their obstacle slices in shared memory: ask for the whole array
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (kPolicy) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    if (kPolicy) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 192 * 1024 - (int)sizeof(LeanWarp<BALLENV_W, BALLENV_KS, BALLENV_KD, BALLENV_G>) * (kLeanEnvsPerBlock * BALLENV_G / 32));
     configured[dev] = true;
   }
   // programmatic stream serialisation: the grid may begin while its predecessor on the stream drains; the kernel

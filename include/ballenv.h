@@ -228,12 +228,14 @@ int ballenv_step_many(BallenvHandle *h, const void *actions, int action_kind, in
  * Sampling: word x of Philox4x32-10(counter = {global env id, tick, 0, stream 3}, key = seed), u = (word >> 8) 2^-24,
  * action = first j with u * sum(e) < e_0 + .. + e_j, e = exp(logit - max): Categorical by inverse CDF, reproducible and
  * independent of the sharding; greedy != 0 takes the first maximum instead.
- * Production configuration only (BALLENV_F32, gym ruleset, Philox draws, BALLENV_OBS_F32 rows) with WINDOW = 5 and
- * 13 + 5 or 8 + 24 obstacles; BALLENV_ESTATE otherwise (step from the caller's policy with ballenv_step).
+ * Production configuration only (BALLENV_F32, gym ruleset, Philox draws, BALLENV_OBS_F32 rows) with WINDOW = 5 or 10
+ * and 13 + 5 or 8 + 24 obstacles - the lean kernels' instances; BALLENV_ESTATE otherwise (step from the caller's
+ * policy with ballenv_step).  The block's copy of the weights must fit shared memory (160 KB: hidden = 208 for
+ * WINDOW = 10 takes 99 KB).
  */
 typedef struct BallenvPolicyMLP {
   int32_t n_inputs;            /* 4 + WINDOW^2 */
-  int32_t hidden;              /* Policy.hidden_layer (128 for WINDOW = 5); a multiple of 8 */
+  int32_t hidden;              /* Policy.hidden_layer (128 for WINDOW = 5, 208 for 10); a multiple of 8 */
   int32_t greedy;              /* 0: sample, 1: argmax */
   int32_t reserved;
   const float *fc1_weight;     /* device [hidden][n_inputs] */

@@ -137,13 +137,38 @@ def test_fused_rollout_does_not_depend_on_the_sharding():
 
 @pytest.mark.gpu
 def test_fused_rollout_needs_a_configuration_it_is_built_for():
+    from gym_ballenv_b200 import BallVecEnv
     from gym_ballenv_b200._lib import BallenvError
-    env, torch = _make(64, window=10)
+    import torch
+    env = BallVecEnv(64, window=5, device="cuda:0", parity=True)       # fp64 parity mode: no lean kernel
     env.reset()
-    pol = _policy(torch, window=10)
-    with pytest.raises(BallenvError):
+    pol = _policy(torch)
+    with pytest.raises((BallenvError, ValueError)):
         _fused(env, torch, pol, 4)
     env.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kd", [5, 24])
+def test_fused_rollout_window_10(kd):
+    """WINDOW = 10 (104 inputs, 208 hidden units - the reference's other shipped shape): same two checks."""
+    n, T = 1500, 30
+    env, torch = _make(n, kd=kd, window=10)
+    twin, _ = _make(n, kd=kd, window=10)
+    env.reset()
+    twin.reset()
+    pol = _policy(torch, window=10, scale=2.0)
+    first, obs, act, rew, done = _fused(env, torch, pol, T, greedy=True)
+    o2, r2, d2 = twin.step_many(act, keep_all_obs=True)
+    assert torch.equal(o2, obs) and torch.equal(r2, rew) and torch.equal(d2.to(torch.uint8), done)
+    seen = torch.cat([first.unsqueeze(0), obs[:-1]], 0)
+    with torch.no_grad():
+        probs, _ = pol(seen.reshape(T * n, -1))
+    top2 = probs.topk(2, -1).values
+    assert bool(((probs.argmax(-1) == act.reshape(-1)) | ((top2[:, 0] - top2[:, 1]) < 1e-5)).all())
+    assert len(torch.unique(act)) >= 5
+    env.close()
+    twin.close()
 
 
 @pytest.mark.gpu
