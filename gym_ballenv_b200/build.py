@@ -34,10 +34,11 @@ INSTANCES = [("float", 5, 0, "launch_f32_w5"), ("float", 10, 0, "launch_f32_w10"
 
 # thread-per-environment kernels (ballenv_lean.cuh): (window, static obstacles, dynamic obstacles)
 LEAN_INSTANCES = [(5, 13, 5), (10, 13, 5), (10, 8, 24), (5, 8, 24)]
+LEAN_RT_WINDOWS = [5, 10]
 
 
 def _sources():
-    deps = [os.path.join(CSRC, f) for f in ("ballenv_kernels.cuh", "ballenv_rng.cuh", "ballenv_lean.cuh",
+    deps = [os.path.join(CSRC, f) for f in ("ballenv_kernels.cuh", "ballenv_rng.cuh", "ballenv_lean.cuh", "ballenv_lean_rt.cuh",
                                             "ballenv_features.cuh", "ballenv_patches.cuh", "ballenv_reset_fixed.cuh")]
     deps.append(os.path.join(os.path.dirname(HERE), "include", "ballenv.h"))
     jobs = [(os.path.join(CSRC, "ballenv_capi.cu"), os.path.join(OBJ, "ballenv_capi.o"), [])]
@@ -52,6 +53,12 @@ def _sources():
             # the policy-in-the-loop rollout (ballenv_rollout_policy) of the same configuration
             defs.append("-DBALLENV_POLICY_NAME=" + name.replace("launch_lean_", "launch_lean_policy_"))
             jobs.append((os.path.join(CSRC, "ballenv_lean_inst.cu"), os.path.join(OBJ, name + ".o"), defs))
+    for w in LEAN_RT_WINDOWS:   # the same kernels with the obstacle counts read from the configuration at run time
+        for g in (1, 2):
+            name = "launch_lean_w%d_rt_g%d" % (w, g)
+            jobs.append((os.path.join(CSRC, "ballenv_lean_rt_inst.cu"), os.path.join(OBJ, name + ".o"),
+                         ["-DBALLENV_W=%d" % w, "-DBALLENV_KS=-1", "-DBALLENV_KD=-1", "-DBALLENV_G=%d" % g,
+                          "-DBALLENV_NAME=" + name, "-DBALLENV_SMEM_NAME=lean_rt_smem_w%d_g%d" % (w, g)]))
     return deps, jobs
 
 

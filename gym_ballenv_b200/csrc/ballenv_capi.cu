@@ -39,6 +39,16 @@ BALLENV_LEAN_DECL(5, 13, 5)
 BALLENV_LEAN_DECL(10, 13, 5)
 BALLENV_LEAN_DECL(10, 8, 24)
 BALLENV_LEAN_DECL(5, 8, 24)
+// the same with the obstacle counts read at run time (any counts whose lists fit)
+void launch_lean_w5_rt_g1(const Params&, unsigned, cudaStream_t);
+void launch_lean_w5_rt_g2(const Params&, unsigned, cudaStream_t);
+void launch_lean_w10_rt_g1(const Params&, unsigned, cudaStream_t);
+void launch_lean_w10_rt_g2(const Params&, unsigned, cudaStream_t);
+size_t lean_rt_smem_w5_g1(int ks, int kd);
+size_t lean_rt_smem_w5_g2(int ks, int kd);
+size_t lean_rt_smem_w10_g1(int ks, int kd);
+size_t lean_rt_smem_w10_g2(int ks, int kd);
+constexpr int kLeanRtMaxObstacles = 64;   // ballenv_lean_rt.cuh
 BALLENV_LEAN_POLICY_DECL(5, 13, 5)
 BALLENV_LEAN_POLICY_DECL(10, 13, 5)
 BALLENV_LEAN_POLICY_DECL(10, 8, 24)
@@ -278,6 +288,7 @@ struct BallenvHandle {
   bool no_rollout = false;      // BALLENV_NO_ROLLOUT=1: ballenv_step_many launches one kernel per step (tests, profiling)
   int lean_g = 0;               // BALLENV_LEAN_G=1|2: lanes per environment of the lean kernels (0: the measured best)
   bool no_lean = false;         // BALLENV_NO_LEAN=1: never pick the thread-per-environment kernels (tests, A/B runs)
+  bool lean_rt_only = false;    // BALLENV_LEAN_RT=1: the run-time-count lean kernels even where a fixed instance exists (tests, A/B runs)
   bool force_generic = false;   // BALLENV_FORCE_GENERIC=1 in the environment: never pick the fast specialisation (tests)
 };
 
@@ -312,11 +323,29 @@ LeanLauncher lean_launcher(const BallenvHandle* h, const Params& p, int* lanes =
                                {10, 8, 24, 2, launch_lean_w10_s8_d24_g1, launch_lean_w10_s8_d24_g2},
                                {5, 8, 24, 2, launch_lean_w5_s8_d24_g1, launch_lean_w5_s8_d24_g2}};
   for (const Inst& i : kInst)
-    if (i.w == c.window && i.ks == c.ks && i.kd == c.kd) {
+    if (i.w == c.window && i.ks == c.ks && i.kd == c.kd && !h->lean_rt_only) {
       const int g = h->lean_g ? h->lean_g : (p.n_steps > 1 ? i.g : 2);
       if (lanes != nullptr) *lanes = g;
       return g == 2 ? i.g2 : i.g1;
     }
+  // any other obstacle counts: the same kernels reading the counts at run time (ballenv_lean_rt.cuh), as long as the
+  // lists fit (the reset's near mask holds 64 obstacles) and at least two blocks' regions fit an SM's shared memory.
+  // Measured against the block-of-roles kernel at 65 536 environments (tools/rt_rate.py): single-step launches - a pair
+  // of lanes, always (13 + 5 counts 10.1 us against 15.0, 8 + 24 counts 18.1 against 22.1); rollouts - one lane per
+  // environment while the moving obstacles are few (13 + 5: 4.0 us per step against 5.9), the block of roles from four
+  // moving quads up (8 + 24: 11.1 against 9.1: the lane walks its quads one Philox block at a time).
+  if ((c.window == 5 || c.window == 10) && c.kd >= 1 && c.ks + c.kd <= kLeanRtMaxObstacles) {
+    const int dyn_quads = (c.kd + 3) / 4;
+    if (p.n_steps > 1 && dyn_quads >= 4 && !h->lean_g && !h->lean_rt_only) return nullptr;
+    const int g = h->lean_g ? h->lean_g : (p.n_steps > 1 ? 1 : 2);
+    const size_t need = 4096 + (c.window == 5 ? (g == 2 ? lean_rt_smem_w5_g2(c.ks, c.kd) : lean_rt_smem_w5_g1(c.ks, c.kd))
+                                              : (g == 2 ? lean_rt_smem_w10_g2(c.ks, c.kd) : lean_rt_smem_w10_g1(c.ks, c.kd)));
+    if (2 * need <= 220 * 1024) {
+      if (lanes != nullptr) *lanes = g;
+      if (c.window == 5) return g == 2 ? launch_lean_w5_rt_g2 : launch_lean_w5_rt_g1;
+      return g == 2 ? launch_lean_w10_rt_g2 : launch_lean_w10_rt_g1;
+    }
+  }
   return nullptr;
 }
 
@@ -548,6 +577,8 @@ int ballenv_create(const BallenvConfig* cfg, int64_t n_envs, int64_t global_env_
   h->force_generic = fg != nullptr && fg[0] == '1';
   const char* nl = getenv("BALLENV_NO_LEAN");
   h->no_lean = nl != nullptr && nl[0] == '1';
+  const char* lr = getenv("BALLENV_LEAN_RT");
+  h->lean_rt_only = lr != nullptr && lr[0] == '1';
   const char* lg = getenv("BALLENV_LEAN_G");
   h->lean_g = lg != nullptr && (lg[0] == '1' || lg[0] == '2') ? lg[0] - '0' : 0;
   const char* nr = getenv("BALLENV_NO_ROLLOUT");

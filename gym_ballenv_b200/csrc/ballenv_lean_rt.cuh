@@ -1,43 +1,24 @@
-// Lane-per-environment (or lane-pair-per-environment) form of the fused step + window-observe kernel (sm_100a) - the
-// production path for the obstacle counts it is instantiated for (ballenv_lean_inst.cu); ballenv_kernels.cuh stays the
-// kernel of every other configuration and mode.  Same arithmetic, same draws, same results (tests: fast vs generic, rollout vs per step,
-// both against the oracle).
+// The lane-per-environment kernels of ballenv_lean.cuh with the OBSTACLE COUNTS READ AT RUN TIME (sm_100a): the
+// production path of every gym-ruleset configuration that has no tuned instance (any counts up to 64 obstacles whose
+// rows fit shared memory, WINDOW 5 or 10) - before, those ran the block-of-roles kernel of round 1.
 //
-//   agent move + wall clamp            gym_ballenv/envs/ballenv_env.py:236-259
-//   obstacle motion                    ballenv_env.py:262-264, 323-353
-//   distance, goal / obstacle tests,   ballenv_env.py:268-286, 200-229, 179-191
-//   reward, accumulated reward, done
-//   TimeLimit(1000) truncation         gym_ballenv/__init__.py:7 (gym 0.10.9 wrapper, restated)
-//   auto-reset of finished envs        ballenv_env.py:113-167 (Philox draws)
-//   WINDOW x WINDOW occupancy + goal   examples/ball_cnn_ac3.py:330-352, 384-412 (incl. the row-offset quirk :409)
-//   quadrant observation
+// Same algorithm, same draws, same results as ballenv_lean.cuh (read its header first; reference lines are cited
+// there and below), written against LeanMem: a warp's shared-memory region is carved out of dynamic shared memory by
+// the configuration's counts, the per-quad loops are real loops (one Philox block at a time), the quads' goal / counter
+// bytes live in per-lane shared-memory words instead of registers, the bounding-box tests always take the
+// branch-per-obstacle form (no bound on a lane's obstacle slots).  The code still carries the fixed-count branches
+// (KS, KD >= 0) it was derived from - compiled out here, instantiated only with KS = KD = -1 (ballenv_lean_rt_inst.cu).
 //
-// Why a second mapping.  The block-of-roles kernel spends its time at named barriers (ncu, round 1: 4.4 barrier
-// stalls per issue, 52 % of the issue slots, 6.0 M warp instructions per step of 65 536 environments) because an
-// environment is spread over a scalar thread and eight quad threads that meet three times per step.  Here one lane
-// (G = 1) or two neighbouring lanes (G = 2) of a warp own ONE environment for the whole launch and never wait for
-// anybody else:
-//   * a pair splits the environment's obstacle quads (lane parity = quad parity); the scalar bookkeeping (agent,
-//     distance, reward, flags) is computed by both lanes - in SIMT that costs the same issue slots as computing it
-//     once - so the only exchange of a step is one shuffle for the first obstacle hit;
-//   * the obstacle coordinates stay in the warp's shared-memory rows, laid out exactly as in HBM ([32 / G
-//     environments][K]: conflict-free 128-bit accesses), goal index and change counter packed four to a register, the
-//     scalars of the reward phase in per-lane shared-memory slots; a step has no barrier and no mailbox, and its
-//     latency is hidden by instruction-level parallelism (independent Philox blocks, moves and tests) plus, for
-//     G = 2, 28 resident warps per SM (one lane per environment leaves 14: measured 39 % of the issue slots for the
-//     32-obstacle configuration, stalled on its own dependencies; 61 % with pairs);
-//   * a warp is autonomous: its environments' rows are one contiguous, 128-byte aligned span of the output, the
-//     lanes OR their private observation bits into one bit-stream in shared memory and expand it with 128-bit
-//     streaming stores; the only synchronisation is __syncwarp;
-//   * the obstacle slices of a warp come in and go out as TMA bulk copies (cp.async.bulk global <-> shared), so the
-//     rows never cause strided global accesses;
-//   * the rare near obstacles (bounding-box test) go to a per-lane list and are rasterised from a table of column
-//     masks indexed by the obstacle's offset from the window (exact for the integral coordinates the gym ruleset
-//     produces; the per-cell arithmetic of the generic kernel is the fallback for anything else);
-//   * a finished environment is reset by its own pair inside the step (rejection loops and all), nobody waits.
-// Nothing here is a dense contraction: no tensor cores.
+// Why a second file instead of one kernel for both: the merged form was measured 1 - 10 % slower on the tuned instances
+// (same instruction counts, different ptxas schedule of the hot loop: 13 + 5 rollout 3.49 -> 3.85 us per step, C3
+// single-step 12.2 -> 13.1 us per launch, same box, alternating runs), and those are the headline configurations.
+// This header must not be included together with ballenv_lean.cuh (same names, own translation unit).
+// Measured (65 536 environments, us per env-step of all): C3 counts 11.1 rollout / 18.1 per launch (tuned instance 6.4 /
+// 12.2, block of roles 9.2 / 22.3); 13 + 5: 4.3 / 9.8 (tuned 3.5 / 7.9, block of roles 5.9 / 15.1).
 #pragma once
-#define BALLENV_LEAN_FIXED_INCLUDED 1
+#ifdef BALLENV_LEAN_FIXED_INCLUDED
+#error "ballenv_lean_rt.cuh and ballenv_lean.cuh define the same names: one per translation unit"
+#endif
 #include <stdint.h>
 
 #include <type_traits>
@@ -76,12 +57,20 @@ struct LeanTab {
   static constexpr int kEntries = U * S;
 };
 
+// Obstacle counts are template parameters of the tuned instantiations (KS, KD >= 0: everything unrolls, the quads'
+// goal / counter bytes and Philox blocks live in registers) or, with KS = KD = -1, read from the configuration at run
+// time (any counts whose lists fit: loops over the lane's quads, goal / counter bytes in shared memory, the warp's
+// region carved out of dynamic shared memory) - the same code below, written against LeanMem.
+constexpr int kLeanRtMaxObstacles = 64;   // run-time counts: static + moving obstacles (reset_warp's near mask)
+
 template <int W, int KS, int KD, int G>
 struct LeanShape {
   static_assert(G == 1 || G == 2, "one lane or a pair of lanes per environment");
+  static_assert((KS >= 0) == (KD >= 0), "both obstacle counts fixed, or both at run time");
+  static constexpr bool kRt = KS < 0;
   static constexpr int EW = 32 / G;                // environments per warp
   static constexpr int kThreads = kLeanEnvsPerBlock * G;
-  static constexpr int QS = (KS + 3) / 4, QD = (KD + 3) / 4;
+  static constexpr int QS = kRt ? 0 : (KS + 3) / 4, QD = kRt ? 0 : (KD + 3) / 4;
   static constexpr int NSQ = (QS + G - 1) / G, NDQ = (QD + G - 1) / G;   // quads of a kind per lane: q = g, g + G, ...
   static constexpr int SS = 4 * QS, DS = 4 * QD;   // elements per environment row (Layout::stat_stride / dyn_stride)
   static constexpr int NB = 4 + W * W;             // observation bits per environment
@@ -110,6 +99,97 @@ struct __align__(128) LeanWarp {
   uint32_t epi[32];                                // episodes begun so far (the reset draws' counter)
   uint32_t exact;                                  // 1: table raster applies, 2: integer square root applies
   unsigned long long mbar;
+};
+
+// What the kernel sees of a warp's shared memory and of the obstacle counts.  Fixed counts: the struct above, every
+// count a constant.  Run-time counts: a region of dynamic shared memory laid out here (the same pieces, plus the
+// quads' goal / counter words, [quad of the lane][lane]).
+template <int W, int KS, int KD, int G>
+struct LeanMem {
+  using S = LeanShape<W, KS, KD, G>;
+  LeanWarp<W, KS, KD, G>* w;
+  __device__ __forceinline__ static constexpr int ks() { return KS; }
+  __device__ __forceinline__ static constexpr int kd() { return KD; }
+  __device__ __forceinline__ static constexpr int qs() { return S::QS; }
+  __device__ __forceinline__ static constexpr int qd() { return S::QD; }
+  __device__ __forceinline__ static constexpr int ss() { return S::SS; }
+  __device__ __forceinline__ static constexpr int ds() { return S::DS; }
+  __device__ __forceinline__ static constexpr int ndq() { return S::NDQ; }
+  __device__ __forceinline__ static constexpr int nsq() { return S::NSQ; }
+  __device__ __forceinline__ float* dx() const { return w->dx; }
+  __device__ __forceinline__ float* dy() const { return w->dy; }
+  __device__ __forceinline__ float* sx() const { return w->sx; }
+  __device__ __forceinline__ float* sy() const { return w->sy; }
+  __device__ __forceinline__ uint32_t* dm() const { return w->dm; }
+  __device__ __forceinline__ float2* near() const { return &w->near[0][0]; }
+  __device__ __forceinline__ uint32_t* stream(int par) const { return w->stream[par]; }
+  __device__ __forceinline__ double* dist() const { return w->dist; }
+  __device__ __forceinline__ double* total() const { return w->total; }
+  __device__ __forceinline__ double* acc() const { return w->acc; }
+  __device__ __forceinline__ float* gx() const { return w->gx; }
+  __device__ __forceinline__ float* gy() const { return w->gy; }
+  __device__ __forceinline__ int* len() const { return w->len; }
+  __device__ __forceinline__ uint32_t* tick() const { return w->tick; }
+  __device__ __forceinline__ uint32_t* epi() const { return w->epi; }
+  __device__ __forceinline__ uint32_t& exact() const { return w->exact; }
+  __device__ __forceinline__ unsigned long long* mbar() const { return &w->mbar; }
+  __device__ __forceinline__ uint32_t* metag() const { return nullptr; }   // (registers)
+  __device__ __forceinline__ uint32_t* metac() const { return nullptr; }
+};
+
+template <int W, int G>
+struct LeanMem<W, -1, -1, G> {
+  using S = LeanShape<W, -1, -1, G>;
+  unsigned char* b;
+  int ks_, kd_;
+  __host__ __device__ __forceinline__ static int quads(int k) { return (k + 3) >> 2; }
+  __device__ __forceinline__ int ks() const { return ks_; }
+  __device__ __forceinline__ int kd() const { return kd_; }
+  __device__ __forceinline__ int qs() const { return quads(ks_); }
+  __device__ __forceinline__ int qd() const { return quads(kd_); }
+  __device__ __forceinline__ int ss() const { return 4 * quads(ks_); }
+  __device__ __forceinline__ int ds() const { return 4 * quads(kd_); }
+  __device__ __forceinline__ int ndq() const { return (quads(kd_) + G - 1) / G; }
+  __device__ __forceinline__ int nsq() const { return (quads(ks_) + G - 1) / G; }
+  // byte offsets of the pieces (every piece a multiple of 16 bytes: the bulk copies need it)
+  __host__ __device__ __forceinline__ static int o_dy(int ks, int kd) { return S::EW * 16 * quads(kd); }
+  __host__ __device__ __forceinline__ static int o_dm(int ks, int kd) { return 2 * o_dy(ks, kd); }
+  __host__ __device__ __forceinline__ static int o_sx(int ks, int kd) { return 3 * o_dy(ks, kd); }
+  __host__ __device__ __forceinline__ static int o_sy(int ks, int kd) { return o_sx(ks, kd) + S::EW * 16 * quads(ks); }
+  __host__ __device__ __forceinline__ static int o_near(int ks, int kd) { return o_sy(ks, kd) + S::EW * 16 * quads(ks); }
+  __host__ __device__ __forceinline__ static int o_stream(int ks, int kd) { return o_near(ks, kd) + kLeanListCap * 32 * 8; }
+  __host__ __device__ __forceinline__ static int o_slots(int ks, int kd) {
+    return (o_stream(ks, kd) + 2 * (S::NSW + 4) * 4 + 15) / 16 * 16;
+  }
+  // slots: dist, total, acc (3 x 256 bytes), gx, gy, len, tick, epi (5 x 128), then the quads' goal and counter words
+  __host__ __device__ __forceinline__ static int o_meta(int ks, int kd) { return o_slots(ks, kd) + 3 * 256 + 5 * 128; }
+  __host__ __device__ __forceinline__ static int o_tail(int ks, int kd) {
+    return o_meta(ks, kd) + 2 * 128 * ((quads(kd) + G - 1) / G);
+  }
+  __host__ __device__ __forceinline__ static int bytes(int ks, int kd) { return (o_tail(ks, kd) + 16 + 127) / 128 * 128; }
+  __device__ __forceinline__ float* dx() const { return reinterpret_cast<float*>(b); }
+  __device__ __forceinline__ float* dy() const { return reinterpret_cast<float*>(b + o_dy(ks_, kd_)); }
+  __device__ __forceinline__ uint32_t* dm() const { return reinterpret_cast<uint32_t*>(b + o_dm(ks_, kd_)); }
+  __device__ __forceinline__ float* sx() const { return reinterpret_cast<float*>(b + o_sx(ks_, kd_)); }
+  __device__ __forceinline__ float* sy() const { return reinterpret_cast<float*>(b + o_sy(ks_, kd_)); }
+  __device__ __forceinline__ float2* near() const { return reinterpret_cast<float2*>(b + o_near(ks_, kd_)); }
+  __device__ __forceinline__ uint32_t* stream(int par) const {
+    return reinterpret_cast<uint32_t*>(b + o_stream(ks_, kd_)) + par * (S::NSW + 4);
+  }
+  __device__ __forceinline__ double* dist() const { return reinterpret_cast<double*>(b + o_slots(ks_, kd_)); }
+  __device__ __forceinline__ double* total() const { return dist() + 32; }
+  __device__ __forceinline__ double* acc() const { return dist() + 64; }
+  __device__ __forceinline__ float* gx() const { return reinterpret_cast<float*>(b + o_slots(ks_, kd_) + 768); }
+  __device__ __forceinline__ float* gy() const { return gx() + 32; }
+  __device__ __forceinline__ int* len() const { return reinterpret_cast<int*>(gx() + 64); }
+  __device__ __forceinline__ uint32_t* tick() const { return reinterpret_cast<uint32_t*>(gx() + 96); }
+  __device__ __forceinline__ uint32_t* epi() const { return reinterpret_cast<uint32_t*>(gx() + 128); }
+  __device__ __forceinline__ uint32_t* metag() const { return reinterpret_cast<uint32_t*>(b + o_meta(ks_, kd_)); }
+  __device__ __forceinline__ uint32_t* metac() const { return metag() + 32 * ndq(); }
+  __device__ __forceinline__ uint32_t& exact() const { return *reinterpret_cast<uint32_t*>(b + o_tail(ks_, kd_)); }
+  __device__ __forceinline__ unsigned long long* mbar() const {
+    return reinterpret_cast<unsigned long long*>(b + o_tail(ks_, kd_) + 8);
+  }
 };
 
 namespace lean {
@@ -336,7 +416,7 @@ __device__ __forceinline__ void raster_one(uint32_t (&bits)[NW], bool exact, con
 // ones) or the reset (static, then moving) queued them, and rasterise those beyond the list.
 template <int W, int KS, int KD, int G>
 __device__ __noinline__ Bits<LeanShape<W, KS, KD, G>::NW> rescan_near(Bits<LeanShape<W, KS, KD, G>::NW> in, const Params& p,
-                                                                     const LeanWarp<W, KS, KD, G>& ws, int lane, float ax,
+                                                                     const LeanMem<W, KS, KD, G> ws, int lane, float ax,
                                                                      float ay, bool after_reset, bool exact) {
   using Sh = LeanShape<W, KS, KD, G>;
   const int el = lane / G, g = lane % G;
@@ -345,9 +425,9 @@ __device__ __noinline__ Bits<LeanShape<W, KS, KD, G>::NW> rescan_near(Bits<LeanS
 #pragma unroll 1
   for (int pass = 0; pass < 2; ++pass) {
     const bool dyn = (pass == 0) != after_reset;
-    const int nq = dyn ? Sh::QD : Sh::QS, kk = dyn ? KD : KS;
-    const float* const rx = dyn ? ws.dx + el * Sh::DS : ws.sx + el * Sh::SS;
-    const float* const ry = dyn ? ws.dy + el * Sh::DS : ws.sy + el * Sh::SS;
+    const int nq = dyn ? ws.qd() : ws.qs(), kk = dyn ? ws.kd() : ws.ks();
+    const float* const rx = dyn ? ws.dx() + el * ws.ds() : ws.sx() + el * ws.ss();
+    const float* const ry = dyn ? ws.dy() + el * ws.ds() : ws.sy() + el * ws.ss();
 #pragma unroll 1
     for (int q = g; q < nq; q += G) {
 #pragma unroll 1
@@ -424,12 +504,12 @@ static __device__ __noinline__ uint4 philox_rolled(uint32_t c0, uint32_t c1, uin
 // rescan_near(after_reset) expects: their static quads, then their moving ones.  Same draws at the same Philox
 // addresses as ever.  Called by all 32 lanes; returns (ax, ay, ncnt) unchanged for the lanes of the other environments.
 template <int W, int KS, int KD, int G>
-__device__ __noinline__ ResetOut reset_warp(const ResetCtx p, LeanWarp<W, KS, KD, G>& ws, int lane, uint32_t e0,
+__device__ __noinline__ ResetOut reset_warp(const ResetCtx p, LeanMem<W, KS, KD, G> ws, int lane, uint32_t e0,
                                             uint32_t fin_lanes, bool want_obs, ResetOut out) {
   using Sh = LeanShape<W, KS, KD, G>;
-  constexpr int SS = Sh::SS, DS = Sh::DS;
-  static_assert(KS + KD <= 64, "the near obstacles of a new episode fit one 64-bit mask");
-  using Mask = typename std::conditional<(KS + KD <= 32), uint32_t, unsigned long long>::type;
+  const int SS = ws.ss(), DS = ws.ds(), KSv = ws.ks(), KDv = ws.kd();
+  static_assert(Sh::kRt || KS + KD <= kLeanRtMaxObstacles, "the near obstacles of a new episode fit one 64-bit mask");
+  using Mask = typename std::conditional<(!Sh::kRt && KS + KD <= 32), uint32_t, unsigned long long>::type;
   const int el = lane / G, g = lane % G;
   const float margin = p.margin;
   bool was_reset = false;
@@ -441,7 +521,7 @@ __device__ __noinline__ ResetOut reset_warp(const ResetCtx p, LeanWarp<W, KS, KD
     todo &= todo - 1u;
     const uint32_t e = e0 + (uint32_t)rel;
     const uint32_t genv = p.g0 + e;
-    const uint32_t episode = ws.epi[rel * G] + 1u;
+    const uint32_t episode = ws.epi()[rel * G] + 1u;
     __syncwarp();   // everybody has read the counter
     const uint4 hw = philox_rolled(genv, episode, kResetHead << 28, kStreamReset, p.k0, p.k1);
     const float gx = (float)__umulhi(hw.x, 500u);                                    // :115-116
@@ -451,12 +531,12 @@ __device__ __noinline__ ResetOut reset_warp(const ResetCtx p, LeanWarp<W, KS, KD
     Mask near_k = 0;
     // obstacle k of the list (static first) is drawn by lane k mod 32
 #pragma unroll 1
-    for (int k0 = 0; k0 < KS + KD; k0 += 32) {
+    for (int k0 = 0; k0 < KSv + KDv; k0 += 32) {
       const int k = k0 + lane;
       bool near = false;
-      if (k < KS + KD) {
-        const bool stat = k < KS;
-        const uint32_t j = (uint32_t)(stat ? k : k - KS);
+      if (k < KSv + KDv) {
+        const bool stat = k < KSv;
+        const uint32_t j = (uint32_t)(stat ? k : k - KSv);
         float ox = 0.0f, oy = 0.0f;
         // static: redraw until clear of the agent and the goal (:131-149), two attempts per Philox block; moving: one
         // draw each, two per block (the caller sets goal j, counter 0)
@@ -477,8 +557,8 @@ __device__ __noinline__ ResetOut reset_warp(const ResetCtx p, LeanWarp<W, KS, KD
             break;
           }
         }
-        (stat ? ws.sx + rel * SS : ws.dx + rel * DS)[j] = ox;
-        (stat ? ws.sy + rel * SS : ws.dy + rel * DS)[j] = oy;
+        (stat ? ws.sx() + rel * SS : ws.dx() + rel * DS)[j] = ox;
+        (stat ? ws.sy() + rel * SS : ws.dy() + rel * DS)[j] = oy;
         if (stat) {
           p.stat_x[(size_t)e * SS + j] = ox;
           p.stat_y[(size_t)e * SS + j] = oy;
@@ -494,13 +574,13 @@ __device__ __noinline__ ResetOut reset_warp(const ResetCtx p, LeanWarp<W, KS, KD
       const double d0 = sqrt_int22(__fmaf_rn(fdx, fdx, __fmul_rn(fdy, fdy)));
       out.ax = nax;
       out.ay = nay;
-      ws.gx[lane] = gx;
-      ws.gy[lane] = gy;
-      ws.dist[lane] = d0;
-      ws.total[lane] = d0;
-      ws.acc[lane] = 0.0;
-      ws.len[lane] &= ~0xfffffff;   // a new episode; the flags of the finished step stay
-      ws.epi[lane] = episode;
+      ws.gx()[lane] = gx;
+      ws.gy()[lane] = gy;
+      ws.dist()[lane] = d0;
+      ws.total()[lane] = d0;
+      ws.acc()[lane] = 0.0;
+      ws.len()[lane] &= ~0xfffffff;   // a new episode; the flags of the finished step stay
+      ws.epi()[lane] = episode;
       if (g == 0) p.episode[e] = episode;
       was_reset = true;
       near_mine = near_k;
@@ -514,11 +594,11 @@ __device__ __noinline__ ResetOut reset_warp(const ResetCtx p, LeanWarp<W, KS, KD
     while (near_mine != 0) {
       const int k = (sizeof(Mask) == 4 ? __ffs((int)near_mine) : __ffsll((long long)near_mine)) - 1;
       near_mine &= near_mine - 1;
-      const bool stat = k < KS;
-      const int j = stat ? k : k - KS;
+      const bool stat = k < KSv;
+      const int j = stat ? k : k - KSv;
       if (((j >> 2) % G) == g) {   // one of this lane's quads
         if (out.ncnt < kLeanListCap)
-          ws.near[out.ncnt][lane] = make_float2((stat ? ws.sx + el * SS : ws.dx + el * DS)[j], (stat ? ws.sy + el * SS : ws.dy + el * DS)[j]);
+          ws.near()[(out.ncnt) * 32 + lane] = make_float2((stat ? ws.sx() + el * SS : ws.dx() + el * DS)[j], (stat ? ws.sy() + el * SS : ws.dy() + el * DS)[j]);
         ++out.ncnt;
       }
     }
@@ -617,23 +697,37 @@ template <int W, int KS, int KD, int G, bool kRollout, bool kPolicy = false>
 __global__ void __launch_bounds__(kLeanEnvsPerBlock * G, kPolicy ? 4 : kLeanMinBlocks) ballenv_lean_kernel(const __grid_constant__ Params p) {
   using namespace lean;
   using Sh = LeanShape<W, KS, KD, G>;
-  constexpr int QS = Sh::QS, QD = Sh::QD, NSQ = Sh::NSQ, NDQ = Sh::NDQ, SS = Sh::SS, DS = Sh::DS, NB = Sh::NB, NW = Sh::NW;
-  constexpr int EW = Sh::EW, kLeanThreads = Sh::kThreads;
-  static_assert(KS > 0 && KD > 0 && W > 1 && W <= 16, "instantiated for windows up to 16 with both kinds of obstacles");
+  constexpr bool kRt = Sh::kRt;   // obstacle counts at run time
+  constexpr int NB = Sh::NB, NW = Sh::NW, EW = Sh::EW, kLeanThreads = Sh::kThreads;
+  constexpr int kRegQuads = kRt ? 1 : (Sh::NDQ > 0 ? Sh::NDQ : 1);   // quads whose goal / counter bytes and draws live in registers
+  static_assert(W > 1 && W <= 16, "instantiated for windows up to 16");
+  static_assert(kRt || (KS > 0 && KD > 0), "the fixed instances have both kinds of obstacles");
+  static_assert(!(kRt && kPolicy), "the policy in the loop comes with the fixed instances");
   // single-step launches hand the moved rows to the copy engine right after the moves when there is enough of them to
   // matter (measured: 24 moving obstacles 12.7 -> 12.2 us per launch; 5 moving obstacles 7.95 -> 8.3 us, so not there)
-  constexpr bool kEarlyStore = !kRollout && LEAN_EARLY_STORE != 0 && KD >= 16;
+  constexpr bool kEarlyStore = !kRollout && LEAN_EARLY_STORE != 0 && !kRt && KD >= 16;
   static_assert(!kPolicy || kRollout, "the policy runs inside the rollout loop");
-  __shared__ LeanWarp<W, KS, KD, G> wsh[kLeanThreads / 32];
+  // dynamic shared memory: the warps' regions (run-time counts) or the block's copy of the policy (kPolicy)
+  extern __shared__ __align__(128) unsigned char lean_dyn[];
   __shared__ float2 s_goal[BALLENV_MAX_GOALS];
   __shared__ float2 s_mv[12];
-  __shared__ __align__(16) float s_speed[DS];
+  __shared__ __align__(16) float s_speed[kRt ? BALLENV_MAX_DYNAMIC : Sh::DS + 4];
   __shared__ __align__(16) float4 s_lut[16];
   const DevConfig& cfg = p.cfg;
   const int tid = threadIdx.x, lane = tid & 31;
   const int el = lane / G;                    // environment of the warp this lane works for
   const uint32_t g = (uint32_t)(lane % G);    // which of its quads: q = g, g + G, ...
-  LeanWarp<W, KS, KD, G>& ws = wsh[tid >> 5];
+  LeanMem<W, KS, KD, G> ws;
+  if constexpr (kRt) {
+    ws.ks_ = cfg.ks;
+    ws.kd_ = cfg.kd;
+    ws.b = lean_dyn + (size_t)(tid >> 5) * (size_t)LeanMem<W, KS, KD, G>::bytes(cfg.ks, cfg.kd);
+  } else {
+    __shared__ LeanWarp<W, KS, KD, G> wsh[kLeanThreads / 32];
+    ws.w = &wsh[tid >> 5];
+  }
+  // the obstacle counts: constants of the instance, or the configuration's
+  const int KSv = ws.ks(), KDv = ws.kd(), QS = ws.qs(), QD = ws.qd(), NSQ = ws.nsq(), NDQ = ws.ndq(), SS = ws.ss(), DS = ws.ds();
   // environment indices fit 31 bits (ballenv_create): 32-bit arithmetic, cheap enough to recompute instead of keeping
   const uint32_t n32 = (uint32_t)p.n;
   const uint32_t e0 = (blockIdx.x * (uint32_t)(kLeanThreads / 32) + (uint32_t)(tid >> 5)) * (uint32_t)EW;   // the warp's first environment
@@ -649,11 +743,11 @@ __global__ void __launch_bounds__(kLeanEnvsPerBlock * G, kPolicy ? 4 : kLeanMinB
     s_lut[tid] = make_float4(tid & 1 ? 1.0f : 0.0f, tid & 2 ? 1.0f : 0.0f, tid & 4 ? 1.0f : 0.0f, tid & 8 ? 1.0f : 0.0f);
   if (tid < 9) s_mv[tid] = make_float2((float)table2(kObstDx, (uint32_t)tid), (float)table2(kObstDy, (uint32_t)tid));
   for (int i = tid; i < cfg.n_goals; i += kLeanThreads) s_goal[i] = cfg.f_goal[i];
-  for (int i = tid; i < DS; i += kLeanThreads) s_speed[i] = i < KD ? cfg.f_speed[i] : 0.0f;
+  for (int i = tid; i < DS; i += kLeanThreads) s_speed[i] = i < KDv ? cfg.f_speed[i] : 0.0f;
   if (warp_live) {
-    for (int i = lane; i < Sh::NSW + 4; i += 32) ws.stream[0][i] = ws.stream[1][i] = 0u;
+    for (int i = lane; i < Sh::NSW + 4; i += 32) ws.stream(0)[i] = ws.stream(1)[i] = 0u;
     if (lane == 0) {
-      mbar_init(&ws.mbar, 1);
+      mbar_init(ws.mbar(), 1);
       bulk_fence_smem_writes();   // fence.proxy.async: the initialised barrier is visible to the copy engine
     }
   }
@@ -665,7 +759,7 @@ __global__ void __launch_bounds__(kLeanEnvsPerBlock * G, kPolicy ? 4 : kLeanMinB
   grid_dependency_wait();
   LEAN_STAMP(2);
   // ---- (policy in the loop) the block's copy of the weights - after the wait: the previous kernel may be the optimiser
-  extern __shared__ __align__(16) float pol_sm[];
+  float* const pol_sm = reinterpret_cast<float*>(lean_dyn);
   if constexpr (kPolicy) {
     const int H = p.pol_hidden, HS = H + 4;
     float* const w1t = pol_sm;
@@ -691,7 +785,7 @@ __global__ void __launch_bounds__(kLeanEnvsPerBlock * G, kPolicy ? 4 : kLeanMinB
   // (the scalar loads go out before the bulk copies: what a single-step launch can do without the obstacle rows - its
   // Philox blocks - then overlaps the arrival of the slices, the bulk of the launch's read burst)
   const uint32_t dirty = p.state_dirty[0];
-  uint4 blk_first[kRollout ? 1 : (NDQ > 0 ? NDQ : 1)];
+  uint4 blk_first[(kRollout || kRt) ? 1 : kRegQuads];
   {
     float gx = 0.0f, gy = 0.0f;
     double dist = 0.0, total = 1.0, acc = 0.0;
@@ -712,61 +806,91 @@ __global__ void __launch_bounds__(kLeanEnvsPerBlock * G, kPolicy ? 4 : kLeanMinB
     }
     // ---- the warp's obstacle slices: five bulk copies into shared memory, in flight during the rest of the setup
     if (warp_live && lane == 0) {
-      mbar_expect_tx(&ws.mbar, (uint32_t)(EW * 4 * (3 * DS + 2 * SS)));
-      bulk_load(ws.dx, reinterpret_cast<const float*>(p.dyn_x) + (size_t)e0 * DS, EW * DS * 4, &ws.mbar);
-      bulk_load(ws.dy, reinterpret_cast<const float*>(p.dyn_y) + (size_t)e0 * DS, EW * DS * 4, &ws.mbar);
-      bulk_load(ws.dm, p.dyn_meta + (size_t)e0 * DS, EW * DS * 4, &ws.mbar);
-      bulk_load(ws.sx, reinterpret_cast<const float*>(p.stat_x) + (size_t)e0 * SS, EW * SS * 4, &ws.mbar);
-      bulk_load(ws.sy, reinterpret_cast<const float*>(p.stat_y) + (size_t)e0 * SS, EW * SS * 4, &ws.mbar);
+      mbar_expect_tx(ws.mbar(), (uint32_t)(EW * 4 * (3 * DS + 2 * SS)));
+      if (!kRt || DS > 0) {
+        bulk_load(ws.dx(), reinterpret_cast<const float*>(p.dyn_x) + (size_t)e0 * DS, EW * DS * 4, ws.mbar());
+        bulk_load(ws.dy(), reinterpret_cast<const float*>(p.dyn_y) + (size_t)e0 * DS, EW * DS * 4, ws.mbar());
+        bulk_load(ws.dm(), p.dyn_meta + (size_t)e0 * DS, EW * DS * 4, ws.mbar());
+      }
+      if (!kRt || SS > 0) {
+        bulk_load(ws.sx(), reinterpret_cast<const float*>(p.stat_x) + (size_t)e0 * SS, EW * SS * 4, ws.mbar());
+        bulk_load(ws.sy(), reinterpret_cast<const float*>(p.stat_y) + (size_t)e0 * SS, EW * SS * 4, ws.mbar());
+      }
     }
-    ws.gx[lane] = gx;
-    ws.gy[lane] = gy;
-    ws.dist[lane] = dist;
-    ws.total[lane] = total;
-    ws.acc[lane] = acc;
-    ws.len[lane] = len;
-    ws.epi[lane] = epi;
+    ws.gx()[lane] = gx;
+    ws.gy()[lane] = gy;
+    ws.dist()[lane] = dist;
+    ws.total()[lane] = total;
+    ws.acc()[lane] = acc;
+    ws.len()[lane] = len;
+    ws.epi()[lane] = epi;
     small_goal = small_int(gx) && small_int(gy);
-    if constexpr (kRollout) {
-      ws.tick[lane] = tick;
+    if constexpr (kRollout || kRt) {
+      ws.tick()[lane] = tick;
     } else {
       // the draws of the launch's only step (ballenv_env.py:332, 340, 345, 352): their address is (environment, tick)
-      ws.tick[lane] = tick + 1;
-      if ((LEAN_SKIP & 1) == 0) philox_blocks<NDQ, G>(p, p.g0 + e, tick, g, kStreamStep, blk_first);
+      ws.tick()[lane] = tick + 1;
+      if ((LEAN_SKIP & 1) == 0) philox_blocks<kRegQuads, G>(p, p.g0 + e, tick, g, kStreamStep, blk_first);
     }
   }
   __syncthreads();   // the block tables are complete
   if (!warp_live) return;
-  mbar_wait(&ws.mbar, 0);
+  mbar_wait(ws.mbar(), 0);
   LEAN_STAMP(3);
 
   // this lane's rows: quad q of a kind sits at element 4 q of the environment's row
-  float* const my_dx = ws.dx + el * DS;
-  float* const my_dy = ws.dy + el * DS;
-  const float* const my_sx = ws.sx + el * SS;
-  const float* const my_sy = ws.sy + el * SS;
+  float* const my_dx = ws.dx() + el * DS;
+  float* const my_dy = ws.dy() + el * DS;
+  const float* const my_sx = ws.sx() + el * SS;
+  const float* const my_sy = ws.sy() + el * SS;
 
   // ---- goal index and change counter of this lane's moving quads, packed four to a register (one byte each; the
   //      counter never exceeds change_step <= 254, a stored counter beyond it means the same as change_step); slots
   //      that hold no obstacle (last quad) mirror the quad's first one so that the quad-wide tests hold
   const uint32_t cs = (uint32_t)cfg.change_step;
-  uint32_t g4[NDQ], c4[NDQ];
-#pragma unroll
-  for (int i = 0; i < NDQ; ++i) {
+  //      (fixed counts: in the registers g4 / c4; run-time counts: in the lane's shared-memory words)
+  uint32_t g4[kRegQuads], c4[kRegQuads];
+  auto meta_get = [&](int i, uint32_t& gq, uint32_t& cq) {
+    if constexpr (kRt) {
+      gq = ws.metag()[i * 32 + lane];
+      cq = ws.metac()[i * 32 + lane];
+    } else {
+      gq = g4[i];
+      cq = c4[i];
+    }
+  };
+  auto meta_set = [&](int i, uint32_t gq, uint32_t cq) {
+    if constexpr (kRt) {
+      ws.metag()[i * 32 + lane] = gq;
+      ws.metac()[i * 32 + lane] = cq;
+    } else {
+      g4[i] = gq;
+      c4[i] = cq;
+    }
+  };
+  auto meta_unpack = [&](int i) {
     const int q = (int)g + G * i;
-    g4[i] = c4[i] = 0u;
+    uint32_t gq = 0u, cq = 0u;
     if (q < QD) {
-      const uint4 vm = *reinterpret_cast<const uint4*>(&ws.dm[el * DS + 4 * q]);
+      const uint4 vm = *reinterpret_cast<const uint4*>(&ws.dm()[el * DS + 4 * q]);
       const uint32_t fm[4] = {vm.x, vm.y, vm.z, vm.w};
       uint32_t mm[4], cc[4];
 #pragma unroll
       for (int s = 0; s < 4; ++s) {
-        mm[s] = 4 * q + s < KD ? fm[s] : fm[0];
+        mm[s] = 4 * q + s < KDv ? fm[s] : fm[0];
         cc[s] = min(mm[s] >> 8, cs);
       }
-      g4[i] = __byte_perm(__byte_perm(mm[0], mm[1], 0x0040), __byte_perm(mm[2], mm[3], 0x0040), 0x5410);
-      c4[i] = __byte_perm(__byte_perm(cc[0], cc[1], 0x0040), __byte_perm(cc[2], cc[3], 0x0040), 0x5410);
+      gq = __byte_perm(__byte_perm(mm[0], mm[1], 0x0040), __byte_perm(mm[2], mm[3], 0x0040), 0x5410);
+      cq = __byte_perm(__byte_perm(cc[0], cc[1], 0x0040), __byte_perm(cc[2], cc[3], 0x0040), 0x5410);
     }
+    meta_set(i, gq, cq);
+  };
+  if constexpr (kRt) {
+#pragma unroll 1
+    for (int i = 0; i < NDQ; ++i) meta_unpack(i);
+  } else {
+#pragma unroll
+    for (int i = 0; i < Sh::NDQ; ++i) meta_unpack(i);
   }
   // Integral coordinates (what the gym ruleset produces: integer draws, unit steps, integral obstacle speeds) stay
   // integral while the loop runs: the exact shortcuts apply - sqrt_int22 for the distance to the goal (its own,
@@ -775,27 +899,27 @@ __global__ void __launch_bounds__(kLeanEnvsPerBlock * G, kPolicy ? 4 : kLeanMinB
   // otherwise is every coordinate of the warp looked at.  (Warp-uniform; kept in a shared word rather than in two of
   // the lane's 72 registers.)
   if (dirty == 0u) {
-    if (lane == 0) ws.exact = cfg.lean_integral_speeds != 0 ? 3u : 0u;
+    if (lane == 0) ws.exact() = cfg.lean_integral_speeds != 0 ? 3u : 0u;
   } else {
     bool integral = small_integral(ax) && small_integral(ay);
 #pragma unroll 1
     for (int q = (int)g; q < QD; q += G) {
 #pragma unroll
       for (int s = 0; s < 4; ++s)
-        if (4 * q + s < KD) integral = integral && small_integral(my_dx[4 * q + s]) && small_integral(my_dy[4 * q + s]);
+        if (4 * q + s < KDv) integral = integral && small_integral(my_dx[4 * q + s]) && small_integral(my_dy[4 * q + s]);
     }
 #pragma unroll 1
     for (int q = (int)g; q < QS; q += G) {
 #pragma unroll
       for (int s = 0; s < 4; ++s)
-        if (4 * q + s < KS) integral = integral && small_integral(my_sx[4 * q + s]) && small_integral(my_sy[4 * q + s]);
+        if (4 * q + s < KSv) integral = integral && small_integral(my_sx[4 * q + s]) && small_integral(my_sy[4 * q + s]);
     }
     const bool xr = __all_sync(0xffffffffu, !mine || integral) && cfg.lean_integral_speeds != 0;
     const bool xs = xr && __all_sync(0xffffffffu, !mine || (small_int(ax) && small_int(ay) && small_goal));
-    if (lane == 0) ws.exact = (xr ? 1u : 0u) | (xs ? 2u : 0u);
+    if (lane == 0) ws.exact() = (xr ? 1u : 0u) | (xs ? 2u : 0u);
   }
   LEAN_STAMP(9);
-  __syncwarp();   // everybody has read its part of ws.dm: the near lists may take its place; ws.exact is visible
+  __syncwarp();   // everybody has read its part of ws.dm(): the near lists may take its place; ws.exact() is visible
   const float margin = cfg.f_margin;
   const uint32_t genv = p.g0 + e;
   LEAN_STAMP(4);
@@ -827,7 +951,7 @@ __global__ void __launch_bounds__(kLeanEnvsPerBlock * G, kPolicy ? 4 : kLeanMinB
         Bits<NW> xb;
 #pragma unroll
         for (int i = 0; i < NW; ++i) xb.w[i] = cur_bits[i];
-        const uint4 aw = philox4x32_10(genv, ws.tick[lane], 0u, kStreamAction, p.k0, p.k1);
+        const uint4 aw = philox4x32_10(genv, ws.tick()[lane], 0u, kStreamAction, p.k0, p.k1);
         ai = policy_action<NB, NW, G>(pol_sm, p.pol_hidden, xb, aw.x, (int)g, p.pol_greedy);
         if (g == 0u && mine) p.pol_actions[(size_t)((uint32_t)t * n32 + e)] = ai;
       } else if (kRollout && t + 1 < n_steps && mine) {
@@ -851,7 +975,8 @@ __global__ void __launch_bounds__(kLeanEnvsPerBlock * G, kPolicy ? 4 : kLeanMinB
       // step for the near ones - better wherever a lane tests many obstacles or a launch is a chain of latencies (one
       // lane per environment: 3.52 -> 3.40 us per step for 13 + 5; single-step launches: 17.1 -> 16.9 us) - or a branch
       // per obstacle, 1 % better in the pair-per-environment rollout loop (6.31 against 6.39 us per step for C3).
-      constexpr bool kScanMask = LEAN_SCANMASK >= 0 ? (LEAN_SCANMASK != 0) : (G == 1 || !kRollout);
+      // (run-time counts: always the branch per obstacle - no bound on the slots of a lane)
+      constexpr bool kScanMask = !kRt && (LEAN_SCANMASK >= 0 ? (LEAN_SCANMASK != 0) : (G == 1 || !kRollout));
       uint32_t near_mask = 0;   // bit = this lane's slot: its moving quads first (4 i + s), then its static ones
       auto scan4 = [&](const float (&ox)[4], const float (&oy)[4], int k0, int nvalid, int slot0) {
         if constexpr (kScanMask) {
@@ -870,7 +995,7 @@ __global__ void __launch_bounds__(kLeanEnvsPerBlock * G, kPolicy ? 4 : kLeanMinB
               if ((LEAN_SKIP & 16) == 0 && __fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy)) <= r2)
                 hit_first = min(hit_first, k0 + s);
               if (want_obs) {
-                if (ncnt < kLeanListCap) ws.near[ncnt][lane] = make_float2(ox[s], oy[s]);
+                if (ncnt < kLeanListCap) ws.near()[(ncnt) * 32 + lane] = make_float2(ox[s], oy[s]);
                 ++ncnt;
               }
             }
@@ -880,78 +1005,98 @@ __global__ void __launch_bounds__(kLeanEnvsPerBlock * G, kPolicy ? 4 : kLeanMinB
 
       // ---- obstacle motion (ballenv_env.py:262-264, 323-353): one Philox block per quad, word s for obstacle 4 q + s
       {
-        uint4 blk[NDQ];
-        if constexpr (kRollout) {
-          const uint32_t tick = ws.tick[lane];   // steps since creation: the draw address of this step
-          ws.tick[lane] = tick + 1;
-          if ((LEAN_SKIP & 1) == 0) philox_blocks<NDQ, G>(p, genv, tick, g, kStreamStep, blk);
-        } else {
+        // one moving quad of this lane: q = g + G i, its Philox block, its goal / counter bytes
+        auto dyn_quad = [&](int i, int q, const uint4& bq, uint32_t& gq4, uint32_t& cq4) {
+          const uint32_t wq[4] = {bq.x, bq.y, bq.z, bq.w};
+          float qx[4], qy[4];
+          const int nvalid = (!kRt && KD % 4 == 0) ? 4 : min(4, KDv - 4 * q);
+          const uint32_t z = cq4 ^ cfg.lean_cs4;   // change_step in every byte (launch constant)
+          if ((LEAN_SKIP & 1) != 0) {
+            unpack4(*reinterpret_cast<const float4*>(&my_dx[4 * q]), qx);
+            unpack4(*reinterpret_cast<const float4*>(&my_dy[4 * q]), qy);
+          } else if (z != 0u && !has_zero_byte(z)) {
+            // everybody moves (:327-348)
+            unpack4(*reinterpret_cast<const float4*>(&my_dx[4 * q]), qx);
+            unpack4(*reinterpret_cast<const float4*>(&my_dy[4 * q]), qy);
+            float sp[4];
+            unpack4(*reinterpret_cast<const float4*>(&s_speed[4 * q]), sp);
 #pragma unroll
-          for (int i = 0; i < NDQ; ++i) blk[i] = blk_first[i];   // drawn while the slices were in flight
-        }
-        if (!kRollout) LEAN_STAMP(10);
-#pragma unroll
-        for (int i = 0; i < NDQ; ++i) {
-          const int q = (int)g + G * i;
-          if (QD % G == 0 || q < QD) {
-            const uint32_t wq[4] = {blk[i].x, blk[i].y, blk[i].z, blk[i].w};
-            float qx[4], qy[4];
-            const int nvalid = (KD % 4 == 0) ? 4 : min(4, KD - 4 * q);
-            const uint32_t z = c4[i] ^ cfg.lean_cs4;   // change_step in every byte (launch constant)
-            if ((LEAN_SKIP & 1) != 0) {
-              unpack4(*reinterpret_cast<const float4*>(&my_dx[4 * q]), qx);
-              unpack4(*reinterpret_cast<const float4*>(&my_dy[4 * q]), qy);
-            } else if (z != 0u && !has_zero_byte(z)) {
-              // everybody moves (:327-348)
-              unpack4(*reinterpret_cast<const float4*>(&my_dx[4 * q]), qx);
-              unpack4(*reinterpret_cast<const float4*>(&my_dy[4 * q]), qy);
-              float sp[4];
-              unpack4(*reinterpret_cast<const float4*>(&s_speed[4 * q]), sp);
+            for (int s = 0; s < 4; ++s) {
+              const uint32_t w1 = wq[s];
+              const float2 gl = s_goal[(gq4 >> (8 * s)) & 0xffu];
+              const float tx = r_sub(gl.x, qx[s]), ty = r_sub(gl.y, qy[s]);        // :329-330
+              const bool diag = tx != 0.0f && ty != 0.0f;                          // :331
+              const unsigned long long pr = (unsigned long long)w1 * 100ull;      // randint(100) and the second draw
+              const bool seek = diag && (int)(uint32_t)(pr >> 32) < cfg.rd_th;     // :332
+              // :340 / :345, or :334-335 tempx / abs(tempx), tempy / abs(tempy)
+              float2 mv = s_mv[__umulhi(diag ? (uint32_t)pr : w1, 9u)];
+              mv.x = seek ? copysignf(1.0f, tx) : mv.x;
+              mv.y = seek ? copysignf(1.0f, ty) : mv.y;
+              qx[s] = fmaf(mv.x, sp[s], qx[s]);   // rounds like x + m * s: m is -1, 0 or 1 (empty slots: speed 0)
+              qy[s] = fmaf(mv.y, sp[s], qy[s]);
+            }
+            cq4 += 0x01010101u;                                                  // :348
+            *reinterpret_cast<float4*>(&my_dx[4 * q]) = make_float4(qx[0], qx[1], qx[2], qx[3]);
+            *reinterpret_cast<float4*>(&my_dy[4 * q]) = make_float4(qy[0], qy[1], qy[2], qy[3]);
+          } else {
+            if (z == 0u) {
+              LEAN_FLAG(0);
+              // the whole quad reached the change step (the obstacles of an environment run in lockstep): everybody
+              // picks another goal and nobody moves (:349-353)
+              uint32_t gq = gq4;
 #pragma unroll
               for (int s = 0; s < 4; ++s) {
-                const uint32_t w1 = wq[s];
-                const float2 gl = s_goal[(g4[i] >> (8 * s)) & 0xffu];
-                const float tx = r_sub(gl.x, qx[s]), ty = r_sub(gl.y, qy[s]);        // :329-330
-                const bool diag = tx != 0.0f && ty != 0.0f;                          // :331
-                const unsigned long long pr = (unsigned long long)w1 * 100ull;      // randint(100) and the second draw
-                const bool seek = diag && (int)(uint32_t)(pr >> 32) < cfg.rd_th;     // :332
-                // :340 / :345, or :334-335 tempx / abs(tempx), tempy / abs(tempy)
-                float2 mv = s_mv[__umulhi(diag ? (uint32_t)pr : w1, 9u)];
-                mv.x = seek ? copysignf(1.0f, tx) : mv.x;
-                mv.y = seek ? copysignf(1.0f, ty) : mv.y;
-                qx[s] = fmaf(mv.x, sp[s], qx[s]);   // rounds like x + m * s: m is -1, 0 or 1 (empty slots: speed 0)
-                qy[s] = fmaf(mv.y, sp[s], qy[s]);
-              }
-              c4[i] += 0x01010101u;                                                  // :348
-              *reinterpret_cast<float4*>(&my_dx[4 * q]) = make_float4(qx[0], qx[1], qx[2], qx[3]);
-              *reinterpret_cast<float4*>(&my_dy[4 * q]) = make_float4(qy[0], qy[1], qy[2], qy[3]);
-            } else {
-              if (z == 0u) {
-                LEAN_FLAG(0);
-                // the whole quad reached the change step (the obstacles of an environment run in lockstep): everybody
-                // picks another goal and nobody moves (:349-353)
-                uint32_t gq = g4[i];
-#pragma unroll
-                for (int s = 0; s < 4; ++s) {
-                  if (s < nvalid) {
-                    const uint32_t gi = (gq >> (8 * s)) & 0xffu;
-                    const uint32_t m = __umulhi(wq[s], (uint32_t)(cfg.n_goals - 1));
-                    gq = (gq & ~(0xffu << (8 * s))) | ((m + (m >= gi ? 1u : 0u)) << (8 * s));
-                  }
+                if (s < nvalid) {
+                  const uint32_t gi = (gq >> (8 * s)) & 0xffu;
+                  const uint32_t m = __umulhi(wq[s], (uint32_t)(cfg.n_goals - 1));
+                  gq = (gq & ~(0xffu << (8 * s))) | ((m + (m >= gi ? 1u : 0u)) << (8 * s));
                 }
-                g4[i] = gq;
-                c4[i] = 0u;
-              } else {
-                LEAN_FLAG(1);
-                const uint2 gc = move_mixed(cfg, s_goal, s_mv, &s_speed[4 * q], &my_dx[4 * q], &my_dy[4 * q], blk[i], g4[i],
-                                            c4[i], nvalid);
-                g4[i] = gc.x;
-                c4[i] = gc.y;
               }
-              unpack4(*reinterpret_cast<const float4*>(&my_dx[4 * q]), qx);
-              unpack4(*reinterpret_cast<const float4*>(&my_dy[4 * q]), qy);
+              gq4 = gq;
+              cq4 = 0u;
+            } else {
+              LEAN_FLAG(1);
+              const uint2 gc = move_mixed(cfg, s_goal, s_mv, &s_speed[4 * q], &my_dx[4 * q], &my_dy[4 * q], bq, gq4,
+                                          cq4, nvalid);
+              gq4 = gc.x;
+              cq4 = gc.y;
             }
-            if ((LEAN_SKIP & 2) == 0) scan4(qx, qy, KS + 4 * q, nvalid, 4 * i);
+            unpack4(*reinterpret_cast<const float4*>(&my_dx[4 * q]), qx);
+            unpack4(*reinterpret_cast<const float4*>(&my_dy[4 * q]), qy);
+          }
+          if ((LEAN_SKIP & 2) == 0) scan4(qx, qy, KSv + 4 * q, nvalid, 4 * i);
+        };
+        if constexpr (kRt) {
+          const uint32_t tick = ws.tick()[lane];   // steps since creation: the draw address of this step
+          ws.tick()[lane] = tick + 1;
+          // (two quads per trip with interleaved Philox rounds measured slower: 11.1 -> 11.6 us for 24 moving obstacles)
+#pragma unroll 1
+          for (int i = 0; i < NDQ; ++i) {
+            const int q = (int)g + G * i;
+            if (q < QD) {
+              uint4 bq[1];
+              philox_blocks<1, G>(p, genv, tick, (uint32_t)q, kStreamStep, bq);
+              uint32_t gq4, cq4;
+              meta_get(i, gq4, cq4);
+              dyn_quad(i, q, bq[0], gq4, cq4);
+              meta_set(i, gq4, cq4);
+            }
+          }
+        } else {
+          uint4 blk[kRegQuads];
+          if constexpr (kRollout) {
+            const uint32_t tick = ws.tick()[lane];   // steps since creation: the draw address of this step
+            ws.tick()[lane] = tick + 1;
+            if ((LEAN_SKIP & 1) == 0) philox_blocks<kRegQuads, G>(p, genv, tick, g, kStreamStep, blk);
+          } else {
+#pragma unroll
+            for (int i = 0; i < Sh::NDQ; ++i) blk[i] = blk_first[i];   // drawn while the slices were in flight
+          }
+          if (!kRollout) LEAN_STAMP(10);
+#pragma unroll
+          for (int i = 0; i < Sh::NDQ; ++i) {
+            const int q = (int)g + G * i;
+            if (Sh::QD % G == 0 || q < Sh::QD) dyn_quad(i, q, blk[i], g4[i], c4[i]);
           }
         }
       }
@@ -962,26 +1107,32 @@ __global__ void __launch_bounds__(kLeanEnvsPerBlock * G, kPolicy ? 4 : kLeanMinB
         bulk_fence_smem_writes();
         __syncwarp();
         if (lane == 0) {
-          bulk_store(reinterpret_cast<float*>(p.dyn_x) + (size_t)e0 * DS, ws.dx, EW * DS * 4);
-          bulk_store(reinterpret_cast<float*>(p.dyn_y) + (size_t)e0 * DS, ws.dy, EW * DS * 4);
+          bulk_store(reinterpret_cast<float*>(p.dyn_x) + (size_t)e0 * DS, ws.dx(), EW * DS * 4);
+          bulk_store(reinterpret_cast<float*>(p.dyn_y) + (size_t)e0 * DS, ws.dy(), EW * DS * 4);
           bulk_commit();
         }
       }
       // ---- the static obstacles of this lane
-#pragma unroll
-      for (int i = 0; i < NSQ; ++i) {
+      auto stat_quad = [&](int i) {
         const int q = (int)g + G * i;
-        if (QS % G == 0 || q < QS) {
+        if (q < QS) {
           float fx[4], fy[4];
           unpack4(*reinterpret_cast<const float4*>(&my_sx[4 * q]), fx);
           unpack4(*reinterpret_cast<const float4*>(&my_sy[4 * q]), fy);
-          const int nvalid = (KS % 4 == 0) ? 4 : min(4, KS - 4 * q);
+          const int nvalid = (!kRt && KS % 4 == 0) ? 4 : min(4, KSv - 4 * q);
           if ((LEAN_SKIP & 2) == 0) scan4(fx, fy, 4 * q, nvalid, 4 * NDQ + 4 * i);
         }
+      };
+      if constexpr (kRt) {
+#pragma unroll 1
+        for (int i = 0; i < NSQ; ++i) stat_quad(i);
+      } else {
+#pragma unroll
+        for (int i = 0; i < Sh::NSQ; ++i) stat_quad(i);
       }
       // the rare near ones (one branch per step): exact hit test (check_overlap; the first hit in list order decides
       // the penalty) and the raster queue.  Their coordinates come back from the lane's rows by slot.
-      static_assert(4 * (NDQ + NSQ) <= 32, "a lane's obstacle slots fit one mask");
+      static_assert(!kScanMask || 4 * (Sh::NDQ + Sh::NSQ) <= 32, "a lane's obstacle slots fit one mask");
       while (near_mask != 0u) {
         const int slot = __ffs((int)near_mask) - 1;
         near_mask &= near_mask - 1u;
@@ -991,9 +1142,9 @@ __global__ void __launch_bounds__(kLeanEnvsPerBlock * G, kPolicy ? 4 : kLeanMinB
         const float ox = dyn ? my_dx[idx] : my_sx[idx], oy = dyn ? my_dy[idx] : my_sy[idx];
         const float ddx = r_sub(ax, ox), ddy = r_sub(ay, oy);
         if ((LEAN_SKIP & 16) == 0 && __fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy)) <= r2)
-          hit_first = min(hit_first, dyn ? KS + idx : idx);
+          hit_first = min(hit_first, dyn ? KSv + idx : idx);
         if (want_obs) {
-          if (ncnt < kLeanListCap) ws.near[ncnt][lane] = make_float2(ox, oy);
+          if (ncnt < kLeanListCap) ws.near()[(ncnt) * 32 + lane] = make_float2(ox, oy);
           ++ncnt;
         }
       }
@@ -1004,30 +1155,30 @@ __global__ void __launch_bounds__(kLeanEnvsPerBlock * G, kPolicy ? 4 : kLeanMinB
 
     {
       // ---- distance, progress reward, goal and time-limit flags (ballenv_env.py:268-286, 200-206), hits (:208-224)
-      const float gx = ws.gx[lane], gy = ws.gy[lane];
+      const float gx = ws.gx()[lane], gy = ws.gy()[lane];
       double d;
-      if (ws.exact & 2u) {
+      if (ws.exact() & 2u) {
         const float fdx = gx - ax, fdy = gy - ay;     // exact, as are the squares
         d = sqrt_int22(__fmaf_rn(fdx, fdx, __fmul_rn(fdy, fdy)));
       } else {
         d = dist64((double)gx, (double)gy, (double)ax, (double)ay);   // :268
       }
-      const int ep_len = (ws.len[lane] & 0xfffffff) + 1;
+      const int ep_len = (ws.len()[lane] & 0xfffffff) + 1;
       const bool truncated = cfg.max_steps > 0 && ep_len >= cfg.max_steps;
       const bool goal_flag = d < cfg.goal_threshold;                  // :276
       double reward;                                                  // :205-206, old = state[2] (:236)
       {
-        const double num = ws.dist[lane] - d, den = ws.total[lane];
+        const double num = ws.dist()[lane] - d, den = ws.total()[lane];
         const bool zero = num == 0.0;        // (+-0) / den = +-0 for den > 0
         const double q = div64_fast_path(zero ? 1.0 : num, den);
         reward = zero ? num : q;
       }
       const bool hit = hit_first != kNoHit;
-      const bool hit_dyn = hit && hit_first >= KS;
+      const bool hit_dyn = hit && hit_first >= KSv;
       if (hit) reward -= hit_dyn ? cfg.dynamic_penalty : cfg.static_penalty;   // :222-224
       const bool done = goal_flag || hit;                             // :286
       const bool done_out = done || truncated;
-      ws.acc[lane] += reward;                                         // :280
+      ws.acc()[lane] += reward;                                         // :280
       const uint32_t flags = (goal_flag ? BALLENV_FLAG_GOAL : 0) | (hit ? BALLENV_FLAG_HIT : 0) |
                              (truncated ? BALLENV_FLAG_TRUNCATED : 0) | (hit_dyn ? BALLENV_FLAG_HIT_DYNAMIC : 0);
       if (g == 0u && mine) {
@@ -1036,8 +1187,8 @@ __global__ void __launch_bounds__(kLeanEnvsPerBlock * G, kPolicy ? 4 : kLeanMinB
         if (p.reward != nullptr) reinterpret_cast<float*>(p.reward)[et] = (float)reward;
         if (p.done != nullptr) p.done[et] = done_out ? 1 : 0;
       }
-      ws.dist[lane] = d;
-      ws.len[lane] = ep_len | (int)(flags << 28);
+      ws.dist()[lane] = d;
+      ws.len()[lane] = ep_len | (int)(flags << 28);
       fin = (done_out && mine) ? (1u | (goal_flag ? 2u : 0u) | ((hit && !hit_dyn) ? 4u : 0u) | (hit_dyn ? 8u : 0u) |
                                   ((truncated && !done) ? 16u : 0u))
                                : 0u;
@@ -1051,8 +1202,8 @@ __global__ void __launch_bounds__(kLeanEnvsPerBlock * G, kPolicy ? 4 : kLeanMinB
       LEAN_FLAG(3);
       if (g == 0u && fin != 0u) {
         atomicAdd(&p.stats[BALLENV_STAT_EPISODES], 1.0);
-        atomicAdd(&p.stats[BALLENV_STAT_RETURN_SUM], ws.acc[lane]);
-        atomicAdd(&p.stats[BALLENV_STAT_LENGTH_SUM], (double)(ws.len[lane] & 0xfffffff));
+        atomicAdd(&p.stats[BALLENV_STAT_RETURN_SUM], ws.acc()[lane]);
+        atomicAdd(&p.stats[BALLENV_STAT_LENGTH_SUM], (double)(ws.len()[lane] & 0xfffffff));
         if (fin & 2u) atomicAdd(&p.stats[BALLENV_STAT_GOALS], 1.0);
         if (fin & 12u) atomicAdd(&p.stats[(fin & 8u) ? BALLENV_STAT_HITS_DYNAMIC : BALLENV_STAT_HITS_STATIC], 1.0);
         if (fin & 16u) atomicAdd(&p.stats[BALLENV_STAT_TIMEOUTS], 1.0);
@@ -1084,14 +1235,19 @@ __global__ void __launch_bounds__(kLeanEnvsPerBlock * G, kPolicy ? 4 : kLeanMinB
         ncnt = r.ncnt;
       }
       if (fin != 0u && cfg.auto_reset) {
-#pragma unroll
-        for (int i = 0; i < NDQ; ++i) {   // goal j for obstacle j, counter 0 (:160)
+        auto meta_new = [&](int i) {   // goal j for obstacle j, counter 0 (:160)
           const uint32_t q = g + (uint32_t)(G * i);
           uint32_t gq = 0;
 #pragma unroll
-          for (int s = 0; s < 4; ++s) gq |= (4u * q + (uint32_t)s < (uint32_t)KD ? 4u * q + (uint32_t)s : 4u * q) << (8 * s);
-          g4[i] = gq;
-          c4[i] = 0u;
+          for (int s = 0; s < 4; ++s) gq |= (4u * q + (uint32_t)s < (uint32_t)KDv ? 4u * q + (uint32_t)s : 4u * q) << (8 * s);
+          meta_set(i, gq, 0u);
+        };
+        if constexpr (kRt) {
+#pragma unroll 1
+          for (int i = 0; i < NDQ; ++i) meta_new(i);
+        } else {
+#pragma unroll
+          for (int i = 0; i < Sh::NDQ; ++i) meta_new(i);
         }
       }
     }
@@ -1100,24 +1256,24 @@ __global__ void __launch_bounds__(kLeanEnvsPerBlock * G, kPolicy ? 4 : kLeanMinB
     //      near lists, OR into the warp's bit-stream, expand to rows
     if (!kRollout) LEAN_STAMP(12);
     if (want_obs) {
-      uint32_t* const st = ws.stream[t & 1];
+      uint32_t* const st = ws.stream(t & 1);
       if (ncnt > 0) LEAN_FLAG(2);
       {
         uint32_t bits[NW];
 #pragma unroll
         for (int i = 0; i < NW; ++i) bits[i] = 0u;
-        if (g == 0u) bits[0] = 1u << goal_quadrant_bit(r_sub(ws.gx[lane], ax) < 0.0f, r_sub(ws.gy[lane], ay) < 0.0f);
+        if (g == 0u) bits[0] = 1u << goal_quadrant_bit(r_sub(ws.gx()[lane], ax) < 0.0f, r_sub(ws.gy()[lane], ay) < 0.0f);
         const int nl = (LEAN_SKIP & 8) ? 0 : (ncnt < kLeanListCap ? ncnt : kLeanListCap);
         for (int i = 0; i < nl; ++i) {
-          const float2 o = ws.near[i][lane];
-          raster_one<W, NW>(bits, (ws.exact & 1u) != 0u, cfg, p.lean_tab, o.x, o.y, ax, ay);
+          const float2 o = ws.near()[(i) * 32 + lane];
+          raster_one<W, NW>(bits, (ws.exact() & 1u) != 0u, cfg, p.lean_tab, o.x, o.y, ax, ay);
         }
         if (ncnt > kLeanListCap) {   // (very rare) more near obstacles than list slots
           LEAN_FLAG(4);
           Bits<NW> b;
 #pragma unroll
           for (int i = 0; i < NW; ++i) b.w[i] = bits[i];
-          b = rescan_near<W, KS, KD, G>(b, p, ws, lane, ax, ay, fin != 0u && cfg.auto_reset, (ws.exact & 1u) != 0u);
+          b = rescan_near<W, KS, KD, G>(b, p, ws, lane, ax, ay, fin != 0u && cfg.auto_reset, (ws.exact() & 1u) != 0u);
 #pragma unroll
           for (int i = 0; i < NW; ++i) bits[i] = b.w[i];
         }
@@ -1215,36 +1371,43 @@ __global__ void __launch_bounds__(kLeanEnvsPerBlock * G, kPolicy ? 4 : kLeanMinB
   if (mine && g == 0u) {
     reinterpret_cast<float*>(p.agent_x)[e] = ax;
     reinterpret_cast<float*>(p.agent_y)[e] = ay;
-    reinterpret_cast<float*>(p.goal_x)[e] = ws.gx[lane];
-    reinterpret_cast<float*>(p.goal_y)[e] = ws.gy[lane];
-    p.dist[e] = ws.dist[lane];
-    p.total[e] = ws.total[lane];
-    p.acc[e] = ws.acc[lane];
-    p.ep_len[e] = ws.len[lane] & 0xfffffff;
-    p.tick[e] = ws.tick[lane];
-    p.flags[e] = (uint8_t)((uint32_t)ws.len[lane] >> 28);
+    reinterpret_cast<float*>(p.goal_x)[e] = ws.gx()[lane];
+    reinterpret_cast<float*>(p.goal_y)[e] = ws.gy()[lane];
+    p.dist[e] = ws.dist()[lane];
+    p.total[e] = ws.total()[lane];
+    p.acc[e] = ws.acc()[lane];
+    p.ep_len[e] = ws.len()[lane] & 0xfffffff;
+    p.tick[e] = ws.tick()[lane];
+    p.flags[e] = (uint8_t)((uint32_t)ws.len()[lane] >> 28);
     if (e == 0u) atomicAdd(&p.stats[BALLENV_STAT_STEPS], (double)p.n * (double)n_steps);
   }
-  __syncwarp();   // the near lists are done with: ws.dm takes their place again
-#pragma unroll
-  for (int i = 0; i < NDQ; ++i) {
+  __syncwarp();   // the near lists are done with: ws.dm() takes their place again
+  auto meta_pack = [&](int i) {
     const int q = (int)g + G * i;
     if (q < QD) {
-      uint32_t fm[4];
+      uint32_t gq, cq, fm[4];
+      meta_get(i, gq, cq);
 #pragma unroll
       for (int s = 0; s < 4; ++s)
-        fm[s] = 4 * q + s < KD ? (__byte_perm(g4[i], c4[i], 0x0040 + 0x11 * s) & 0xffffu) : 0u;
-      *reinterpret_cast<uint4*>(&ws.dm[el * DS + 4 * q]) = make_uint4(fm[0], fm[1], fm[2], fm[3]);
+        fm[s] = 4 * q + s < KDv ? (__byte_perm(gq, cq, 0x0040 + 0x11 * s) & 0xffffu) : 0u;
+      *reinterpret_cast<uint4*>(&ws.dm()[el * DS + 4 * q]) = make_uint4(fm[0], fm[1], fm[2], fm[3]);
     }
+  };
+  if constexpr (kRt) {
+#pragma unroll 1
+    for (int i = 0; i < NDQ; ++i) meta_pack(i);
+  } else {
+#pragma unroll
+    for (int i = 0; i < Sh::NDQ; ++i) meta_pack(i);
   }
   bulk_fence_smem_writes();
   __syncwarp();
-  if (lane == 0) {
+  if (lane == 0 && (!kRt || DS > 0)) {
     if (rows_dirty) {
-      bulk_store(reinterpret_cast<float*>(p.dyn_x) + (size_t)e0 * DS, ws.dx, EW * DS * 4);
-      bulk_store(reinterpret_cast<float*>(p.dyn_y) + (size_t)e0 * DS, ws.dy, EW * DS * 4);
+      bulk_store(reinterpret_cast<float*>(p.dyn_x) + (size_t)e0 * DS, ws.dx(), EW * DS * 4);
+      bulk_store(reinterpret_cast<float*>(p.dyn_y) + (size_t)e0 * DS, ws.dy(), EW * DS * 4);
     }
-    bulk_store(p.dyn_meta + (size_t)e0 * DS, ws.dm, EW * DS * 4);
+    bulk_store(p.dyn_meta + (size_t)e0 * DS, ws.dm(), EW * DS * 4);
     bulk_commit();
     bulk_wait_sources_read();
   }

@@ -179,7 +179,7 @@ def test_train_fused_updates_the_policy():
     pol = Policy(5).to("cuda:0")
     before = [p.detach().clone() for p in pol.parameters()]
     losses = []
-    train_fused(env, pol, iterations=4, n_steps=16, log=lambda it, loss, batch: losses.append(float(loss)))
+    train_fused(env, pol, iterations=4, n_steps=16, log=lambda it, loss, batch: losses.append(float(loss.detach())))
     assert len(losses) == 4 and all(np.isfinite(losses))
     assert any(not torch.equal(a, b) for a, b in zip(before, pol.parameters()))
     # the evaluate() of the stored pairs is the policy's own forward pass

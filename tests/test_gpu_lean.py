@@ -308,3 +308,107 @@ def test_lean_row_formats(w, cfgname, n, fmt):
     assert env.error_flags() == 0
     env.close()
     ref.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# run-time obstacle counts (ballenv_lean_kernel<W, -1, -1, G, ..>): the same kernels for every other configuration
+def _cfg_counts(ks, kd, change=7):
+    from gym_ballenv_b200 import EnvConfig
+    goals = ["%d,%d" % (30 + (53 * i) % 440, 25 + (97 * i) % 450) for i in range(max(kd, 2) + 1)]
+    return EnvConfig(static_obstacles=ks, dynamic_obstacles=kd, obstacle_speed=[1 + (j % 3) for j in range(kd)],
+                     obs_goal_position=goals, time_step_for_change=change, rd_th_obs=55)
+
+
+@pytest.mark.parametrize("lanes", [1, 2])
+@pytest.mark.parametrize("w,ks,kd,n", [(5, 10, 7, 1000), (10, 3, 2, 333), (5, 0, 1, 64), (10, 1, 9, 200), (5, 31, 33, 150),
+                                       (10, 20, 12, 97), (5, 4, 4, 2048)])
+def test_runtime_count_lean_kernels_match_the_other_kernels(w, ks, kd, n, lanes, monkeypatch):
+    """Obstacle counts without a fixed instance: single-step launches and the rollout loop of the run-time-count lean
+    kernels against the block-of-roles kernel (single steps), bit for bit, with resets and goal changes every 7 steps."""
+    from gym_ballenv_b200 import BallVecEnv
+    cfg = _cfg_counts(ks, kd)
+    monkeypatch.setenv("BALLENV_LEAN_G", str(lanes))
+    lean = BallVecEnv(n, window=w, config=cfg, seed=9, max_episode_steps=19)
+    roll = BallVecEnv(n, window=w, config=cfg, seed=9, max_episode_steps=19)
+    monkeypatch.delenv("BALLENV_LEAN_G")
+    monkeypatch.setenv("BALLENV_NO_LEAN", "1")
+    monkeypatch.setenv("BALLENV_NO_ROLLOUT", "1")
+    ref = BallVecEnv(n, window=w, config=cfg, seed=9, max_episode_steps=19)
+    monkeypatch.delenv("BALLENV_NO_LEAN")
+    monkeypatch.delenv("BALLENV_NO_ROLLOUT")
+    assert lean.kernel_variant(1) == "lean" and roll.kernel_variant(40) == "lean" and ref.kernel_variant(1) != "lean"
+    assert torch.equal(lean.reset(), ref.reset())
+    roll.reset()
+    g = torch.Generator().manual_seed(3)
+    T = 80
+    acts = torch.randint(0, 9, (T, n), generator=g).cuda()
+    for t in range(T):
+        ol, rl, dl, il = lean.step(acts[t])
+        orf, rr, dr, ir = ref.step(acts[t])
+        assert torch.equal(ol, orf), t
+        assert torch.equal(rl, rr), t
+        assert torch.equal(dl, dr), t
+        assert torch.equal(il["flags"], ir["flags"]), t
+    _same_state(lean, ref)
+    o1, r1, d1 = roll.step_many(acts, keep_all_obs=False)
+    assert torch.equal(o1, orf)
+    _same_state(roll, ref)
+    assert lean.stats()["episodes"] > n
+    for e in (lean, roll, ref):
+        e.close()
+
+
+@pytest.mark.parametrize("w,cfgname", [(5, "default"), (10, "dense")])
+def test_runtime_count_kernels_equal_the_fixed_instances(w, cfgname, monkeypatch):
+    """BALLENV_LEAN_RT=1 sends a configuration that HAS a fixed instance through the run-time-count kernel: same results
+    (rollout with all rows kept, uint8 and bit-packed rows included)."""
+    from gym_ballenv_b200 import BallVecEnv
+    cfg = _env_config(_cfg(cfgname))
+    n, T = 1500, 70
+    for dt in (torch.float32, torch.uint8, "bits"):
+        fixed = BallVecEnv(n, window=w, config=cfg, seed=4, max_episode_steps=23, obs_dtype=dt)
+        monkeypatch.setenv("BALLENV_LEAN_RT", "1")
+        rt = BallVecEnv(n, window=w, config=cfg, seed=4, max_episode_steps=23, obs_dtype=dt)
+        monkeypatch.delenv("BALLENV_LEAN_RT")
+        assert torch.equal(fixed.reset(), rt.reset())
+        a = torch.randint(0, 9, (T, n), generator=torch.Generator().manual_seed(8)).cuda()
+        o1, r1, d1 = fixed.step_many(a, keep_all_obs=True)
+        o2, r2, d2 = rt.step_many(a, keep_all_obs=True)
+        assert torch.equal(o1, o2) and torch.equal(r1, r2) and torch.equal(d1, d2)
+        _same_state(fixed, rt)
+        fixed.close()
+        rt.close()
+
+
+def test_runtime_count_kernels_against_the_c_oracle():
+    """(10, 7) obstacles, W = 5, 2048 environments x 100 single steps with TimeLimit 13 against oracle/ballenv_oracle.c."""
+    from gym_ballenv_b200 import BallVecEnv
+    from oracle.c_oracle import COracleVec
+    from oracle.ballenv_oracle import OracleConfig, RULESET_GYM
+    cfg = _cfg_counts(10, 7)
+    n, T, seed = 2048, 100, 31
+    env = BallVecEnv(n, window=5, config=cfg, seed=seed, max_episode_steps=13)
+    assert env.kernel_variant(1) == "lean"
+    goals = [tuple(int(v) for v in s.split(",")) for s in cfg.obs_goal_position]
+    oc = OracleConfig(ruleset=RULESET_GYM, window=5, n_static=10, n_dynamic=7, speeds=list(cfg.obstacle_speed), goals=goals,
+                      change_step=cfg.time_step_for_change, rd_th_obs=cfg.rd_th_obs, static_penalty=cfg.static_penalty[1],
+                      dynamic_penalty=cfg.dynamic_penalty[1], max_episode_steps=13, auto_reset=True)
+    c = COracleVec(oc, seed, n)
+    obs = env.reset()
+    c.reset()
+    g = torch.Generator().manual_seed(2)
+    assert np.array_equal(obs.cpu().numpy(), c.observe())
+    for t in range(T):
+        a = torch.randint(0, 9, (n,), generator=g)
+        obs, rew, done, info = env.step(a.cuda())
+        r, d, f = c.step(a.numpy())
+        assert np.array_equal(obs.cpu().numpy(), c.observe()), t
+        assert np.array_equal(done.cpu().numpy(), d), t
+        assert np.array_equal(info["flags"].cpu().numpy(), f), t
+        np.testing.assert_allclose(rew.cpu().numpy(), r, rtol=1e-5, atol=0)
+    st, ref = env.get_state(), c.state()
+    assert np.array_equal(st["dist"].cpu().numpy(), ref["dist"])
+    assert np.array_equal(st["dynamic_x"].cpu().numpy().T, ref["obstacles"][:, 10:, 0].astype(np.float32))
+    assert np.array_equal(st["dynamic_counter"].cpu().numpy().T, ref["dyn_counter"])
+    assert env.error_flags() == 0
+    env.close()
