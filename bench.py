@@ -221,7 +221,7 @@ def kernel_facts(env, spec, n_steps):
     roll = n_steps > 1
     if variant == "lean":
         name = "ballenv_lean_kernel<%d,%d,%d,lanes=%d,%s>" % (w, ks, kd, lanes, "rollout" if roll else "single-step")
-        key = "_ZN7ballenv19ballenv_lean_kernelILi%dELi%dELi%dELi%dELb%dEEEvNS_6ParamsE" % (w, ks, kd, lanes, 1 if roll else 0)
+        key = "_ZN7ballenv19ballenv_lean_kernelILi%dELi%dELi%dELi%dELb%dELb0EEEvNS_6ParamsE" % (w, ks, kd, lanes, 1 if roll else 0)
     else:
         name = "ballenv_kernel<float,%d,%s,%s>" % (w, "fast" if variant == "roles" else "generic",
                                                    "rollout" if roll else "single-step")
