@@ -59,13 +59,21 @@ class BallenvPolicyMLP(C.Structure):
                 ("action_bias", C.c_void_p)]
 
 
+class BallenvA2CUpdate(C.Structure):
+    """include/ballenv.h: BallenvA2CUpdate (ballenv_a2c_grads)."""
+    _fields_ = [("n_inputs", C.c_int32), ("hidden", C.c_int32)] + [
+        (n, C.c_void_p) for n in ("fc1_weight", "fc1_bias", "action_weight", "action_bias", "value_weight", "value_bias",
+                                  "fc1_weight_grad", "fc1_bias_grad", "action_weight_grad", "action_bias_grad",
+                                  "value_weight_grad", "value_bias_grad", "loss")]
+
+
 EXPORTS = (
     "ballenv_abi_version", "ballenv_last_error", "ballenv_config_default", "ballenv_state_bytes",
     "ballenv_create", "ballenv_destroy", "ballenv_state_ptrs", "ballenv_reset", "ballenv_step",
     "ballenv_step_many", "ballenv_observe", "ballenv_observe_features", "ballenv_observe_blocks", "ballenv_step_host", "ballenv_set_draw_tape", "ballenv_stats",
     "ballenv_stats_reset", "ballenv_error_flags", "ballenv_launch_count", "ballenv_selftest", "ballenv_kernel_variant",
     "ballenv_step_many_host", "ballenv_reset_fixed", "ballenv_state_written", "ballenv_observe_patches",
-    "ballenv_rollout_policy", "ballenv_discounted_returns",
+    "ballenv_rollout_policy", "ballenv_discounted_returns", "ballenv_a2c_workspace_bytes", "ballenv_a2c_grads",
 )
 
 
@@ -91,6 +99,9 @@ def _bind(lib):
     lib.ballenv_observe_patches.argtypes = [vp, vp, i32, i32, i32, i32, vp]
     lib.ballenv_rollout_policy.argtypes = [vp, C.POINTER(BallenvPolicyMLP), i32, vp, vp, vp, vp, vp, vp]
     lib.ballenv_discounted_returns.argtypes = [vp, vp, vp, C.c_float, i32, i64, vp, vp]
+    lib.ballenv_a2c_workspace_bytes.argtypes = [i32, i32, i64]
+    lib.ballenv_a2c_workspace_bytes.restype = i64
+    lib.ballenv_a2c_grads.argtypes = [C.POINTER(BallenvA2CUpdate), vp, vp, vp, i64, vp, i64, vp]
     lib.ballenv_step_host.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp]
     lib.ballenv_step_many_host.argtypes = [vp, vp, C.c_int, i32, vp, vp, vp, vp]
     lib.ballenv_set_draw_tape.argtypes = [vp, vp, i64, vp, i64, i32]

@@ -182,25 +182,94 @@ def train_fused(env: BallVecEnv, policy: Policy, iterations: int, n_steps: int =
     return train_graphed(env, policy, iterations, n_steps, gamma, lr, log, rollout_cls=FusedRollout)
 
 
+class FusedUpdate:
+    """``a2c_loss(...).backward()`` for ``Policy`` without autograd: the loss and the gradients of all six parameter
+    tensors from hand-written kernels (ballenv_a2c_grads - forward and backward per sample on chip, per-unit sums
+    without atomics, a deterministic second pass), written straight into ``param.grad``.  The returns are prepared as
+    ``a2c_loss`` does (discounted, restarted at episode ends, bootstrapped, normalised over the batch); the advantage
+    is a constant, as in the reference (``value.item()``, examples/ball_cnn_ac3.py:234)."""
+
+    def __init__(self, policy: Policy, n_samples: int):
+        import ctypes as C
+        from . import _lib as L
+        self.policy, self.n_samples = policy, int(n_samples)
+        ps = [policy.fc1.weight, policy.fc1.bias, policy.action_head.weight, policy.action_head.bias,
+              policy.value_head.weight, policy.value_head.bias]
+        for q in ps:
+            if q.dtype != torch.float32 or not q.is_cuda or not q.is_contiguous():
+                raise ValueError("FusedUpdate needs contiguous float32 CUDA parameters")
+            if q.grad is None:
+                q.grad = torch.zeros_like(q)          # fixed buffers: the kernels overwrite them every call
+        self.params = ps
+        self.device = ps[0].device
+        hidden, n_in = policy.fc1.weight.shape
+        with torch.cuda.device(self.device):
+            nbytes = L.check(L.LIB.ballenv_a2c_workspace_bytes(n_in, hidden, self.n_samples))
+        self.workspace = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        self.loss = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self._u = L.BallenvA2CUpdate(n_in, hidden, *[q.data_ptr() for q in ps], *[q.grad.data_ptr() for q in ps],
+                                     self.loss.data_ptr())
+        self._C, self._L = C, L
+
+    def grads(self, obs: torch.Tensor, action: torch.Tensor, returns: torch.Tensor) -> torch.Tensor:
+        """obs [S, row] float32, action [S] int64, returns [S] float32 (normalised) -> loss (device scalar view); the
+        parameters' ``.grad`` hold d loss / d parameter afterwards."""
+        C, L = self._C, self._L
+        S = self.n_samples
+        if not (obs.is_contiguous() and action.is_contiguous() and returns.is_contiguous() and obs.numel() == S * obs.shape[-1]
+                and action.numel() == S and returns.numel() == S and obs.dtype == torch.float32
+                and action.dtype == torch.int64 and returns.dtype == torch.float32):
+            raise ValueError("grads needs contiguous obs [S, row] f32, action [S] i64, returns [S] f32")
+        for q, g in zip(self.params, (q.grad for q in self.params)):   # (an optimizer's zero_grad(set_to_none=True) drops them)
+            if g is None:
+                raise RuntimeError("keep the .grad buffers: call zero_grad(set_to_none=False) or none at all")
+        with torch.cuda.device(self.device):
+            L.check(L.LIB.ballenv_a2c_grads(C.byref(self._u), C.c_void_p(obs.data_ptr()), C.c_void_p(action.data_ptr()),
+                                            C.c_void_p(returns.data_ptr()), S, C.c_void_p(self.workspace.data_ptr()),
+                                            self.workspace.numel(),
+                                            C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+        return self.loss[0]
+
+
+def normalised_returns(reward: torch.Tensor, done: torch.Tensor, gamma: float, bootstrap: Optional[torch.Tensor] = None):
+    """The returns ``a2c_loss`` regresses on: discounted (restarted at episode ends, bootstrapped), then normalised by
+    the batch's mean and unbiased standard deviation + eps (examples/ball_cnn_ac3.py:228-232)."""
+    returns = discounted_returns(reward.float(), done, gamma, bootstrap)
+    return (returns - returns.mean()) / (returns.std() + EPS)
+
+
 class GraphedTrainer:
     """One whole iteration of the actor-critic loop - the fused T-step rollout (one launch), the batched
-    ``finish_episode`` update (forward over the stored pairs, discounted returns, loss, backward) and the Adam step - as
-    ONE CUDA graph, replayed per iteration: nothing is launched from Python inside the loop (the update is a few dozen
-    small kernels that are launch-bound when issued one by one).  Needs a configuration with a policy-in-the-loop
-    kernel (``BallVecEnv.rollout_policy``)."""
+    ``finish_episode`` update and the Adam step - as ONE CUDA graph, replayed per iteration: nothing is launched from
+    Python inside the loop.  ``fused_update`` (default): loss and gradients come from ``FusedUpdate`` (hand-written
+    forward + backward, two launches); otherwise from autograd over the stored pairs (``evaluate`` + ``a2c_loss`` +
+    ``backward``: a few dozen small kernels that move the hidden activations through HBM).  Needs a configuration with
+    a policy-in-the-loop kernel (``BallVecEnv.rollout_policy``)."""
 
-    def __init__(self, env: BallVecEnv, policy: Policy, n_steps: int = 32, gamma: float = 0.99, lr: float = 1e-3):
+    def __init__(self, env: BallVecEnv, policy: Policy, n_steps: int = 32, gamma: float = 0.99, lr: float = 1e-3,
+                 fused_update: bool = True):
         self.env, self.policy, self.n_steps, self.gamma = env, policy, n_steps, gamma
         self.opt = torch.optim.Adam(policy.parameters(), lr=lr, capturable=True)
         self.roll = FusedRollout(env, policy, n_steps)
         self.loss = torch.zeros((), dtype=torch.float32, device=env.device)
+        self.update = FusedUpdate(policy, n_steps * env.num_envs) if fused_update else None
         self.graph = None
 
     def _body(self):
         raw = self.roll.run()
+        T = self.n_steps
+        if self.update is not None:
+            # the update without autograd: returns as a2c_loss prepares them, then loss + gradients in two launches
+            with torch.no_grad():
+                _, v_last = self.policy(raw["obs"][T])
+                returns = normalised_returns(raw["reward"], self.roll.done, self.gamma, bootstrap=v_last.squeeze(-1))
+            loss = self.update.grads(raw["obs"][:T], raw["action"], returns)
+            self.opt.step()
+            self.loss.copy_(loss)
+            return
         batch = self.roll.evaluate(raw)
         with torch.no_grad():
-            _, v_last = self.policy(raw["obs"][self.n_steps])
+            _, v_last = self.policy(raw["obs"][T])
         loss = a2c_loss(batch, self.gamma, bootstrap=v_last.squeeze(-1))
         self.opt.zero_grad(set_to_none=True)
         loss.backward()
@@ -219,7 +288,8 @@ class GraphedTrainer:
                     self._body()
             torch.cuda.current_stream(dev).wait_stream(side)
             self.graph = torch.cuda.CUDAGraph()
-            self.opt.zero_grad(set_to_none=True)
+            if self.update is None:
+                self.opt.zero_grad(set_to_none=True)
             with torch.cuda.graph(self.graph):
                 self._body()
             return self.loss

@@ -39,7 +39,7 @@ LEAN_RT_WINDOWS = [5, 10]
 
 def _sources():
     deps = [os.path.join(CSRC, f) for f in ("ballenv_kernels.cuh", "ballenv_rng.cuh", "ballenv_lean.cuh", "ballenv_lean_rt.cuh",
-                                            "ballenv_features.cuh", "ballenv_patches.cuh", "ballenv_reset_fixed.cuh")]
+                                            "ballenv_features.cuh", "ballenv_patches.cuh", "ballenv_reset_fixed.cuh", "ballenv_a2c.cuh")]
     deps.append(os.path.join(os.path.dirname(HERE), "include", "ballenv.h"))
     jobs = [(os.path.join(CSRC, "ballenv_capi.cu"), os.path.join(OBJ, "ballenv_capi.o"), [])]
     for t, w, fast, name in INSTANCES:

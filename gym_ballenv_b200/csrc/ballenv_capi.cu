@@ -12,6 +12,7 @@
 #include "ballenv_features.cuh"
 #include "ballenv_lean.cuh"
 #include "ballenv_patches.cuh"
+#include "ballenv_a2c.cuh"
 #include "ballenv_reset_fixed.cuh"
 
 using namespace ballenv;
@@ -1195,6 +1196,86 @@ int ballenv_discounted_returns(const float* reward, const uint8_t* done, const f
   if (n_steps < 0 || n < 0) return fail(BALLENV_EINVAL, "negative size");
   if (n_steps == 0 || n == 0) return BALLENV_OK;
   discounted_returns_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(reward, done, bootstrap, gamma, n_steps, n, out);
+  CUDA_TRY(cudaGetLastError());
+  return BALLENV_OK;
+}
+
+namespace {
+int a2c_grid(int n_in, int hidden, int tile, int nw, int64_t n_samples, size_t* smem_out) {
+  const size_t smem = a2c::smem_bytes(n_in, hidden, tile, nw);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int per_sm = (int)((220 * 1024) / (smem + 1024));
+  if (per_sm > 4) per_sm = 4;
+  if (per_sm < 1) per_sm = 1;
+  int64_t grid = (int64_t)sms * per_sm;
+  const int64_t tiles = (n_samples + tile - 1) / tile;
+  if (grid > tiles) grid = tiles;
+  if (smem_out != nullptr) *smem_out = smem;
+  return (int)(grid < 1 ? 1 : grid);
+}
+int a2c_tile(int hidden) { return hidden <= 128 ? 128 : (hidden + 31) / 32 * 32; }
+}  // namespace
+
+int64_t ballenv_a2c_workspace_bytes(int32_t n_inputs, int32_t hidden, int64_t n_samples) {
+  if (n_inputs < 1 || hidden < 4 || hidden > a2c::kMaxHidden || (hidden & 3) != 0 || n_samples < 0) return fail(BALLENV_EINVAL, "bad policy shape");
+  const int grid = a2c_grid(n_inputs, hidden, a2c_tile(hidden), (n_inputs + 31) / 32, n_samples > 0 ? n_samples : 1, nullptr);
+  return (int64_t)grid * (a2c::n_params(n_inputs, hidden) + 1) * 4;
+}
+
+int ballenv_a2c_grads(const BallenvA2CUpdate* u, const float* obs, const int64_t* actions, const float* returns,
+                      int64_t n_samples, void* workspace, int64_t workspace_bytes, ballenv_stream_t stream) {
+  if (u == nullptr || obs == nullptr || actions == nullptr || returns == nullptr || workspace == nullptr)
+    return fail(BALLENV_EINVAL, "NULL argument");
+  const void* ptrs[] = {u->fc1_weight, u->fc1_bias, u->action_weight, u->action_bias, u->value_weight, u->value_bias,
+                        u->fc1_weight_grad, u->fc1_bias_grad, u->action_weight_grad, u->action_bias_grad, u->value_weight_grad,
+                        u->value_bias_grad, u->loss};
+  for (const void* q : ptrs)
+    if (q == nullptr) return fail(BALLENV_EINVAL, "NULL policy parameter / gradient pointer");
+  const int nw = (u->n_inputs + 31) / 32;
+  if (u->n_inputs < 1 || (nw != 1 && nw != 4)) return fail(BALLENV_EINVAL, "n_inputs must be 4 + W*W for WINDOW = 5 (29) or up to 128 (WINDOW = 10: 104)");
+  if (u->hidden < 4 || u->hidden > a2c::kMaxHidden || (u->hidden & 3) != 0) return fail(BALLENV_EINVAL, "hidden must be a multiple of 4 in 4..%d", a2c::kMaxHidden);
+  if (n_samples < 1) return fail(BALLENV_EINVAL, "n_samples < 1");
+  const int tile = a2c_tile(u->hidden);
+  size_t smem = 0;
+  const int grid = a2c_grid(u->n_inputs, u->hidden, tile, nw, n_samples, &smem);
+  const int P = a2c::n_params(u->n_inputs, u->hidden);
+  if (workspace_bytes < (int64_t)grid * (P + 1) * 4) return fail(BALLENV_EINVAL, "workspace too small: ballenv_a2c_workspace_bytes");
+  if (smem > 220 * 1024) return fail(BALLENV_EINVAL, "the policy does not fit in shared memory");
+  a2c::Args a;
+  a.n_in = u->n_inputs;
+  a.hidden = u->hidden;
+  a.tile = tile;
+  a.n_samples = n_samples;
+  a.fc1_w = u->fc1_weight;
+  a.fc1_b = u->fc1_bias;
+  a.act_w = u->action_weight;
+  a.act_b = u->action_bias;
+  a.val_w = u->value_weight;
+  a.val_b = u->value_bias;
+  a.obs = obs;
+  a.action = reinterpret_cast<const long long*>(actions);
+  a.ret = returns;
+  a.partial = reinterpret_cast<float*>(workspace);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (nw == 1) {
+    CUDA_TRY(cudaFuncSetAttribute(a2c::grad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    a2c::grad_kernel<1><<<grid, tile, smem, s>>>(a);
+  } else {
+    CUDA_TRY(cudaFuncSetAttribute(a2c::grad_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    a2c::grad_kernel<4><<<grid, tile, smem, s>>>(a);
+  }
+  CUDA_TRY(cudaGetLastError());
+  a2c::Outs o;
+  o.fc1_w = u->fc1_weight_grad;
+  o.fc1_b = u->fc1_bias_grad;
+  o.act_w = u->action_weight_grad;
+  o.act_b = u->action_bias_grad;
+  o.val_w = u->value_weight_grad;
+  o.val_b = u->value_bias_grad;
+  o.loss = u->loss;
+  a2c::reduce_kernel<<<(P + 1 + 255) / 256, 256, 0, s>>>(a.partial, grid, u->n_inputs, u->hidden, o);
   CUDA_TRY(cudaGetLastError());
   return BALLENV_OK;
 }

@@ -257,6 +257,29 @@ int ballenv_rollout_policy(BallenvHandle *h, const BallenvPolicyMLP *policy, int
 int ballenv_discounted_returns(const float *reward, const uint8_t *done, const float *bootstrap, float gamma,
                                int32_t n_steps, int64_t n, float *out, ballenv_stream_t stream);
 
+/*
+ * Replaces: finish_episode's loss and its backward pass (examples/ball_cnn_ac3.py:233-244: policy loss
+ * -log_prob(a) * (R - V.item()), value loss smooth_l1(V, R), summed over the steps, loss.backward()) for Policy(window)
+ * (:109-146), over n_samples (observation, action, return) triples at once - hand-written forward + backward, no
+ * activation ever leaves the chip.  All pointers device, float32, on the CURRENT device, in nn.Linear layout; the *_grad
+ * arrays and loss[0] are OVERWRITTEN (not accumulated).  returns: the normalised discounted returns (:228-232).
+ * workspace: ballenv_a2c_workspace_bytes(n_inputs, hidden, n_samples) bytes of device memory.  The gradients are sums
+ * in a fixed order (deterministic); they agree with autograd's to float32 rounding of the summation order.
+ * n_inputs: 4 + WINDOW^2 with WINDOW = 5 or 10; hidden: a multiple of 4, at most 256.
+ */
+typedef struct BallenvA2CUpdate {
+  int32_t n_inputs, hidden;
+  const float *fc1_weight, *fc1_bias;         /* [hidden][n_inputs], [hidden] */
+  const float *action_weight, *action_bias;   /* [9][hidden], [9] */
+  const float *value_weight, *value_bias;     /* [1][hidden], [1] */
+  float *fc1_weight_grad, *fc1_bias_grad, *action_weight_grad, *action_bias_grad, *value_weight_grad, *value_bias_grad;
+  float *loss;                                /* [1] */
+} BallenvA2CUpdate;
+int64_t ballenv_a2c_workspace_bytes(int32_t n_inputs, int32_t hidden, int64_t n_samples);
+int ballenv_a2c_grads(const BallenvA2CUpdate *u, const float *obs /* [n_samples][n_inputs] */,
+                      const int64_t *actions /* [n_samples] */, const float *returns /* [n_samples] */, int64_t n_samples,
+                      void *workspace, int64_t workspace_bytes, ballenv_stream_t stream);
+
 /* prep_state4 on the current state without stepping (examples/ball_cnn_ac3.py:384-412). */
 int ballenv_observe(BallenvHandle *h, void *obs_out, ballenv_stream_t stream);
 

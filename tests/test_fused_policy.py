@@ -227,7 +227,7 @@ def test_graphed_trainer_is_the_eager_iteration():
         pol = Policy(5).to("cuda:0")
         losses = []
         if graphed:
-            tr = GraphedTrainer(env, pol, n_steps=8)
+            tr = GraphedTrainer(env, pol, n_steps=8, fused_update=False)
             tr.step()                       # three eager iterations + the capture
             for _ in range(4):
                 losses.append(float(tr.step()))
@@ -252,3 +252,60 @@ def test_graphed_trainer_is_the_eager_iteration():
     assert np.allclose(la, lb, rtol=1e-4), (la, lb)
     for a, b in zip(pa, pb):
         assert torch.allclose(a, b, rtol=1e-3, atol=1e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("window,n,T", [(5, 3000, 13), (10, 700, 9), (5, 100, 1)])
+def test_fused_update_is_autograd(window, n, T):
+    """ballenv_a2c_grads against torch.autograd on the same batch: the loss of a2c_loss and the gradient of every parameter
+    (float32 sums of up to 39 000 terms in another order: 2e-4 relative to the gradient's scale)."""
+    import torch
+    from gym_ballenv_b200.a2c import FusedRollout, FusedUpdate, a2c_loss, normalised_returns
+    env, torch = _make(n, window=window)
+    env.reset()
+    pol = _policy(torch, window=window, scale=1.5)
+    roll = FusedRollout(env, pol, T)
+    raw = roll.run()
+    with torch.no_grad():
+        _, v_last = pol(raw["obs"][T])
+    batch = roll.evaluate(raw)
+    loss = a2c_loss(batch, 0.99, bootstrap=v_last.squeeze(-1))
+    pol.zero_grad(set_to_none=True)
+    loss.backward()
+    want = [p.grad.detach().clone() for p in pol.parameters()]
+    pol.zero_grad(set_to_none=True)
+    upd = FusedUpdate(pol, T * n)
+    returns = normalised_returns(raw["reward"], roll.done, 0.99, bootstrap=v_last.squeeze(-1))
+    got_loss = upd.grads(raw["obs"][:T], raw["action"], returns)
+    assert torch.allclose(got_loss, loss.detach(), rtol=2e-4), (float(got_loss), float(loss))
+    for (name, p), w in zip(pol.named_parameters(), want):
+        scale = float(w.abs().max())
+        assert scale > 0, name
+        assert float((p.grad - w).abs().max()) <= 2e-4 * scale, (name, float((p.grad - w).abs().max()), scale)
+    # deterministic: a second call gives the same bits
+    g1 = [p.grad.clone() for p in pol.parameters()]
+    upd.grads(raw["obs"][:T], raw["action"], returns)
+    assert all(torch.equal(a, p.grad) for a, p in zip(g1, pol.parameters()))
+    env.close()
+
+
+@pytest.mark.gpu
+def test_graphed_trainer_with_the_fused_update_learns_like_autograd():
+    """Whole iterations: rollout launch + FusedUpdate + Adam replayed as one graph against the autograd update - same
+    rollouts (deterministic draws), losses and weights equal to float32 rounding after the same number of iterations."""
+    from gym_ballenv_b200.a2c import GraphedTrainer, Policy
+    out = []
+    for fused in (True, False):
+        env, torch = _make(2048)
+        env.reset()
+        torch.manual_seed(0)
+        pol = Policy(5).to("cuda:0")
+        tr = GraphedTrainer(env, pol, n_steps=8, fused_update=fused)
+        losses = [float(tr.step()) for _ in range(5)]
+        out.append((losses, [p.detach().clone() for p in pol.parameters()]))
+        assert env.error_flags() == 0
+        env.close()
+    (la, pa), (lb, pb) = out
+    assert np.allclose(la, lb, rtol=1e-3), (la, lb)
+    for a, b in zip(pa, pb):
+        assert torch.allclose(a, b, rtol=1e-2, atol=1e-4)

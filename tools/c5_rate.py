@@ -53,7 +53,8 @@ env = BallVecEnv(N, window=5, seed=0, device="cuda:0")
 env.reset()
 torch.manual_seed(0)
 pol = Policy(5).to("cuda:0")
-tr = GraphedTrainer(env, pol, T)
+FUSED = os.environ.get("FUSED_UPDATE", "1") == "1"
+tr = GraphedTrainer(env, pol, T, fused_update=FUSED)
 tr.step()
 tr.step()
 torch.cuda.synchronize()
@@ -64,5 +65,5 @@ for _ in range(20):
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 20
-print("GraphedTrainer  lanes=2 n=%d: iteration %.3f ms (%.1f M env-steps/s) loss %.4f errs=%d" % (N, ms, N * T / ms / 1e3, float(loss), env.error_flags()))
+print(("GraphedTrainer fused_update=%s " % FUSED) + "lanes=2 n=%d: iteration %.3f ms (%.1f M env-steps/s) loss %.4f errs=%d" % (N, ms, N * T / ms / 1e3, float(loss), env.error_flags()))
 env.close()
