@@ -355,10 +355,11 @@ def measure_c5(torch, dev, iterations=12, n_steps=32, n=16384):
     """BASELINE.json config 5: the actor-critic loop of examples/ball_cnn_ac3.py:528-646 driving 16 K GPU environments
     end to end.  An iteration = one n_steps-step policy-in-the-loop rollout of all environments - ONE launch
     (ballenv_rollout_policy: the environments' own lanes evaluate Policy(5) and draw the action between two steps) - and
-    the batched finish_episode update (forward over the stored pairs with autograd, discounted returns, loss, backward,
-    Adam), the whole iteration replayed as one CUDA graph (a2c.GraphedTrainer).  Beside it: the rollout alone, and the
-    same iteration with the per-step torch policy (GraphedRollout: Policy forward + multinomial + ballenv_step per
-    env-step, replayed as a graph; what this leg measured before the fused launch existed)."""
+    the batched finish_episode update: discounted returns (ballenv_discounted_returns), normalisation, loss and all
+    gradients from hand-written kernels (ballenv_a2c_grads: two launches, checked against autograd), torch's Adam; the
+    whole iteration replayed as one CUDA graph (a2c.GraphedTrainer).  Beside it: the rollout alone, the same iteration
+    with the autograd update, and with the per-step torch policy (GraphedRollout: Policy forward + multinomial +
+    ballenv_step per env-step, replayed as a graph; what this leg measured before the fused launches existed)."""
     from gym_ballenv_b200 import BallVecEnv
     from gym_ballenv_b200.a2c import FusedRollout, GraphedRollout, GraphedTrainer, Policy, a2c_loss
 
@@ -387,6 +388,16 @@ def measure_c5(torch, dev, iterations=12, n_steps=32, n=16384):
     ms_roll, _ = timed(roll.run, iterations)
     errs = env.error_flags()
     env.close()
+    torch.manual_seed(0)
+    env = BallVecEnv(n, window=5, seed=0, device=dev)
+    policy_ag = Policy(5).to(dev)
+    env.reset()
+    trainer_ag = GraphedTrainer(env, policy_ag, n_steps, fused_update=False)
+    trainer_ag.step()
+    trainer_ag.step()
+    ms_ag, _ = timed(trainer_ag.step, iterations)
+    errs |= env.error_flags()
+    env.close()
 
     # the per-step torch policy, for comparison
     torch.manual_seed(0)
@@ -413,16 +424,18 @@ def measure_c5(torch, dev, iterations=12, n_steps=32, n=16384):
     env.close()
     return {"workload": "config 5: 16384 envs, WINDOW=5, reference defaults (13 + 5 obstacles), Policy(5) MLP 29-128-{9,1} in "
                         "the loop (Categorical by inverse CDF of the env's Philox stream), %d-step rollouts in ONE launch "
-                        "(ballenv_rollout_policy), batched finish_episode + Adam per rollout, the iteration replayed as one "
-                        "CUDA graph" % n_steps,
+                        "(ballenv_rollout_policy), batched finish_episode (loss + gradients by ballenv_a2c_grads) + Adam per "
+                        "rollout, the iteration replayed as one CUDA graph" % n_steps,
             "value": n * n_steps / (ms_it * 1e-3), "unit": UNIT, "ms_per_iteration": ms_it,
             "rollout_only": {"value": n * n_steps / (ms_roll * 1e-3), "unit": UNIT, "ms_per_rollout": ms_roll,
                              "us_per_env_step_of_all_envs": ms_roll * 1e3 / n_steps},
+            "autograd_update": {"value": n * n_steps / (ms_ag * 1e-3), "unit": UNIT, "ms_per_iteration": ms_ag,
+                                "what": "same rollout launch, update by torch autograd over the stored pairs"},
             "torch_policy_per_step": {"value": n * n_steps / (ms_torch * 1e-3), "unit": UNIT, "ms_per_iteration": ms_torch,
                                       "what": "GraphedRollout: torch Policy forward + multinomial + ballenv_step per env-step "
                                               "(one CUDA graph per rollout), same update issued eagerly"},
             "env_kernel": "ballenv_lean_kernel<5,13,5,lanes=2,rollout,policy>",
-            "gpu_launches_per_iteration": 1, "iterations": iterations,
+            "gpu_launches_per_iteration": 4, "iterations": iterations,
             "loss_finite": bool(torch.isfinite(loss).item()), "device_error_flags": errs}
 
 

@@ -235,13 +235,21 @@ struct Outs {
   float *fc1_w, *fc1_b, *act_w, *act_b, *val_w, *val_b, *loss;
 };
 
-// sums of the blocks' partials, in double, in block order: one thread per parameter
+// sums of the blocks' partials, in double, in a fixed order: 32 parameters per block of 256 threads, eight threads per
+// parameter each adding every eighth block's partial, then the eight in order (deterministic; 592 partials per
+// parameter summed by one thread were a 47 us chain of dependent loads)
 __global__ void __launch_bounds__(256) reduce_kernel(const float* __restrict__ partial, int n_blocks, int n_in, int hidden, Outs o) {
+  __shared__ double part[8][32];
   const int P = n_params(n_in, hidden);
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i > P) return;
+  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + lane;
   double t = 0.0;
-  for (int b = 0; b < n_blocks; ++b) t += (double)partial[(size_t)b * (P + 1) + i];
+  if (i <= P)
+    for (int b = slice; b < n_blocks; b += 8) t += (double)partial[(size_t)b * (P + 1) + i];
+  part[slice][lane] = t;
+  __syncthreads();
+  if (slice != 0 || i > P) return;
+  for (int q = 1; q < 8; ++q) t += part[q][lane];
   const float v = (float)t;
   const int H = hidden, NB = n_in;
   if (i < NB * H) o.fc1_w[i] = v;

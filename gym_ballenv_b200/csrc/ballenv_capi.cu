@@ -1275,7 +1275,7 @@ int ballenv_a2c_grads(const BallenvA2CUpdate* u, const float* obs, const int64_t
   o.val_w = u->value_weight_grad;
   o.val_b = u->value_bias_grad;
   o.loss = u->loss;
-  a2c::reduce_kernel<<<(P + 1 + 255) / 256, 256, 0, s>>>(a.partial, grid, u->n_inputs, u->hidden, o);
+  a2c::reduce_kernel<<<(P + 1 + 31) / 32, 256, 0, s>>>(a.partial, grid, u->n_inputs, u->hidden, o);
   CUDA_TRY(cudaGetLastError());
   return BALLENV_OK;
 }
