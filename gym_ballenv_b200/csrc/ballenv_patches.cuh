@@ -135,6 +135,7 @@ __host__ __device__ inline size_t patch_smem_bytes(int width, int out, int ksize
   b += 4 * ((size_t)out * ksize + 2 * out);            // coefficients, bounds
   b += 4 * (size_t)out;                                // the horizontal result of an all-white row
   b += 4 * 2 * (size_t)width;                          // per row: first / last painted column
+  b += 4 * 2 * (size_t)out;                            // per result column: first / last source row that is not white
   b += 4 * 8;                                          // block-wide ranges
   b += 12 * (size_t)n_objects;                         // objects: x, y, kind
   return b;
@@ -161,7 +162,9 @@ __global__ void __launch_bounds__(kPatchThreads) ballenv_patch_kernel(const __gr
   int* const white = bounds + 2 * O;
   int* const rowlo = white + O;
   int* const rowhi = rowlo + W;
-  int* const rng = rowhi + W;     // 0 / 1: first / last painted row; 2 / 3: first / last painted column
+  int* const collo = rowhi + W;   // per result column: first / last row of the horizontal pass that is not white
+  int* const colhi = collo + O;
+  int* const rng = colhi + O;     // 0 / 1: first / last painted row; 2 / 3: first / last painted column; 4..7: result ranges
   int* const obj = rng + 8;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int kWarps = kPatchThreads / 32;
@@ -201,11 +204,19 @@ __global__ void __launch_bounds__(kPatchThreads) ballenv_patch_kernel(const __gr
     for (int i = tid; i < (W * W + 3) / 4; i += kPatchThreads) c4[i] = 0x07070707u;   // white; also the padding (:137)
     uint32_t* const r4 = reinterpret_cast<uint32_t*>(res);
     for (int i = tid; i < (3 * O * O + 3) / 4; i += kPatchThreads) r4[i] = 0xffffffffu;
+    for (int i = tid; i < O; i += kPatchThreads) {
+      collo[i] = W;
+      colhi[i] = -1;
+    }
     if (tid == 0) {
       rng[0] = W;
       rng[1] = -1;
       rng[2] = W;
       rng[3] = -1;
+      rng[4] = O;
+      rng[5] = -1;
+      rng[6] = O;
+      rng[7] = -1;
     }
   }
   __syncthreads();
@@ -261,21 +272,23 @@ __global__ void __launch_bounds__(kPatchThreads) ballenv_patch_kernel(const __gr
     // result rows / columns whose support [first, first + count) meets the painted rows / columns (supports move
     // monotonically with the index), then the source rows those result rows read
     const int i0 = rng[0], i1 = rng[1], j0 = rng[2], j1 = rng[3];
-    int XA = O, XB = -1, YA = O, YB = -1;
-    for (int xx = 0; xx < O; ++xx) {
+    for (int xx = tid; xx < O; xx += kPatchThreads) {
       const int f = bounds[2 * xx], c = bounds[2 * xx + 1];
       if (f + c > j0 && f <= j1) {
-        XA = min(XA, xx);
-        XB = xx;
+        atomicMin(&rng[4], xx);
+        atomicMax(&rng[5], xx);
       }
       if (f + c > i0 && f <= i1) {
-        YA = min(YA, xx);
-        YB = xx;
+        atomicMin(&rng[6], xx);
+        atomicMax(&rng[7], xx);
       }
     }
+    __syncthreads();
+    const int XA = rng[4], XB = rng[5], YA = rng[6], YB = rng[7];
     if (XB >= 0 && YB >= 0) {
       const int I0 = bounds[2 * YA], I1 = bounds[2 * YB] + bounds[2 * YB + 1] - 1;
-      // ---- horizontal pass (Resample.c: ImagingResampleHorizontal_8bpc) into uint8 [3][W][O], the needed part
+      // ---- horizontal pass (Resample.c: ImagingResampleHorizontal_8bpc) into uint8 [3][W][O], the needed part; per
+      //      result column the rows whose value is not the all-white one are remembered
       for (int i = I0 + warp; i <= I1; i += kWarps) {
         const int lo = rowlo[i], hi = rowhi[i];
         for (int xx = XA + lane; xx <= XB; xx += 32) {
@@ -284,18 +297,24 @@ __global__ void __launch_bounds__(kPatchThreads) ballenv_patch_kernel(const __gr
           if (hi < 0 || xmin + cnt <= lo || xmin > hi) {
             v0 = v1 = v2 = white[xx];
           } else {
-            int s0 = 1 << (kPatchPrecisionBits - 1), s1 = s0, s2 = s0;
+            // colour codes: 7 white, 1 red, 2 green, 0 black - sums of the weights by code, 255 factored out
+            int tw = 0, tr = 0, tg = 0;
             const unsigned char* const src = cls + (size_t)i * W + xmin;
             const int* const k = coef + xx * KZ;
             for (int x = 0; x < cnt; ++x) {
-              const int c = src[x], kv = 255 * k[x];
-              s0 += (c & 1) ? kv : 0;
-              s1 += (c & 2) ? kv : 0;
-              s2 += (c & 4) ? kv : 0;
+              const int c = src[x], kv = k[x];
+              tw += c == 7 ? kv : 0;
+              tr += c == 1 ? kv : 0;
+              tg += c == 2 ? kv : 0;
             }
-            v0 = min(max(s0 >> kPatchPrecisionBits, 0), 255);
-            v1 = min(max(s1 >> kPatchPrecisionBits, 0), 255);
-            v2 = min(max(s2 >> kPatchPrecisionBits, 0), 255);
+            const int half = 1 << (kPatchPrecisionBits - 1);
+            v0 = min(max((half + 255 * (tw + tr)) >> kPatchPrecisionBits, 0), 255);
+            v1 = min(max((half + 255 * (tw + tg)) >> kPatchPrecisionBits, 0), 255);
+            v2 = min(max((half + 255 * tw) >> kPatchPrecisionBits, 0), 255);
+            if (v0 != white[xx] || v1 != white[xx] || v2 != white[xx]) {
+              atomicMin(&collo[xx], i);
+              atomicMax(&colhi[xx], i);
+            }
           }
           hor[i * O + xx] = (unsigned char)v0;
           hor[W * O + i * O + xx] = (unsigned char)v1;
@@ -303,16 +322,24 @@ __global__ void __launch_bounds__(kPatchThreads) ballenv_patch_kernel(const __gr
         }
       }
       __syncthreads();
-      // ---- vertical pass (ImagingResampleVertical_8bpc) into the result
-      for (int r = warp; r < 3 * (YB - YA + 1); r += kWarps) {
-        const int ch = r / (YB - YA + 1), yy = YA + r - ch * (YB - YA + 1);
+      // ---- vertical pass (ImagingResampleVertical_8bpc) into the result: only where the support of the result row
+      //      meets the column's non-white rows (the rest is the all-white value the result was initialised with)
+      for (int yy = YA + warp; yy <= YB; yy += kWarps) {
         const int ymin = bounds[2 * yy], cnt = bounds[2 * yy + 1];
         const int* const k = coef + yy * KZ;
         for (int xx = XA + lane; xx <= XB; xx += 32) {
-          const unsigned char* const src = hor + (size_t)ch * W * O + (size_t)ymin * O + xx;
-          int s = 1 << (kPatchPrecisionBits - 1);
-          for (int y = 0; y < cnt; ++y) s += (int)src[y * O] * k[y];
-          res[ch * O * O + yy * O + xx] = (unsigned char)min(max(s >> kPatchPrecisionBits, 0), 255);
+          if (ymin + cnt <= collo[xx] || ymin > colhi[xx]) continue;
+          const unsigned char* const src = hor + (size_t)ymin * O + xx;
+          int s0 = 1 << (kPatchPrecisionBits - 1), s1 = s0, s2 = s0;
+          for (int y = 0; y < cnt; ++y) {
+            const int kv = k[y];
+            s0 += (int)src[y * O] * kv;
+            s1 += (int)src[W * O + y * O] * kv;
+            s2 += (int)src[2 * W * O + y * O] * kv;
+          }
+          res[yy * O + xx] = (unsigned char)min(max(s0 >> kPatchPrecisionBits, 0), 255);
+          res[O * O + yy * O + xx] = (unsigned char)min(max(s1 >> kPatchPrecisionBits, 0), 255);
+          res[2 * O * O + yy * O + xx] = (unsigned char)min(max(s2 >> kPatchPrecisionBits, 0), 255);
         }
       }
     }
