@@ -64,7 +64,7 @@ class BallenvA2CUpdate(C.Structure):
     _fields_ = [("n_inputs", C.c_int32), ("hidden", C.c_int32)] + [
         (n, C.c_void_p) for n in ("fc1_weight", "fc1_bias", "action_weight", "action_bias", "value_weight", "value_bias",
                                   "fc1_weight_grad", "fc1_bias_grad", "action_weight_grad", "action_bias_grad",
-                                  "value_weight_grad", "value_bias_grad", "loss")]
+                                  "value_weight_grad", "value_bias_grad", "loss", "returns_stats")]
 
 
 EXPORTS = (

@@ -207,14 +207,24 @@ class FusedUpdate:
             nbytes = L.check(L.LIB.ballenv_a2c_workspace_bytes(n_in, hidden, self.n_samples))
         self.workspace = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
         self.loss = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self.stats = torch.zeros(2, dtype=torch.float32, device=self.device)     # {mean, std + eps} of raw returns
         self._u = L.BallenvA2CUpdate(n_in, hidden, *[q.data_ptr() for q in ps], *[q.grad.data_ptr() for q in ps],
-                                     self.loss.data_ptr())
+                                     self.loss.data_ptr(), None)
         self._C, self._L = C, L
 
-    def grads(self, obs: torch.Tensor, action: torch.Tensor, returns: torch.Tensor) -> torch.Tensor:
-        """obs [S, row] float32, action [S] int64, returns [S] float32 (normalised) -> loss (device scalar view); the
-        parameters' ``.grad`` hold d loss / d parameter afterwards."""
+    def grads(self, obs: torch.Tensor, action: torch.Tensor, returns: torch.Tensor, normalise: bool = False) -> torch.Tensor:
+        """obs [S, row] float32, action [S] int64, returns [S] float32 -> loss (device scalar view); the parameters'
+        ``.grad`` hold d loss / d parameter afterwards.  ``returns`` are the normalised returns, or with
+        ``normalise=True`` the raw discounted ones: their mean and unbiased std + eps are taken here (one reduction) and
+        the kernel forms (R - mean) / (std + eps) itself (examples/ball_cnn_ac3.py:231-232)."""
         C, L = self._C, self._L
+        if normalise:
+            var, mean = torch.var_mean(returns.reshape(-1))
+            self.stats[0] = mean
+            self.stats[1] = var.sqrt() + EPS
+            self._u.returns_stats = self.stats.data_ptr()
+        else:
+            self._u.returns_stats = None
         S = self.n_samples
         if not (obs.is_contiguous() and action.is_contiguous() and returns.is_contiguous() and obs.numel() == S * obs.shape[-1]
                 and action.numel() == S and returns.numel() == S and obs.dtype == torch.float32
@@ -249,7 +259,8 @@ class GraphedTrainer:
     def __init__(self, env: BallVecEnv, policy: Policy, n_steps: int = 32, gamma: float = 0.99, lr: float = 1e-3,
                  fused_update: bool = True):
         self.env, self.policy, self.n_steps, self.gamma = env, policy, n_steps, gamma
-        self.opt = torch.optim.Adam(policy.parameters(), lr=lr, capturable=True)
+        # (fused: the whole Adam step of the six tensors is one kernel)
+        self.opt = torch.optim.Adam(policy.parameters(), lr=lr, capturable=True, fused=bool(fused_update))
         self.roll = FusedRollout(env, policy, n_steps)
         self.loss = torch.zeros((), dtype=torch.float32, device=env.device)
         self.update = FusedUpdate(policy, n_steps * env.num_envs) if fused_update else None
@@ -262,8 +273,8 @@ class GraphedTrainer:
             # the update without autograd: returns as a2c_loss prepares them, then loss + gradients in two launches
             with torch.no_grad():
                 _, v_last = self.policy(raw["obs"][T])
-                returns = normalised_returns(raw["reward"], self.roll.done, self.gamma, bootstrap=v_last.squeeze(-1))
-            loss = self.update.grads(raw["obs"][:T], raw["action"], returns)
+                returns = discounted_returns(raw["reward"], self.roll.done, self.gamma, bootstrap=v_last.squeeze(-1))
+                loss = self.update.grads(raw["obs"][:T], raw["action"], returns, normalise=True)
             self.opt.step()
             self.loss.copy_(loss)
             return

@@ -38,7 +38,8 @@ struct Args {
   const float *fc1_w, *fc1_b, *act_w, *act_b, *val_w, *val_b;
   const float* obs;           // [S][n_in]
   const long long* action;    // [S]
-  const float* ret;           // [S] normalised returns
+  const float* ret;           // [S] returns: normalised already, or raw with ret_stats = {mean, std + eps} on the device
+  const float* ret_stats;     // nullptr, or [2]: R = (ret - mean) / (std + eps) is formed here (:231-232)
   float* partial;             // [grid][n_params + 1]
 };
 
@@ -145,7 +146,9 @@ __global__ void __launch_bounds__(kMaxHidden) grad_kernel(const Args a) {
         sum += e[j];
       }
       const int act = valid ? (int)a.action[s] : 0;
-      const float R = valid ? a.ret[s] : 0.0f, v = acc[9];
+      float R = valid ? a.ret[s] : 0.0f;
+      if (a.ret_stats != nullptr) R = valid ? __fdiv_rn(__fsub_rn(R, a.ret_stats[0]), a.ret_stats[1]) : 0.0f;
+      const float v = acc[9];
       const float adv = R - v;                                  // :234 reward = r - value.item()
       float la = acc[0];
 #pragma unroll

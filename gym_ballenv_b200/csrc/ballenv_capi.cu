@@ -1257,6 +1257,7 @@ int ballenv_a2c_grads(const BallenvA2CUpdate* u, const float* obs, const int64_t
   a.obs = obs;
   a.action = reinterpret_cast<const long long*>(actions);
   a.ret = returns;
+  a.ret_stats = u->returns_stats;
   a.partial = reinterpret_cast<float*>(workspace);
   cudaStream_t s = (cudaStream_t)stream;
   if (nw == 1) {

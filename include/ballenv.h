@@ -262,7 +262,8 @@ int ballenv_discounted_returns(const float *reward, const uint8_t *done, const f
  * -log_prob(a) * (R - V.item()), value loss smooth_l1(V, R), summed over the steps, loss.backward()) for Policy(window)
  * (:109-146), over n_samples (observation, action, return) triples at once - hand-written forward + backward, no
  * activation ever leaves the chip.  All pointers device, float32, on the CURRENT device, in nn.Linear layout; the *_grad
- * arrays and loss[0] are OVERWRITTEN (not accumulated).  returns: the normalised discounted returns (:228-232).
+ * arrays and loss[0] are OVERWRITTEN (not accumulated).  returns: the normalised discounted returns (:228-232), or the
+ * raw ones together with returns_stats.
  * workspace: ballenv_a2c_workspace_bytes(n_inputs, hidden, n_samples) bytes of device memory.  The gradients are sums
  * in a fixed order (deterministic); they agree with autograd's to float32 rounding of the summation order.
  * n_inputs: 4 + WINDOW^2 with WINDOW = 5 or 10; hidden: a multiple of 4, at most 256.
@@ -274,6 +275,8 @@ typedef struct BallenvA2CUpdate {
   const float *value_weight, *value_bias;     /* [1][hidden], [1] */
   float *fc1_weight_grad, *fc1_bias_grad, *action_weight_grad, *action_bias_grad, *value_weight_grad, *value_bias_grad;
   float *loss;                                /* [1] */
+  const float *returns_stats;                 /* NULL: `returns` are normalised already; else device [2] = {mean, std + eps}
+                                                 of the raw returns passed: (R - mean) / (std + eps) is formed in the kernel */
 } BallenvA2CUpdate;
 int64_t ballenv_a2c_workspace_bytes(int32_t n_inputs, int32_t hidden, int64_t n_samples);
 int ballenv_a2c_grads(const BallenvA2CUpdate *u, const float *obs /* [n_samples][n_inputs] */,
