@@ -1207,7 +1207,7 @@ int a2c_grid(int n_in, int hidden, int tile, int nw, int64_t n_samples, size_t* 
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int per_sm = (int)((220 * 1024) / (smem + 1024));
-  if (per_sm > 4) per_sm = 4;
+  if (per_sm > 5) per_sm = 5;
   if (per_sm < 1) per_sm = 1;
   int64_t grid = (int64_t)sms * per_sm;
   const int64_t tiles = (n_samples + tile - 1) / tile;
