@@ -313,6 +313,8 @@ int ballenv_observe_blocks(BallenvHandle *h, float *out, ballenv_stream_t stream
  * CURRENT state.  gym ruleset only; width even, <= 128; out_size <= 64.  The resize is Pillow's 8-bit two-pass
  * resampling bit for bit; the frame restates the gym 0.10.9 viewer (pixel centre inside the polygon, no
  * anti-aliasing, coordinates rounded to integers) - parity for that half is unpinned: pyglet / OpenGL cannot run here.
+ * Synchronises `stream` once per new (width, out_size, interp) combination (the resampling tables are built on the host
+ * and uploaded); further calls with the same geometry only enqueue the kernel.
  */
 #define BALLENV_INTERP_BILINEAR 0
 #define BALLENV_INTERP_BICUBIC 1

@@ -309,3 +309,20 @@ def test_graphed_trainer_with_the_fused_update_learns_like_autograd():
     assert np.allclose(la, lb, rtol=1e-3), (la, lb)
     for a, b in zip(pa, pb):
         assert torch.allclose(a, b, rtol=1e-2, atol=1e-4)
+
+
+@pytest.mark.gpu
+def test_a2c_entry_points_reject_bad_arguments():
+    import ctypes as C
+    import torch
+    from gym_ballenv_b200 import _lib as L
+    assert L.LIB.ballenv_a2c_workspace_bytes(29, 130, 100) < 0          # hidden not a multiple of 4
+    assert L.LIB.ballenv_a2c_workspace_bytes(29, 512, 100) < 0          # too wide
+    assert L.LIB.ballenv_a2c_workspace_bytes(29, 128, 100) > 0
+    u = L.BallenvA2CUpdate()
+    u.n_inputs, u.hidden = 29, 128
+    x = torch.zeros(64, device="cuda:0")
+    assert L.LIB.ballenv_a2c_grads(C.byref(u), C.c_void_p(x.data_ptr()), C.c_void_p(x.data_ptr()), C.c_void_p(x.data_ptr()),
+                                   4, C.c_void_p(x.data_ptr()), 256, None) == -1    # NULL parameter pointers
+    assert b"NULL" in L.LIB.ballenv_last_error()
+    assert L.LIB.ballenv_discounted_returns(None, None, None, C.c_float(0.9), 1, 1, None, None) == -1
