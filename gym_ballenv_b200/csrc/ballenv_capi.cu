@@ -334,7 +334,8 @@ LeanLauncher lean_launcher(const BallenvHandle* h, const Params& p, int* lanes =
   // Measured against the block-of-roles kernel at 65 536 environments (tools/rt_rate.py): single-step launches - a pair
   // of lanes, always (13 + 5 counts 10.1 us against 15.0, 8 + 24 counts 18.1 against 22.1); rollouts - one lane per
   // environment while the moving obstacles are few (13 + 5: 4.0 us per step against 5.9), the block of roles from four
-  // moving quads up (8 + 24: 11.1 against 9.1: the lane walks its quads one Philox block at a time).
+  // moving quads up (8 + 24: 11.1 against 9.1: the run-time form's larger shared-memory region leaves five blocks per
+  // SM where the launch needs seven to run in one wave - tools/rt_ncu.sh).
   if ((c.window == 5 || c.window == 10) && c.kd >= 1 && c.ks + c.kd <= kLeanRtMaxObstacles) {
     const int dyn_quads = (c.kd + 3) / 4;
     if (p.n_steps > 1 && dyn_quads >= 4 && !h->lean_g && !h->lean_rt_only) return nullptr;
