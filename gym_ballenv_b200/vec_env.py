@@ -88,9 +88,18 @@ class BallVecEnv:
                            done=torch.empty(n, dtype=torch.uint8, device=self.device)) for _ in range(2)]
         self._flip = 0
         self._tape_refs = None
+        # what step() hands back, built once: a launch of one step is a few microseconds, the Python around it must
+        # not cost more (tools/step_overhead.py) - the buffers' pointers, the bool views of `done`, the info dict
+        self._step_out = [(C.c_void_p(b["obs"].data_ptr()), C.c_void_p(b["reward"].data_ptr()), C.c_void_p(b["done"].data_ptr()),
+                           b["obs"], b["reward"], b["done"].view(torch.bool)) for b in self._bufs]
+        self._info = {"flags": self.state_views["flags"], "state": self.state_views}
+        self._dev_index = self.device.index
+        self._raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
 
     # ------------------------------------------------------------------ plumbing
     def _stream(self):
+        if self._raw_stream is not None:      # the stream's handle without building a torch.cuda.Stream object
+            return C.c_void_p(self._raw_stream(self._dev_index))
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def _views_of(self, arena: torch.Tensor) -> Dict[str, torch.Tensor]:
@@ -211,31 +220,37 @@ class BallVecEnv:
         self._flip ^= 1
         return self._bufs[self._flip]
 
-    @staticmethod
-    def _action_kind(actions: torch.Tensor, n: int):
+    _INDEX_KINDS = {torch.int64: L.ACT_INDEX_I64, torch.int32: L.ACT_INDEX_I32, torch.uint8: L.ACT_INDEX_U8}
+    _XY_KINDS = {torch.float32: L.ACT_XY_F32, torch.float64: L.ACT_XY_F64}
+
+    @classmethod
+    def _action_kind(cls, actions: torch.Tensor, n: int):
         if actions.dim() == 1:
-            kinds = {torch.int64: L.ACT_INDEX_I64, torch.int32: L.ACT_INDEX_I32, torch.uint8: L.ACT_INDEX_U8}
-            if actions.dtype not in kinds or actions.shape[0] != n:
+            kind = cls._INDEX_KINDS.get(actions.dtype)
+            if kind is None or actions.shape[0] != n:
                 raise ValueError("index actions must be int64/int32/uint8 [N]")
-            return kinds[actions.dtype]
+            return kind
         if actions.dim() == 2 and actions.shape == (n, 2):
-            kinds = {torch.float32: L.ACT_XY_F32, torch.float64: L.ACT_XY_F64}
-            if actions.dtype not in kinds:
+            kind = cls._XY_KINDS.get(actions.dtype)
+            if kind is None:
                 raise ValueError("raw actions must be float32/float64 [N, 2]")
-            return kinds[actions.dtype]
+            return kind
         raise ValueError("actions must be [N] indices or [N, 2] raw (dx, dy)")
 
     def step(self, actions: torch.Tensor):
+        """-> (obs, reward, done, info): views of env-owned double buffers, valid until the step after next; ``info`` is
+        the same dict on every call (flags and live state views)."""
         if actions.device != self.device:
             raise ValueError("actions must live on %s" % self.device)
         kind = self._action_kind(actions, self.num_envs)
-        actions = actions.contiguous()
-        buf = self._next_buf()
-        check(LIB.ballenv_step(self._h, C.c_void_p(actions.data_ptr()), kind, C.c_void_p(buf["obs"].data_ptr()),
-                               C.c_void_p(buf["reward"].data_ptr()), C.c_void_p(buf["done"].data_ptr()),
-                               self._stream()))
-        info = {"flags": self.state_views["flags"], "state": self.state_views}
-        return buf["obs"], buf["reward"], buf["done"].view(torch.bool), info
+        if not actions.is_contiguous():
+            actions = actions.contiguous()
+        self._flip ^= 1
+        p_obs, p_rew, p_done, obs, reward, done = self._step_out[self._flip]
+        rc = LIB.ballenv_step(self._h, actions.data_ptr(), kind, p_obs, p_rew, p_done, self._stream())
+        if rc < 0:
+            check(rc)
+        return obs, reward, done, self._info
 
     def step_into(self, actions: torch.Tensor, obs_out: torch.Tensor, reward_out: torch.Tensor, done_out: torch.Tensor):
         """step() writing into caller-owned device tensors (obs [N, row], reward [N], done [N] uint8): fixed
