@@ -326,3 +326,36 @@ def test_a2c_entry_points_reject_bad_arguments():
                                    4, C.c_void_p(x.data_ptr()), 256, None) == -1    # NULL parameter pointers
     assert b"NULL" in L.LIB.ballenv_last_error()
     assert L.LIB.ballenv_discounted_returns(None, None, None, C.c_float(0.9), 1, 1, None, None) == -1
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,T", [(1, 1), (1, 7), (63, 2), (65, 1)])
+def test_fused_rollout_and_update_at_tiny_sizes(n, T):
+    """One environment, one step, ragged warps: the fused rollout against the rollout kernel, the fused update against
+    autograd."""
+    from gym_ballenv_b200.a2c import FusedRollout, FusedUpdate, a2c_loss, normalised_returns
+    env, torch = _make(n)
+    twin, _ = _make(n)
+    env.reset()
+    twin.reset()
+    pol = _policy(torch)
+    roll = FusedRollout(env, pol, T)
+    raw = roll.run()
+    o2, r2, d2 = twin.step_many(raw["action"], keep_all_obs=True)
+    assert torch.equal(o2, raw["obs"][1:]) and torch.equal(r2, raw["reward"]) and torch.equal(d2, raw["done"])
+    if n * T > 1:      # (the normalisation needs two samples)
+        with torch.no_grad():
+            _, v_last = pol(raw["obs"][T])
+        loss = a2c_loss(roll.evaluate(raw), 0.99, bootstrap=v_last.squeeze(-1))
+        pol.zero_grad(set_to_none=True)
+        loss.backward()
+        want = [p.grad.detach().clone() for p in pol.parameters()]
+        pol.zero_grad(set_to_none=True)
+        upd = FusedUpdate(pol, T * n)
+        got = upd.grads(raw["obs"][:T], raw["action"],
+                        normalised_returns(raw["reward"], roll.done, 0.99, bootstrap=v_last.squeeze(-1)))
+        assert torch.allclose(got, loss.detach(), rtol=1e-4, atol=1e-5)
+        for p, w in zip(pol.parameters(), want):
+            assert float((p.grad - w).abs().max()) <= 2e-4 * max(float(w.abs().max()), 1e-3)
+    env.close()
+    twin.close()
