@@ -15,7 +15,8 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from gym_ballenv_b200 import BallVecEnv, EnvConfig          # noqa: E402
-from gym_ballenv_b200.a2c import Policy, train, train_graphed   # noqa: E402
+from gym_ballenv_b200 import BallenvError                   # noqa: E402
+from gym_ballenv_b200.a2c import GraphedTrainer, Policy, train, train_graphed   # noqa: E402
 
 
 def read_arguments():
@@ -39,6 +40,9 @@ def read_arguments():
     p.add_argument('--steps', type=int, default=32, help='steps per update')
     p.add_argument('--iterations', type=int, default=50)
     p.add_argument('--graph', type=int, default=1, help='replay the rollout as one CUDA graph')
+    p.add_argument('--fused', type=int, default=1,
+                   help='policy inside the rollout kernel + hand-written update, the iteration as one CUDA graph '
+                        '(configurations with a policy kernel: WINDOW 5 / 10, 13 + 5 or 8 + 24 obstacles)')
     return p.parse_args()
 
 
@@ -63,7 +67,20 @@ def main():
                   (it, float(loss.detach()), float(batch["reward"].mean()), st["episodes"], st["goals"],
                    st["hits_static"] + st["hits_dynamic"], time.time() - t0))
 
-    if args.graph:
+    trainer = None
+    if args.fused:
+        try:
+            env.reset()
+            trainer = GraphedTrainer(env, policy, n_steps=args.steps, gamma=args.gamma)
+            trainer.step()      # warm-up (three eager iterations) + capture
+        except BallenvError as e:
+            print("no policy-in-the-loop kernel for this configuration (%s): per-step torch policy instead" % e)
+            trainer = None
+    if trainer is not None:
+        for it in range(args.iterations):
+            loss = trainer.step()
+            log(it, loss, {"reward": trainer.roll.reward})
+    elif args.graph:
         train_graphed(env, policy, args.iterations, n_steps=args.steps, gamma=args.gamma, log=log)
     else:
         train(env, policy, args.iterations, n_steps=args.steps, gamma=args.gamma, log=log)
