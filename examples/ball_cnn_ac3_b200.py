@@ -42,7 +42,7 @@ def read_arguments():
     p.add_argument('--graph', type=int, default=1, help='replay the rollout as one CUDA graph')
     p.add_argument('--fused', type=int, default=1,
                    help='policy inside the rollout kernel + hand-written update, the iteration as one CUDA graph '
-                        '(configurations with a policy kernel: WINDOW 5 / 10, 13 + 5 or 8 + 24 obstacles)')
+                        '(configurations with a policy kernel: WINDOW 5 / 10, up to 64 obstacles)')
     return p.parse_args()
 
 

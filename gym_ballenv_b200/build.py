@@ -58,7 +58,8 @@ def _sources():
             name = "launch_lean_w%d_rt_g%d" % (w, g)
             jobs.append((os.path.join(CSRC, "ballenv_lean_rt_inst.cu"), os.path.join(OBJ, name + ".o"),
                          ["-DBALLENV_W=%d" % w, "-DBALLENV_KS=-1", "-DBALLENV_KD=-1", "-DBALLENV_G=%d" % g,
-                          "-DBALLENV_NAME=" + name, "-DBALLENV_SMEM_NAME=lean_rt_smem_w%d_g%d" % (w, g)]))
+                          "-DBALLENV_NAME=" + name, "-DBALLENV_SMEM_NAME=lean_rt_smem_w%d_g%d" % (w, g),
+                          "-DBALLENV_POLICY_NAME=" + name.replace("launch_lean_", "launch_lean_policy_")]))
     return deps, jobs
 
 

@@ -45,6 +45,10 @@ void launch_lean_w5_rt_g1(const Params&, unsigned, cudaStream_t);
 void launch_lean_w5_rt_g2(const Params&, unsigned, cudaStream_t);
 void launch_lean_w10_rt_g1(const Params&, unsigned, cudaStream_t);
 void launch_lean_w10_rt_g2(const Params&, unsigned, cudaStream_t);
+void launch_lean_policy_w5_rt_g1(const Params&, unsigned, cudaStream_t);
+void launch_lean_policy_w5_rt_g2(const Params&, unsigned, cudaStream_t);
+void launch_lean_policy_w10_rt_g1(const Params&, unsigned, cudaStream_t);
+void launch_lean_policy_w10_rt_g2(const Params&, unsigned, cudaStream_t);
 size_t lean_rt_smem_w5_g1(int ks, int kd);
 size_t lean_rt_smem_w5_g2(int ks, int kd);
 size_t lean_rt_smem_w10_g1(int ks, int kd);
@@ -351,10 +355,13 @@ LeanLauncher lean_launcher(const BallenvHandle* h, const Params& p, int* lanes =
   return nullptr;
 }
 
-// the lean kernel with the policy in its loop for this configuration, or nullptr
+// the lean kernel with the policy in its loop for this configuration, or nullptr: a tuned instance, else the
+// run-time-count form (any counts up to 64 obstacles) when its regions and the policy fit shared memory together
 LeanLauncher policy_launcher(const BallenvHandle* h, const Params& p, int* lanes = nullptr) {
-  int g = 0;
-  if (lean_launcher(h, p, &g) == nullptr || p.cfg.obs_format != BALLENV_OBS_F32) return nullptr;
+  if (!fast_eligible(h, p, true) || h->no_lean || p.lean_tab == nullptr || p.cfg.obs_format != BALLENV_OBS_F32) return nullptr;
+  const DevConfig& c = p.cfg;
+  if (c.change_step > 254 || c.n_goals < 2 || c.step_x != 1.0 || c.step_y != 1.0 || c.radius_sum != 25.0) return nullptr;
+  if (c.margin != (double)(25 + c.window / 2 + 2)) return nullptr;
   struct Inst { int w, ks, kd; LeanLauncher g1, g2; };
   static const Inst kInst[] = {{5, 13, 5, launch_lean_policy_w5_s13_d5_g1, launch_lean_policy_w5_s13_d5_g2},
                                {10, 13, 5, launch_lean_policy_w10_s13_d5_g1, launch_lean_policy_w10_s13_d5_g2},
@@ -362,10 +369,19 @@ LeanLauncher policy_launcher(const BallenvHandle* h, const Params& p, int* lanes
                                {5, 8, 24, launch_lean_policy_w5_s8_d24_g1, launch_lean_policy_w5_s8_d24_g2}};
   // a pair of lanes per environment unless told otherwise: the pair also splits the hidden units of the policy, the
   // longest dependent chain of a step
-  g = h->lean_g ? h->lean_g : 2;
+  const int g = h->lean_g ? h->lean_g : 2;
   if (lanes != nullptr) *lanes = g;
-  for (const Inst& i : kInst)
-    if (i.w == p.cfg.window && i.ks == p.cfg.ks && i.kd == p.cfg.kd) return g == 2 ? i.g2 : i.g1;
+  if (!h->lean_rt_only)
+    for (const Inst& i : kInst)
+      if (i.w == c.window && i.ks == c.ks && i.kd == c.kd) return g == 2 ? i.g2 : i.g1;
+  if ((c.window == 5 || c.window == 10) && c.kd >= 1 && c.ks + c.kd <= kLeanRtMaxObstacles) {
+    const size_t regions = c.window == 5 ? (g == 2 ? lean_rt_smem_w5_g2(c.ks, c.kd) : lean_rt_smem_w5_g1(c.ks, c.kd))
+                                         : (g == 2 ? lean_rt_smem_w10_g2(c.ks, c.kd) : lean_rt_smem_w10_g1(c.ks, c.kd));
+    if (regions + 4 * lean::policy_smem_floats(4 + c.window * c.window, p.pol_hidden) + 4096 <= 220 * 1024) {
+      if (c.window == 5) return g == 2 ? launch_lean_policy_w5_rt_g2 : launch_lean_policy_w5_rt_g1;
+      return g == 2 ? launch_lean_policy_w10_rt_g2 : launch_lean_policy_w10_rt_g1;
+    }
+  }
   return nullptr;
 }
 
@@ -918,7 +934,8 @@ int ballenv_rollout_policy(BallenvHandle* h, const BallenvPolicyMLP* pol, int32_
   LeanLauncher fn = policy_launcher(h, p);
   if (fn == nullptr)
     return fail(BALLENV_ESTATE, "no policy-in-the-loop kernel for this configuration (production mode, float32 rows, WINDOW 5 "
-                                "or 10, 13 + 5 or 8 + 24 obstacles): drive ballenv_step from the caller's policy instead");
+                                "or 10, at most 64 obstacles with at least one moving): drive ballenv_step from the caller's "
+                                "policy instead");
   if (4 * lean::policy_smem_floats(n_in, pol->hidden) > 160 * 1024) return fail(BALLENV_EINVAL, "the policy does not fit in shared memory");
   const size_t n = (size_t)h->n;
   const size_t rew_b = 4;

@@ -702,7 +702,6 @@ __global__ void __launch_bounds__(kLeanEnvsPerBlock * G, kPolicy ? 4 : kLeanMinB
   constexpr int kRegQuads = kRt ? 1 : (Sh::NDQ > 0 ? Sh::NDQ : 1);   // quads whose goal / counter bytes and draws live in registers
   static_assert(W > 1 && W <= 16, "instantiated for windows up to 16");
   static_assert(kRt || (KS > 0 && KD > 0), "the fixed instances have both kinds of obstacles");
-  static_assert(!(kRt && kPolicy), "the policy in the loop comes with the fixed instances");
   // single-step launches hand the moved rows to the copy engine right after the moves when there is enough of them to
   // matter (measured: 24 moving obstacles 12.7 -> 12.2 us per launch; 5 moving obstacles 7.95 -> 8.3 us, so not there)
   constexpr bool kEarlyStore = !kRollout && LEAN_EARLY_STORE != 0 && !kRt && KD >= 16;
@@ -759,7 +758,9 @@ __global__ void __launch_bounds__(kLeanEnvsPerBlock * G, kPolicy ? 4 : kLeanMinB
   grid_dependency_wait();
   LEAN_STAMP(2);
   // ---- (policy in the loop) the block's copy of the weights - after the wait: the previous kernel may be the optimiser
-  float* const pol_sm = reinterpret_cast<float*>(lean_dyn);
+  // (the block's copy of the policy lies behind the warps' regions when the counts are read at run time)
+  float* const pol_sm = reinterpret_cast<float*>(
+      lean_dyn + (kRt ? (size_t)(kLeanThreads / 32) * (size_t)LeanMem<W, KS, KD, G>::bytes(cfg.ks, cfg.kd) : (size_t)0));
   if constexpr (kPolicy) {
     const int H = p.pol_hidden, HS = H + 4;
     float* const w1t = pol_sm;

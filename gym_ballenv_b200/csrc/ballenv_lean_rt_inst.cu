@@ -23,8 +23,9 @@ static void launch_lean(const Params& p, unsigned grid, cudaStream_t s) {
   // dynamic shared memory: (policy in the loop) the block's copy of the weights; (run-time obstacle counts) the warps'
   // regions, sized by the configuration
 #if BALLENV_KS < 0
-  const size_t dyn = (size_t)LeanMem<BALLENV_W, BALLENV_KS, BALLENV_KD, BALLENV_G>::bytes(p.cfg.ks, p.cfg.kd) * kWarps;
-  const int dyn_max = 200 * 1024;
+  const size_t dyn = (size_t)LeanMem<BALLENV_W, BALLENV_KS, BALLENV_KD, BALLENV_G>::bytes(p.cfg.ks, p.cfg.kd) * kWarps +
+                     (kPolicy ? 4 * lean::policy_smem_floats(4 + BALLENV_W * BALLENV_W, p.pol_hidden) : 0);
+  const int dyn_max = 220 * 1024;
 #else
   const size_t dyn = kPolicy ? 4 * lean::policy_smem_floats(4 + BALLENV_W * BALLENV_W, p.pol_hidden) : 0;
   const int dyn_max = kPolicy ? 192 * 1024 - (int)sizeof(LeanWarp<BALLENV_W, BALLENV_KS, BALLENV_KD, BALLENV_G>) * kWarps : 0;

@@ -271,7 +271,7 @@ class BallVecEnv:
         (ballenv_rollout_policy).  ``policy``: a module with ``fc1`` / ``action_head`` Linear layers (a2c.Policy; the
         value head is not needed to act).  first_obs [N, row] float32: the current observation; obs_out [T, N, row],
         actions_out [T, N] int64, reward_out [T, N] float32, done_out [T, N] uint8 are written.  Raises BallenvError
-        for configurations without such a kernel (WINDOW other than 5, other obstacle counts, parity mode)."""
+        for configurations without such a kernel (WINDOW other than 5 / 10, more than 64 obstacles, parity mode)."""
         n, row, dev = self.num_envs, self.obs_row, self.device
         w1, b1 = policy.fc1.weight, policy.fc1.bias
         w2, b2 = policy.action_head.weight, policy.action_head.bias

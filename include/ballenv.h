@@ -228,10 +228,10 @@ int ballenv_step_many(BallenvHandle *h, const void *actions, int action_kind, in
  * Sampling: word x of Philox4x32-10(counter = {global env id, tick, 0, stream 3}, key = seed), u = (word >> 8) 2^-24,
  * action = first j with u * sum(e) < e_0 + .. + e_j, e = exp(logit - max): Categorical by inverse CDF, reproducible and
  * independent of the sharding; greedy != 0 takes the first maximum instead.
- * Production configuration only (BALLENV_F32, gym ruleset, Philox draws, BALLENV_OBS_F32 rows) with WINDOW = 5 or 10
- * and 13 + 5 or 8 + 24 obstacles - the lean kernels' instances; BALLENV_ESTATE otherwise (step from the caller's
- * policy with ballenv_step).  The block's copy of the weights must fit shared memory (160 KB: hidden = 208 for
- * WINDOW = 10 takes 99 KB).
+ * Production configuration only (BALLENV_F32, gym ruleset, Philox draws, BALLENV_OBS_F32 rows) with WINDOW = 5 or 10:
+ * the tuned instances (13 + 5, 8 + 24 obstacles) or the run-time-count form (any counts up to 64 obstacles, at least
+ * one moving); BALLENV_ESTATE otherwise (step from the caller's policy with ballenv_step).  The block's copy of the
+ * weights must fit shared memory (160 KB: hidden = 208 for WINDOW = 10 takes 99 KB).
  */
 typedef struct BallenvPolicyMLP {
   int32_t n_inputs;            /* 4 + WINDOW^2 */

@@ -359,3 +359,39 @@ def test_fused_rollout_and_update_at_tiny_sizes(n, T):
             assert float((p.grad - w).abs().max()) <= 2e-4 * max(float(w.abs().max()), 1e-3)
     env.close()
     twin.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("window,ks,kd,lanes", [(5, 10, 7, 2), (10, 3, 2, 1), (5, 20, 30, 2), (5, 0, 1, 2)])
+def test_fused_rollout_with_run_time_obstacle_counts(window, ks, kd, lanes, monkeypatch):
+    """Configurations without a tuned instance: the policy in the loop of the run-time-count kernels - the environment
+    side against ballenv_step_many on a twin, greedy actions against torch's argmax."""
+    import torch
+    from gym_ballenv_b200 import BallVecEnv, EnvConfig
+    goals = ["%d,%d" % (30 + (53 * i) % 440, 25 + (97 * i) % 450) for i in range(max(kd, 2) + 1)]
+    cfg = EnvConfig(static_obstacles=ks, dynamic_obstacles=kd, obstacle_speed=[1 + (j % 2) for j in range(kd)],
+                    obs_goal_position=goals, time_step_for_change=9)
+    n, T = 700, 40
+    monkeypatch.setenv("BALLENV_LEAN_G", str(lanes))
+    env = BallVecEnv(n, window=window, config=cfg, seed=SEED, device="cuda:0", max_episode_steps=21)
+    monkeypatch.delenv("BALLENV_LEAN_G")
+    twin = BallVecEnv(n, window=window, config=cfg, seed=SEED, device="cuda:0", max_episode_steps=21)
+    env.reset()
+    twin.reset()
+    pol = _policy(torch, window=window, scale=2.0)
+    for greedy in (False, True):
+        first, obs, act, rew, done = _fused(env, torch, pol, T, greedy=greedy)
+        o2, r2, d2 = twin.step_many(act, keep_all_obs=True)
+        assert torch.equal(o2, obs) and torch.equal(r2, rew) and torch.equal(d2.to(torch.uint8), done)
+        if greedy:
+            seen = torch.cat([first.unsqueeze(0), obs[:-1]], 0)
+            with torch.no_grad():
+                probs, _ = pol(seen.reshape(T * n, -1))
+            top2 = probs.topk(2, -1).values
+            assert bool(((probs.argmax(-1) == act.reshape(-1)) | ((top2[:, 0] - top2[:, 1]) < 1e-5)).all())
+    sa, sb = env.get_state(), twin.get_state()
+    for k in sa:
+        assert torch.equal(sa[k], sb[k]), k
+    assert int(done.sum()) > 0
+    env.close()
+    twin.close()
