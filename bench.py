@@ -564,6 +564,17 @@ def run_gpu(args, spec):
                      "hbm_bytes_per_env_step_moved": moved_bytes_per_env_step(sp2, chunk)}
         secondary.update(kernel_facts(env2, sp2, chunk))
         env2.close()
+        if args.closed_loop_steps > 0:      # the same configuration with one launch per env-step
+            os.environ["BALLENV_NO_ROLLOUT"] = "1"
+            env2c = make_env(sp2)
+            os.environ["BALLENV_NO_ROLLOUT"] = "0"
+            cs2 = args.closed_loop_steps
+            mc2 = measure(env2c, torch, sp2, n, cs2, 3, chunk, dist, world)
+            secondary["closed_loop"] = {"value": float(world) * n * chunk * cs2 / (mc2["ms"] * 1e-3), "unit": UNIT,
+                                        "avg_launch_us": mc2["ms"] * 1e3 / (cs2 * chunk),
+                                        "best_of_5_launch_us": mc2["best_launch_us"] / chunk,
+                                        "kernel": kernel_facts(env2c, sp2, 1)["kernel"]}
+            env2c.close()
 
     # BASELINE.json config 4: 2^20 environments over the job's GPUs (W=5, reference defaults), stats all-reduced
     c4 = None
