@@ -297,7 +297,14 @@ def reduced_stats(env, torch, dist, world):
         parts = [torch.empty_like(local) for _ in range(world)]
         dist.all_gather(parts, local)
         ref = torch.stack(parts).sum(0)
-        check["ok"] = bool(torch.equal(ref, total))
+        # counters are integers held in doubles: exact whatever the order of the additions; the return sum is a sum of
+        # fractions, and NCCL's reduction order is not the all-gather's: equal to rounding (seen differing in the last
+        # bit on 4 ranks, not on 2 or 8)
+        exact = torch.ones_like(ref, dtype=torch.bool)
+        exact[STAT_NAMES.index("return_sum")] = False
+        check["ok"] = bool(torch.equal(ref[exact], total[exact]) and
+                           torch.allclose(ref[~exact], total[~exact], rtol=1e-12, atol=0.0))
+        check["max_rel_diff"] = float(((ref - total).abs() / ref.abs().clamp_min(1e-300)).max())
         check["episodes_per_rank"] = [float(p_[0]) for p_ in parts]
     vec = total.cpu().tolist()
     return {name: vec[i] for i, name in enumerate(STAT_NAMES)}, check
