@@ -429,6 +429,33 @@ def measure_c5(torch, dev, iterations=12, n_steps=32, n=16384):
         torch_iteration()
     ms_torch, _ = timed(torch_iteration, max(4, iterations // 2))
     env.close()
+
+    # the same loop at the headline size (65 536 environments), and the pixel policies' observation (rgb patches)
+    torch.manual_seed(0)
+    n_big = 65536
+    env = BallVecEnv(n_big, window=5, seed=0, device=dev)
+    policy_big = Policy(5).to(dev)
+    env.reset()
+    trainer_big = GraphedTrainer(env, policy_big, n_steps)
+    trainer_big.step()
+    trainer_big.step()
+    ms_big, _ = timed(trainer_big.step, iterations)
+    roll_big = FusedRollout(env, policy_big, n_steps)
+    roll_big.run()
+    ms_roll_big, _ = timed(roll_big.run, iterations)
+    errs |= env.error_flags()
+    env.close()
+    env = BallVecEnv(n, window=5, seed=0, device=dev)
+    env.reset()
+    env.step_many(torch.randint(0, 9, (100, n), device=dev))
+    patches = env.rgb_patches()
+    ms_patch, _ = timed(lambda: env.rgb_patches(out=patches), 10)
+    errs |= env.error_flags()
+    env.close()
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0))
+    except Exception:
+        peak = 6650.0
     return {"workload": "config 5: 16384 envs, WINDOW=5, reference defaults (13 + 5 obstacles), Policy(5) MLP 29-128-{9,1} in "
                         "the loop (Categorical by inverse CDF of the env's Philox stream), %d-step rollouts in ONE launch "
                         "(ballenv_rollout_policy), batched finish_episode (loss + gradients by ballenv_a2c_grads) + Adam per "
@@ -441,6 +468,11 @@ def measure_c5(torch, dev, iterations=12, n_steps=32, n=16384):
             "torch_policy_per_step": {"value": n * n_steps / (ms_torch * 1e-3), "unit": UNIT, "ms_per_iteration": ms_torch,
                                       "what": "GraphedRollout: torch Policy forward + multinomial + ballenv_step per env-step "
                                               "(one CUDA graph per rollout), same update issued eagerly"},
+            "at_65536_envs": {"value": n_big * n_steps / (ms_big * 1e-3), "unit": UNIT, "ms_per_iteration": ms_big,
+                              "rollout_only": n_big * n_steps / (ms_roll_big * 1e-3), "ms_per_rollout": ms_roll_big},
+            "rgb_patches": {"value": n / (ms_patch * 1e-3), "unit": "patches/s", "us_per_launch": ms_patch * 1e3,
+                            "what": "ballenv_observe_patches: float32 [16384, 3, 40, 40] (extract_patch of the pixel policies)",
+                            "hbm_frac_on_written_bytes": patches.numel() * 4 / (ms_patch * 1e-3) / 1e9 / peak},
             "env_kernel": "ballenv_lean_kernel<5,13,5,lanes=2,rollout,policy>",
             "gpu_launches_per_iteration": 4, "iterations": iterations,
             "loss_finite": bool(torch.isfinite(loss).item()), "device_error_flags": errs}
