@@ -10,7 +10,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BALLENV_LIB_PATH") or os.path.join(HERE, "libballenv_b200.so")   # override: A/B experiments
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 MAX_DYNAMIC = 64
 MAX_GOALS = 64
 MAX_STATIC = 1024
@@ -56,7 +56,7 @@ class BallenvPolicyMLP(C.Structure):
     """include/ballenv.h: BallenvPolicyMLP (ballenv_rollout_policy)."""
     _fields_ = [("n_inputs", C.c_int32), ("hidden", C.c_int32), ("greedy", C.c_int32), ("reserved", C.c_int32),
                 ("fc1_weight", C.c_void_p), ("fc1_bias", C.c_void_p), ("action_weight", C.c_void_p),
-                ("action_bias", C.c_void_p)]
+                ("action_bias", C.c_void_p), ("value_weight", C.c_void_p), ("value_bias", C.c_void_p)]
 
 
 class BallenvA2CUpdate(C.Structure):
@@ -64,7 +64,7 @@ class BallenvA2CUpdate(C.Structure):
     _fields_ = [("n_inputs", C.c_int32), ("hidden", C.c_int32)] + [
         (n, C.c_void_p) for n in ("fc1_weight", "fc1_bias", "action_weight", "action_bias", "value_weight", "value_bias",
                                   "fc1_weight_grad", "fc1_bias_grad", "action_weight_grad", "action_bias_grad",
-                                  "value_weight_grad", "value_bias_grad", "loss", "returns_stats")]
+                                  "value_weight_grad", "value_bias_grad", "loss", "returns_stats", "policy_out")]
 
 
 EXPORTS = (
@@ -97,7 +97,7 @@ def _bind(lib):
     lib.ballenv_observe_features.argtypes = [vp, vp, vp]
     lib.ballenv_observe_blocks.argtypes = [vp, vp, vp]
     lib.ballenv_observe_patches.argtypes = [vp, vp, i32, i32, i32, i32, vp]
-    lib.ballenv_rollout_policy.argtypes = [vp, C.POINTER(BallenvPolicyMLP), i32, vp, vp, vp, vp, vp, vp]
+    lib.ballenv_rollout_policy.argtypes = [vp, C.POINTER(BallenvPolicyMLP), i32, vp, vp, vp, vp, vp, vp, vp]
     lib.ballenv_discounted_returns.argtypes = [vp, vp, vp, C.c_float, i32, i64, vp, vp]
     lib.ballenv_a2c_workspace_bytes.argtypes = [i32, i32, i64]
     lib.ballenv_a2c_workspace_bytes.restype = i64

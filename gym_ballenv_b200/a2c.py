@@ -163,7 +163,14 @@ class FusedRollout(GraphedRollout):
     """The T-step policy-in-the-loop rollout as ONE KERNEL LAUNCH (``BallVecEnv.rollout_policy``): the environments'
     own lanes evaluate the MLP and draw the action between two steps, so nothing but observations, actions, rewards
     and dones touches device memory inside the loop.  Same buffers and ``evaluate`` as GraphedRollout; actions are
-    drawn from the env's Philox stream (inverse CDF of the same softmax) instead of ``torch.multinomial``."""
+    drawn from the env's Philox stream (inverse CDF of the same softmax) instead of ``torch.multinomial``.
+    ``keep_policy_out``: also keep the action probabilities and the value of every step's forward pass
+    (``policy_out`` [T, N, 10]) - with unchanged weights exactly what an update would recompute (FusedUpdate takes it)."""
+
+    def __init__(self, env: BallVecEnv, policy: Policy, n_steps: int, greedy: bool = False, keep_policy_out: bool = False):
+        super().__init__(env, policy, n_steps, greedy)
+        self.policy_out = (torch.zeros((n_steps, env.num_envs, 10), dtype=torch.float32, device=env.device)
+                           if keep_policy_out else None)
 
     @torch.no_grad()
     def run(self, first_obs: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
@@ -172,8 +179,11 @@ class FusedRollout(GraphedRollout):
         self.graph = True      # (no graph to capture: marks that obs[n_steps] holds the last observation)
         self.obs[0].copy_(first_obs)
         self.env.rollout_policy(self.policy, self.n_steps, self.obs[0], self.obs[1:], self.action, self.reward, self.done,
-                                greedy=self.greedy)
-        return dict(obs=self.obs, action=self.action, reward=self.reward, done=self.done.bool())
+                                greedy=self.greedy, policy_out=self.policy_out)
+        out = dict(obs=self.obs, action=self.action, reward=self.reward, done=self.done.bool())
+        if self.policy_out is not None:
+            out["policy_out"] = self.policy_out
+        return out
 
 
 def train_fused(env: BallVecEnv, policy: Policy, iterations: int, n_steps: int = 32, gamma: float = 0.99,
@@ -209,15 +219,23 @@ class FusedUpdate:
         self.loss = torch.zeros(1, dtype=torch.float32, device=self.device)
         self.stats = torch.zeros(2, dtype=torch.float32, device=self.device)     # {mean, std + eps} of raw returns
         self._u = L.BallenvA2CUpdate(n_in, hidden, *[q.data_ptr() for q in ps], *[q.grad.data_ptr() for q in ps],
-                                     self.loss.data_ptr(), None)
+                                     self.loss.data_ptr(), None, None)
         self._C, self._L = C, L
 
-    def grads(self, obs: torch.Tensor, action: torch.Tensor, returns: torch.Tensor, normalise: bool = False) -> torch.Tensor:
+    def grads(self, obs: torch.Tensor, action: torch.Tensor, returns: torch.Tensor, normalise: bool = False,
+              policy_out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """obs [S, row] float32, action [S] int64, returns [S] float32 -> loss (device scalar view); the parameters'
         ``.grad`` hold d loss / d parameter afterwards.  ``returns`` are the normalised returns, or with
         ``normalise=True`` the raw discounted ones: their mean and unbiased std + eps are taken here (one reduction) and
-        the kernel forms (R - mean) / (std + eps) itself (examples/ball_cnn_ac3.py:231-232)."""
+        the kernel forms (R - mean) / (std + eps) itself (examples/ball_cnn_ac3.py:231-232).  ``policy_out`` [S, 10]
+        (FusedRollout's, taken with the SAME weights): the probabilities and values are read instead of recomputed."""
         C, L = self._C, self._L
+        if policy_out is not None:
+            if not (policy_out.is_contiguous() and policy_out.dtype == torch.float32 and policy_out.numel() == self.n_samples * 10):
+                raise ValueError("policy_out must be contiguous float32 [S, 10]")
+            self._u.policy_out = policy_out.data_ptr()
+        else:
+            self._u.policy_out = None
         if normalise:
             var, mean = torch.var_mean(returns.reshape(-1))
             self.stats[0] = mean
@@ -261,7 +279,7 @@ class GraphedTrainer:
         self.env, self.policy, self.n_steps, self.gamma = env, policy, n_steps, gamma
         # (fused: the whole Adam step of the six tensors is one kernel)
         self.opt = torch.optim.Adam(policy.parameters(), lr=lr, capturable=True, fused=bool(fused_update))
-        self.roll = FusedRollout(env, policy, n_steps)
+        self.roll = FusedRollout(env, policy, n_steps, keep_policy_out=bool(fused_update))
         self.loss = torch.zeros((), dtype=torch.float32, device=env.device)
         self.update = FusedUpdate(policy, n_steps * env.num_envs) if fused_update else None
         self.graph = None
@@ -274,7 +292,8 @@ class GraphedTrainer:
             with torch.no_grad():
                 _, v_last = self.policy(raw["obs"][T])
                 returns = discounted_returns(raw["reward"], self.roll.done, self.gamma, bootstrap=v_last.squeeze(-1))
-                loss = self.update.grads(raw["obs"][:T], raw["action"], returns, normalise=True)
+                loss = self.update.grads(raw["obs"][:T], raw["action"], returns, normalise=True,
+                                         policy_out=raw["policy_out"])
             self.opt.step()
             self.loss.copy_(loss)
             return

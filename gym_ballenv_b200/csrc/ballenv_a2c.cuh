@@ -40,6 +40,7 @@ struct Args {
   const long long* action;    // [S]
   const float* ret;           // [S] returns: normalised already, or raw with ret_stats = {mean, std + eps} on the device
   const float* ret_stats;     // nullptr, or [2]: R = (ret - mean) / (std + eps) is formed here (:231-232)
+  const float* pv;            // nullptr, or [S][10]: probabilities and value of the rollout's own forward pass (same weights)
   float* partial;             // [grid][n_params + 1]
 };
 
@@ -102,8 +103,9 @@ __global__ void __launch_bounds__(kMaxHidden) grad_kernel(const Args a) {
     float acc[kHeads];
 #pragma unroll
     for (int j = 0; j < kHeads; ++j) acc[j] = b2[j];
+    const bool stored = a.pv != nullptr;   // (block-uniform) the rollout kernel kept its softmax and value: no forward pass here
 #pragma unroll 1
-    for (int k0 = 0; k0 < H; k0 += 4) {
+    for (int k0 = 0; k0 < (stored ? 0 : H); k0 += 4) {
       float4 h = *reinterpret_cast<const float4*>(b1 + k0);
 #pragma unroll
       for (int w = 0; w < NW; ++w) {
@@ -136,24 +138,35 @@ __global__ void __launch_bounds__(kMaxHidden) grad_kernel(const Args a) {
       }
     }
     {
-      float mx = acc[0];
+      float mx = 0.0f, e[9], sum = 1.0f;
+      if (stored) {   // the probabilities and the value the rollout kernel computed with these weights
+        const float* const q = a.pv + (size_t)(valid ? s : 0) * 10;
 #pragma unroll
-      for (int j = 1; j < 9; ++j) mx = fmaxf(mx, acc[j]);
-      float e[9], sum = 0.0f;
+        for (int j = 0; j < 9; ++j) e[j] = q[j];
+        acc[9] = q[9];
+      } else {
+        mx = acc[0];
 #pragma unroll
-      for (int j = 0; j < 9; ++j) {
-        e[j] = expf(acc[j] - mx);
-        sum += e[j];
+        for (int j = 1; j < 9; ++j) mx = fmaxf(mx, acc[j]);
+        sum = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 9; ++j) {
+          e[j] = expf(acc[j] - mx);
+          sum += e[j];
+        }
       }
       const int act = valid ? (int)a.action[s] : 0;
       float R = valid ? a.ret[s] : 0.0f;
       if (a.ret_stats != nullptr) R = valid ? __fdiv_rn(__fsub_rn(R, a.ret_stats[0]), a.ret_stats[1]) : 0.0f;
       const float v = acc[9];
       const float adv = R - v;                                  // :234 reward = r - value.item()
-      float la = acc[0];
+      float la = acc[0], pa = e[0];
 #pragma unroll
-      for (int j = 1; j < 9; ++j) la = act == j ? acc[j] : la;
-      const float logp = (la - mx) - logf(sum);
+      for (int j = 1; j < 9; ++j) {
+        la = act == j ? acc[j] : la;
+        pa = act == j ? e[j] : pa;
+      }
+      const float logp = stored ? logf(fmaxf(pa, 1e-38f)) : (la - mx) - logf(sum);   // log(probs[a]), :218
       const float d = v - R, ad = fabsf(d);
       if (valid) loss += -logp * adv + (ad < 1.0f ? 0.5f * d * d : ad - 0.5f);   // :237-239
       const float inv = 1.0f / sum;

@@ -902,7 +902,7 @@ int ballenv_step(BallenvHandle* h, const void* actions, int action_kind, void* o
 }
 
 int ballenv_rollout_policy(BallenvHandle* h, const BallenvPolicyMLP* pol, int32_t n_steps, const float* first_obs,
-                           float* obs_out, int64_t* actions_out, void* reward_out, uint8_t* done_out,
+                           float* obs_out, int64_t* actions_out, void* reward_out, uint8_t* done_out, float* policy_out,
                            ballenv_stream_t stream) {
   if (h == nullptr || pol == nullptr || first_obs == nullptr || obs_out == nullptr || actions_out == nullptr)
     return fail(BALLENV_EINVAL, "NULL argument");
@@ -931,6 +931,10 @@ int ballenv_rollout_policy(BallenvHandle* h, const BallenvPolicyMLP* pol, int32_
   p.pol_act_b = pol->action_bias;
   p.pol_hidden = pol->hidden;
   p.pol_greedy = pol->greedy ? 1 : 0;
+  p.pol_val_w = pol->value_weight;
+  p.pol_val_b = pol->value_bias;
+  if (policy_out != nullptr && (pol->value_weight == nullptr || pol->value_bias == nullptr))
+    return fail(BALLENV_EINVAL, "policy_out needs the value head's weight and bias");
   LeanLauncher fn = policy_launcher(h, p);
   if (fn == nullptr)
     return fail(BALLENV_ESTATE, "no policy-in-the-loop kernel for this configuration (production mode, float32 rows, WINDOW 5 "
@@ -947,6 +951,7 @@ int ballenv_rollout_policy(BallenvHandle* h, const BallenvPolicyMLP* pol, int32_
     p.n_steps = (int)tn;
     p.pol_first_obs = t0 == 0 ? first_obs : obs_out + (size_t)(t0 - 1) * n * n_in;
     p.pol_actions = reinterpret_cast<long long*>(actions_out) + (size_t)t0 * n;
+    p.pol_out = policy_out ? policy_out + (size_t)t0 * n * 10 : nullptr;
     p.obs = obs_out + (size_t)t0 * n * n_in;
     p.reward = reward_out ? (char*)reward_out + (size_t)t0 * n * rew_b : nullptr;
     p.done = done_out ? done_out + (size_t)t0 * n : nullptr;
@@ -1276,6 +1281,7 @@ int ballenv_a2c_grads(const BallenvA2CUpdate* u, const float* obs, const int64_t
   a.action = reinterpret_cast<const long long*>(actions);
   a.ret = returns;
   a.ret_stats = u->returns_stats;
+  a.pv = u->policy_out;
   a.partial = reinterpret_cast<float*>(workspace);
   cudaStream_t s = (cudaStream_t)stream;
   if (nw == 1) {

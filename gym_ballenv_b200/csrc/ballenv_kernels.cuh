@@ -149,6 +149,8 @@ struct Params {
   const float *pol_act_w, *pol_act_b;   // [9][hidden], [9]
   const float* pol_first_obs;           // float32 [n][4 + W*W]
   long long* pol_actions;               // int64 [T][n]
+  const float *pol_val_w, *pol_val_b;   // value head [1][hidden], [1] (only for pol_out), or nullptr
+  float* pol_out;                       // float32 [T][n][10]: the 9 action probabilities and the value each step acted on, or nullptr
   int pol_hidden, pol_greedy;
 };
 

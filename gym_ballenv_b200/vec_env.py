@@ -265,12 +265,15 @@ class BallVecEnv:
                                C.c_void_p(reward_out.data_ptr()), C.c_void_p(done_out.data_ptr()), self._stream()))
 
     def rollout_policy(self, policy, n_steps: int, first_obs: torch.Tensor, obs_out: torch.Tensor,
-                       actions_out: torch.Tensor, reward_out: torch.Tensor, done_out: torch.Tensor, greedy: bool = False):
+                       actions_out: torch.Tensor, reward_out: torch.Tensor, done_out: torch.Tensor, greedy: bool = False,
+                       policy_out: Optional[torch.Tensor] = None):
         """n_steps of the loop of examples/ball_cnn_ac3.py:553-613 - observe, ``Policy`` forward, Categorical sample,
         step - for all environments in ONE launch: the kernel evaluates the MLP itself between two steps
         (ballenv_rollout_policy).  ``policy``: a module with ``fc1`` / ``action_head`` Linear layers (a2c.Policy; the
         value head is not needed to act).  first_obs [N, row] float32: the current observation; obs_out [T, N, row],
-        actions_out [T, N] int64, reward_out [T, N] float32, done_out [T, N] uint8 are written.  Raises BallenvError
+        actions_out [T, N] int64, reward_out [T, N] float32, done_out [T, N] uint8 are written; ``policy_out`` (optional,
+        float32 [T, N, 10]) receives the 9 action probabilities and the value of every forward pass (``policy`` then
+        needs a ``value_head``): what the update would otherwise recompute.  Raises BallenvError
         for configurations without such a kernel (WINDOW other than 5 / 10, more than 64 obstacles, parity mode)."""
         n, row, dev = self.num_envs, self.obs_row, self.device
         w1, b1 = policy.fc1.weight, policy.fc1.bias
@@ -291,9 +294,16 @@ class BallVecEnv:
         pol = L.BallenvPolicyMLP(n_inputs=row, hidden=hidden, greedy=1 if greedy else 0, reserved=0,
                                  fc1_weight=w1.data_ptr(), fc1_bias=b1.data_ptr(), action_weight=w2.data_ptr(),
                                  action_bias=b2.data_ptr())
+        po = None
+        if policy_out is not None:
+            wv, bv = policy.value_head.weight, policy.value_head.bias
+            if not (ok(policy_out, (n_steps, n, 10), torch.float32) and ok(wv, (1, hidden), torch.float32) and ok(bv, (1,), torch.float32)):
+                raise ValueError("policy_out must be a contiguous float32 [T, N, 10] device tensor (and the policy needs a value_head)")
+            pol.value_weight, pol.value_bias = wv.data_ptr(), bv.data_ptr()
+            po = C.c_void_p(policy_out.data_ptr())
         check(LIB.ballenv_rollout_policy(self._h, C.byref(pol), int(n_steps), C.c_void_p(first_obs.data_ptr()),
                                          C.c_void_p(obs_out.data_ptr()), C.c_void_p(actions_out.data_ptr()),
-                                         C.c_void_p(reward_out.data_ptr()), C.c_void_p(done_out.data_ptr()), self._stream()))
+                                         C.c_void_p(reward_out.data_ptr()), C.c_void_p(done_out.data_ptr()), po, self._stream()))
 
     def alloc_rollout(self, T: int, keep_all_obs: bool = False):
         """Rollout buffers for step_many(out=...): (obs [T, N, row] or [N, row], reward [T, N], done [T, N] uint8)."""

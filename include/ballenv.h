@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define BALLENV_ABI_VERSION 4
+#define BALLENV_ABI_VERSION 5
 
 #define BALLENV_MAX_DYNAMIC 64
 #define BALLENV_MAX_GOALS 64
@@ -242,9 +242,14 @@ typedef struct BallenvPolicyMLP {
   const float *fc1_bias;       /* device [hidden] */
   const float *action_weight;  /* device [9][hidden] */
   const float *action_bias;    /* device [9] */
+  const float *value_weight;   /* device [1][hidden], or NULL: only needed for policy_out */
+  const float *value_bias;     /* device [1], or NULL */
 } BallenvPolicyMLP;
+/* policy_out : NULL, or device float32 [n_steps][n][10] - the 9 action probabilities and the value V(s) of the forward
+ *              pass each step acted on: with unchanged weights this is exactly what the update's forward pass would
+ *              recompute (ballenv_a2c_grads takes it as BallenvA2CUpdate.policy_out). */
 int ballenv_rollout_policy(BallenvHandle *h, const BallenvPolicyMLP *policy, int32_t n_steps, const float *first_obs,
-                           float *obs_out, int64_t *actions_out, void *reward_out, uint8_t *done_out,
+                           float *obs_out, int64_t *actions_out, void *reward_out, uint8_t *done_out, float *policy_out,
                            ballenv_stream_t stream);
 
 /*
@@ -277,6 +282,9 @@ typedef struct BallenvA2CUpdate {
   float *loss;                                /* [1] */
   const float *returns_stats;                 /* NULL: `returns` are normalised already; else device [2] = {mean, std + eps}
                                                  of the raw returns passed: (R - mean) / (std + eps) is formed in the kernel */
+  const float *policy_out;                    /* NULL: the forward pass is recomputed from obs; else device [n_samples][10],
+                                                 ballenv_rollout_policy's policy_out of the SAME weights: probabilities and
+                                                 values are read instead (obs is still needed for the backward pass) */
 } BallenvA2CUpdate;
 int64_t ballenv_a2c_workspace_bytes(int32_t n_inputs, int32_t hidden, int64_t n_samples);
 int ballenv_a2c_grads(const BallenvA2CUpdate *u, const float *obs /* [n_samples][n_inputs] */,

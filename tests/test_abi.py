@@ -55,6 +55,9 @@ int main(void) {
          offsetof(BallenvConfig, obstacle_speed), offsetof(BallenvConfig, obs_goal_y), sizeof(BallenvStatePtrs));
   printf("%zu %zu %zu\n", offsetof(BallenvStatePtrs, static_stride), offsetof(BallenvStatePtrs, agent_x),
          offsetof(BallenvStatePtrs, error_flags));
+  printf("%zu %zu %zu %zu %zu %zu\n", sizeof(BallenvPolicyMLP), offsetof(BallenvPolicyMLP, fc1_weight),
+         offsetof(BallenvPolicyMLP, value_bias), sizeof(BallenvA2CUpdate), offsetof(BallenvA2CUpdate, fc1_weight_grad),
+         offsetof(BallenvA2CUpdate, policy_out));
   return 0;
 }''')
     exe = tmp_path / "layout"
@@ -63,8 +66,11 @@ int main(void) {
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
     got = [int(v) for v in out]
     cfg, ptr = L.BallenvConfig, L.BallenvStatePtrs
+    pol, upd = L.BallenvPolicyMLP, L.BallenvA2CUpdate
     want = [C.sizeof(cfg), cfg.static_penalty.offset, cfg.obstacle_speed.offset, cfg.obs_goal_y.offset, C.sizeof(ptr),
-            ptr.static_stride.offset, ptr.agent_x.offset, ptr.error_flags.offset]
+            ptr.static_stride.offset, ptr.agent_x.offset, ptr.error_flags.offset,
+            C.sizeof(pol), pol.fc1_weight.offset, pol.value_bias.offset, C.sizeof(upd), upd.fc1_weight_grad.offset,
+            upd.policy_out.offset]
     assert got == want
 
 

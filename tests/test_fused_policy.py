@@ -395,3 +395,32 @@ def test_fused_rollout_with_run_time_obstacle_counts(window, ks, kd, lanes, monk
     assert int(done.sum()) > 0
     env.close()
     twin.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("window,lanes", [(5, 2), (5, 1), (10, 2)])
+def test_rollout_policy_out_is_the_policys_forward_pass(window, lanes):
+    """policy_out of the fused rollout = the torch policy's probabilities and values on the observations it acted on, and
+    the update fed with it gives the gradients of the update that recomputes the forward pass."""
+    from gym_ballenv_b200.a2c import FusedRollout, FusedUpdate, normalised_returns
+    n, T = 1200, 12
+    env, torch = _make(n, window=window, lanes=lanes)
+    env.reset()
+    pol = _policy(torch, window=window, scale=1.5)
+    roll = FusedRollout(env, pol, T, keep_policy_out=True)
+    raw = roll.run()
+    with torch.no_grad():
+        probs, value = pol(raw["obs"][:T].reshape(T * n, -1))
+        _, v_last = pol(raw["obs"][T])
+    po = raw["policy_out"].reshape(T * n, 10)
+    assert torch.allclose(po[:, :9], probs, rtol=1e-4, atol=1e-6)
+    assert torch.allclose(po[:, 9], value.squeeze(-1), rtol=1e-4, atol=1e-5)
+    returns = normalised_returns(raw["reward"], roll.done, 0.99, bootstrap=v_last.squeeze(-1))
+    upd = FusedUpdate(pol, T * n)
+    l1 = upd.grads(raw["obs"][:T], raw["action"], returns).clone()
+    g1 = [p.grad.clone() for p in pol.parameters()]
+    l2 = upd.grads(raw["obs"][:T], raw["action"], returns, policy_out=raw["policy_out"]).clone()
+    assert torch.allclose(l1, l2, rtol=1e-5)
+    for a, p in zip(g1, pol.parameters()):
+        assert float((a - p.grad).abs().max()) <= 1e-4 * max(float(a.abs().max()), 1e-6)
+    env.close()
