@@ -229,3 +229,24 @@ def test_graphed_training_runs():
     train_graphed(env, policy, iterations=4, n_steps=8, log=lambda it, loss, batch: losses.append(float(loss.detach())))
     assert len(losses) == 4 and all(np.isfinite(losses)) and not torch.equal(before, policy.fc1.weight.detach())
     assert env.stats()["steps"] == 8192 * 8 * 4 and env.error_flags() == 0
+
+
+@pytest.mark.gpu
+def test_hand_written_update_matches_the_references_finish_episode():
+    """The same fixture against ballenv_a2c_grads (a2c.FusedUpdate): the reference's own finish_episode on its recorded
+    24-step episode with the shipped checkpoint - loss and the gradient of every parameter from the hand-written
+    forward + backward kernels, no autograd anywhere."""
+    from gym_ballenv_b200.a2c import FusedUpdate, normalised_returns
+    policy, z, meta = _reference_policy()
+    policy = policy.to("cuda:0")
+    x = torch.from_numpy(z["states"]).to("cuda:0").float().contiguous()
+    actions = torch.from_numpy(z["actions"]).to("cuda:0").long().contiguous()
+    rewards = torch.from_numpy(z["rewards"]).to("cuda:0").float().view(-1, 1)
+    done = torch.zeros_like(rewards, dtype=torch.bool)
+    returns = normalised_returns(rewards, done, meta["gamma"]).view(-1).contiguous()      # :228-232, one episode
+    upd = FusedUpdate(policy, x.shape[0])
+    loss = upd.grads(x, actions, returns)
+    assert float(loss) == pytest.approx(float(z["loss"]), rel=2e-5)
+    for name, prm in policy.named_parameters():
+        ref = z["grad_" + name.replace(".", "_")]
+        np.testing.assert_allclose(prm.grad.cpu().numpy(), ref, rtol=2e-3, atol=2e-5 * float(np.abs(ref).max()))
