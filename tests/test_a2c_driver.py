@@ -110,6 +110,36 @@ def test_shipped_checkpoint_closed_loop_on_the_gpu():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("lanes", [1, 2])
+def test_shipped_checkpoint_in_the_fused_rollout(lanes, monkeypatch):
+    """The same recorded episodes against ONE launch: the shipped checkpoint evaluated inside the rollout kernel
+    (ballenv_rollout_policy, greedy) - the actions, rewards, dones and observations the reference's own network and
+    environment produced, step by step."""
+    from gym_ballenv_b200 import BallVecEnv, EnvConfig
+    from gym_ballenv_b200.a2c import FusedRollout
+    from helpers import load_golden
+    policy, _, _ = _reference_policy()
+    policy = policy.cuda()
+    z, meta = load_golden("rollout_checkpoint")
+    n, T = meta["n_envs"], meta["T"]
+    monkeypatch.setenv("BALLENV_LEAN_G", str(lanes))
+    env = BallVecEnv(n, window=5, config=EnvConfig(), seed=meta["seed"], max_episode_steps=meta["max_episode_steps"],
+                     global_env_offset=meta["g0"])
+    monkeypatch.delenv("BALLENV_LEAN_G")
+    env.reset()
+    raw = FusedRollout(env, policy, T, greedy=True).run()
+    assert np.array_equal(raw["action"].cpu().numpy(), z["rec_actions"][:T])
+    np.testing.assert_allclose(raw["reward"].cpu().numpy(), z["rec_reward"][:T], rtol=1e-5, atol=0)
+    assert np.array_equal(raw["done"].cpu().numpy().astype(np.uint8), np.asarray(z["rec_done"][:T], dtype=np.uint8))
+    o = raw["obs"][1:].cpu().numpy()
+    assert np.array_equal(o[:, :, :4].argmax(2), z["rec_quadrant"][:T])
+    rows = (o[:, :, 4:].reshape(T, n, 5, 5) * (1 << np.arange(5))).sum(-1).astype(np.uint32)
+    assert np.array_equal(rows, z["rec_rows5"][:T])
+    assert env.stats()["episodes"] == meta["stats"]["episodes"] and env.error_flags() == 0
+    env.close()
+
+
+@pytest.mark.gpu
 def test_eager_rollout_gradients_do_not_alias_the_env_buffers():
     """rollout() feeds the policy env-owned observation buffers that the kernel rewrites two steps later; the autograd
     graph must hold its own copies.  The gradients of a rollout's loss equal those recomputed from cloned
