@@ -412,3 +412,38 @@ def test_runtime_count_kernels_against_the_c_oracle():
     assert np.array_equal(st["dynamic_counter"].cpu().numpy().T, ref["dyn_counter"])
     assert env.error_flags() == 0
     env.close()
+
+
+@pytest.mark.parametrize("lanes", [1, 2])
+def test_runtime_count_kernels_with_fractional_speeds(lanes, monkeypatch):
+    """Obstacle speeds 0.5 / 1.25 / 2: the coordinates leave the integers, the exact shortcuts (column-mask table, integer
+    square root) must switch themselves off - the run-time-count kernels against the block-of-roles kernel, bit for bit."""
+    from gym_ballenv_b200 import BallVecEnv, EnvConfig
+    goals = ["%d,%d" % (30 + (53 * i) % 440, 25 + (97 * i) % 450) for i in range(7)]
+    cfg = EnvConfig(static_obstacles=6, dynamic_obstacles=6, obstacle_speed=[0.5, 1.25, 2, 0.5, 1, 1.25],
+                    obs_goal_position=goals, time_step_for_change=11, rd_th_obs=50)
+    n, T = 900, 70
+    monkeypatch.setenv("BALLENV_LEAN_G", str(lanes))
+    lean = BallVecEnv(n, window=10, config=cfg, seed=17, max_episode_steps=29)
+    roll = BallVecEnv(n, window=10, config=cfg, seed=17, max_episode_steps=29)
+    monkeypatch.delenv("BALLENV_LEAN_G")
+    monkeypatch.setenv("BALLENV_NO_LEAN", "1")
+    monkeypatch.setenv("BALLENV_NO_ROLLOUT", "1")
+    ref = BallVecEnv(n, window=10, config=cfg, seed=17, max_episode_steps=29)
+    monkeypatch.delenv("BALLENV_NO_LEAN")
+    monkeypatch.delenv("BALLENV_NO_ROLLOUT")
+    assert lean.kernel_variant(1) == "lean" and ref.kernel_variant(1) != "lean"
+    assert torch.equal(lean.reset(), ref.reset())
+    roll.reset()
+    acts = torch.randint(0, 9, (T, n), generator=torch.Generator().manual_seed(1)).cuda()
+    for t in range(T):
+        ol, rl, dl, _ = lean.step(acts[t])
+        orf, rr, dr, _ = ref.step(acts[t])
+        assert torch.equal(ol, orf) and torch.equal(rl, rr) and torch.equal(dl, dr), t
+    o1, r1, d1 = roll.step_many(acts, keep_all_obs=False)
+    assert torch.equal(o1, orf)
+    _same_state(lean, ref)
+    _same_state(roll, ref)
+    assert float(lean.get_state()["dynamic_x"].frac().abs().max()) > 0      # the coordinates did leave the integers
+    for e in (lean, roll, ref):
+        e.close()
