@@ -127,8 +127,13 @@ def test_shipped_checkpoint_in_the_fused_rollout(lanes, monkeypatch):
                      global_env_offset=meta["g0"])
     monkeypatch.delenv("BALLENV_LEAN_G")
     env.reset()
-    raw = FusedRollout(env, policy, T, greedy=True).run()
+    raw = FusedRollout(env, policy, T, greedy=True, keep_policy_out=(lanes == 2)).run()
     assert np.array_equal(raw["action"].cpu().numpy(), z["rec_actions"][:T])
+    if lanes == 2:      # the probabilities and values it kept are the network's on the observations it acted on
+        with torch.no_grad():
+            probs, value = policy(raw["obs"][:T].reshape(T * n, -1))
+        po = raw["policy_out"].reshape(T * n, 10)
+        assert torch.allclose(po[:, :9], probs, rtol=1e-4, atol=1e-6) and torch.allclose(po[:, 9], value[:, 0], rtol=1e-4, atol=1e-5)
     np.testing.assert_allclose(raw["reward"].cpu().numpy(), z["rec_reward"][:T], rtol=1e-5, atol=0)
     assert np.array_equal(raw["done"].cpu().numpy().astype(np.uint8), np.asarray(z["rec_done"][:T], dtype=np.uint8))
     o = raw["obs"][1:].cpu().numpy()
